@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- Connect4 6x7x4 random-rollout env-steps/sec (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--games G]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (legal-move generation -> uniform action choice -> transition
+-> terminal / reward evaluation, looped to the end of every game) over one batch of 16 Mi synthetic
+games per GPU (BASELINE.json configs[1]); each step uses fresh global game ids.  One env-step = one
+ply of one game.  Rank 0 prints ONE JSON line.
+
+  value      whole-job env-steps/s, device-timed (CUDA events on the launching stream), max over ranks
+  e2e        the same metric through the public API (simulator.batch.HostRollout), per-game results
+             and statistics copied device->host into pinned memory inside the timed region
+  roofline   integer-issue roofline of connect_rollout_kernel (100 thread-level 32-bit
+             integer instructions per env-step against SMs x 128 lanes x f_SM)
+  cpu_baseline  the CPU oracle (a port -- the reference's engine cannot be built here) on all
+             host cores, bounded sample, rank 0 at N=1 only
+
+--impl reference times that CPU path alone (rank 0 only under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PRODUCT = os.path.join(ROOT, "board-game-simulator-python_b200")
+for _p in (ROOT, PRODUCT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+CONFIG = (6, 7, 4)
+GAMES_PER_GPU = 16 * 2**20
+OPS_PER_STEP = 100  # algorithmic thread-level 32-bit integer instructions per env-step
+SM_MAX_MHZ_FALLBACK = 1965.0
+METRIC = "connect4_6x7x4_random_rollout_env_steps_per_sec"
+UNIT = "env-steps/s"
+SEED = 20261018
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_rollout_throughput(budget_s: float, threads: int | None = None, chunk: int = 1 << 15):
+    """Times oracle/bgs_oracle.c (bgso_connect_rollout) on `threads` host threads for ~budget_s.
+
+    ctypes releases the GIL during the call, so plain threads scale across cores."""
+    import numpy as np
+
+    from oracle import binding as o  # the checker, used here only as the timed CPU baseline
+
+    threads = threads or os.cpu_count() or 1
+    o.lib()
+    H, W, K = CONFIG
+    o.connect_rollout(H, W, K, 256, want_actions=False, want_grid=False)  # warm up
+    done = [0] * threads
+    games = [0] * threads
+    t_end = time.perf_counter() + budget_s
+
+    def work(tid):
+        i = 0
+        while time.perf_counter() < t_end:
+            gid0 = (tid * 1_000_003 + i) * chunk
+            res = o.connect_rollout(H, W, K, chunk, gid0=gid0, seed=SEED, want_actions=False, want_grid=False)
+            done[tid] += int(res["stats"][o.STAT_STEPS])
+            games[tid] += chunk
+            i += 1
+
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {
+        "value": sum(done) / dt,
+        "unit": UNIT,
+        "cores": threads,
+        "kind": "port",
+        "sample": f"{sum(games)} games ({sum(done)} env-steps) of the same Connect(6,7,4) workload in {dt:.1f} s "
+                  f"on {threads} threads, oracle/bgs_oracle.c (C, -O2)",
+        "seconds": dt,
+        "steps": sum(done),
+    }
+
+
+def python_api_throughput(n_games: int = 300):
+    """BASELINE.json configs[0]-style loop (README.md:52-69) through the oracle's object API, 1 thread."""
+    import importlib
+    import random
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "pyapi"))
+    saved = {k: v for k, v in sys.modules.items() if k == "simulator" or k.startswith("simulator.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        connect = importlib.import_module("simulator.game.connect")
+        random.seed(0)
+        config = connect.Config(*CONFIG)
+        steps = 0
+        t0 = time.perf_counter()
+        for _ in range(n_games):
+            state = config.sample_initial_state()
+            while not state.has_ended:
+                state = random.choice(state.actions).sample_next_state()
+                steps += 1
+            _ = state.reward
+        dt = time.perf_counter() - t0
+    finally:
+        sys.path.remove(os.path.join(ROOT, "oracle", "pyapi"))
+        for k in [k for k in sys.modules if k == "simulator" or k.startswith("simulator.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return steps / dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = max(1.0, min(15.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_rollout_throughput(min(per_step, 1.0))
+    vals, tot_steps, tot_s = [], 0, 0.0
+    last = None
+    for _ in range(args.steps):
+        last = cpu_rollout_throughput(per_step)
+        vals.append(last["value"])
+        tot_steps += last["steps"]
+        tot_s += last["seconds"]
+    value = tot_steps / tot_s
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": last["cores"], "kind": "port",
+            "sample": f"each step = a {per_step:.0f} s bounded sample of the workload on {last['cores']} host threads; "
+                      "oracle/bgs_oracle.c -- the reference's own engine (jojolebarjos/board-game-simulator@c8f8a07) "
+                      "is not in the reference tree and cannot be built offline",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args):
+    return {
+        "workload": "Connect4 Config(6,7,4) uniform-random rollouts from the empty board to terminal, "
+                    f"{args.games} concurrent games per GPU (BASELINE.json configs[1])",
+        "games_per_gpu": args.games,
+        "global_games_per_step": args.games * args.gpus,
+        "seed": SEED,
+        "outputs_per_game": "length u8 + winner i8 (+ int64[256] statistics per step)",
+        "parallelism": f"{args.gpus} independent game-id shards, one NCCL all-reduce(sum) of the statistics vector per step",
+        "l2": "no resident input (the batch starts from the empty board; inputs are launch scalars); a 256 MiB "
+              "buffer is overwritten between timed steps, outside the per-step CUDA-event pairs",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "nvmlClocksThrottleReasonSwPowerCap": "sw_power_cap",
+            "nvmlClocksThrottleReasonHwSlowdown": "hw_slowdown",
+            "nvmlClocksThrottleReasonSwThermalSlowdown": "sw_thermal_slowdown",
+            "nvmlClocksThrottleReasonHwThermalSlowdown": "hw_thermal_slowdown",
+            "nvmlClocksThrottleReasonHwPowerBrakeSlowdown": "hw_power_brake_slowdown",
+        }
+        bits = {getattr(nv, k): v for k, v in names.items() if hasattr(nv, k)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        med = statistics.median(self.samples) if self.samples else None
+        return {
+            "sm_mhz": med, "sm_max_mhz": self.max_mhz or SM_MAX_MHZ_FALLBACK, "reasons": sorted(self.reasons),
+            "samples": len(self.samples), "sm_mhz_min": min(self.samples) if self.samples else None,
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from simulator import _native as N
+    from simulator import batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+        args.gpus = world
+    N.require_cuda()  # fails loudly without the CUDA library / a device: there is no fallback
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.games
+    total = n * world
+    dev = torch.device("cuda", local)
+    stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)
+    res = None
+    step_id = [0]
+
+    def one_step():
+        """One pass of the hot path over this rank's shard of a fresh global batch."""
+        nonlocal res
+        base = step_id[0] * total
+        step_id[0] += 1
+        start, count = batch.shard_range(total, rank, world)
+        stats.zero_()
+        res = batch.connect_rollout(CONFIG, count, SEED, base + start, per_game=True, stats=stats, out=res)
+        batch.all_reduce_stats(stats)  # the path's only collective (no-op at N=1)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+        flush.fill_(1)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    env_steps = torch.zeros((), dtype=torch.int64, device=dev)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        r = one_step()
+        ev[i][1].record()
+        env_steps += r.stats[N.STAT_STEPS]  # after the all-reduce: the whole job's steps
+        flush.fill_(i & 0xFF)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    ms = [a.elapsed_time(b) for a, b in ev]
+    elapsed = torch.tensor(sum(ms) / 1e3, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    elapsed_s = float(elapsed)
+    job_steps = int(env_steps)
+    value = job_steps / elapsed_s
+
+    # ---- dominant kernel alone (rank-local, no collective): roofline -----------------------------
+    barrier()
+    kms, ksteps = [], 0
+    for i in range(args.steps):
+        stats.zero_()
+        a, b = kev[i]
+        a.record()
+        res = batch.connect_rollout(CONFIG, n, SEED, (10_000 + i) * total + rank * n, per_game=True, stats=stats, out=res)
+        b.record()
+        torch.cuda.synchronize()
+        kms.append(a.elapsed_time(b))
+        ksteps += int(stats[N.STAT_STEPS])
+        flush.fill_(i & 0xFF)
+    kernel_s = sum(kms) / 1e3
+
+    # ---- end to end through the public API, pinned host results --------------------------------
+    host = batch.HostRollout(CONFIG, n)
+    for i in range(min(args.warmup, 3)):
+        host.run(SEED, (20_000 + i) * total + rank * n)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 0
+    for i in range(args.steps):
+        st, _, _ = host.run(SEED, (30_000 + i) * total + rank * n)
+        e2e_steps += int(st[N.STAT_STEPS])
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor(time.perf_counter() - t0, dtype=torch.float64, device=dev)
+    e2e_n = torch.tensor(e2e_steps, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
+    e2e_value = int(e2e_n) / float(e2e_t)
+
+    if rank == 0:
+        props = torch.cuda.get_device_properties(local)
+        sms = props.multi_processor_count
+        f_mhz = (clocks or {}).get("sm_mhz") or SM_MAX_MHZ_FALLBACK
+        peak = sms * 128 * f_mhz * 1e6 / 1e9  # G thread-instr/s
+        achieved = (ksteps / kernel_s) * OPS_PER_STEP / 1e9
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("connect_rollout_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * elapsed_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": workload_config(args),
+            "env_steps_per_step": job_steps / args.steps,
+            "wall_s_timed_region": t_wall,
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
+            "clock_samples": clocks["samples"] if clocks else 0,
+            "e2e": {
+                "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes * world,
+                "d2h_bytes_per_step": host.d2h_bytes * world,
+                "api": "simulator.batch.HostRollout.run -> bgs_connect_rollout; length/winner/stats copied to pinned host memory",
+            },
+            "gpu_launches": args.steps,
+            "gpu_launches_note": "1 connect_rollout_kernel per step in each timed region (value, kernel-only, e2e)",
+            "roofline": {
+                "bound": "int_issue", "achieved": achieved, "peak": peak, "unit": "G thread-instr/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "kernel": "connect_rollout_kernel<StaticGeo<6,7,4>,false>",
+                "kernel_ms_per_launch": 1e3 * kernel_s / args.steps,
+                "kernel_env_steps_per_s": ksteps / kernel_s,
+                "algorithmic_ops_per_env_step": OPS_PER_STEP,
+                "peak_def": f"{sms} SMs x 4 schedulers x 32 lanes x {f_mhz:.0f} MHz (median SM clock sampled by NVML "
+                            "during the timed region); the path is register-resident, HBM is not the bound",
+                "hbm_write_GBps": (2 * n + 2048) * args.steps / kernel_s / 1e9,
+                "hbm_peak_GBps_measured": (json.load(open(peaks_path)).get("hbm_gbs") if os.path.exists(peaks_path) else 6650.0),
+            },
+        }
+        if world == 1 and not args.no_cpu:
+            cb = cpu_rollout_throughput(args.cpu_seconds)
+            cb.pop("seconds"), cb.pop("steps")
+            try:
+                cb["python_api_1thread_steps_per_s"] = python_api_throughput(200)
+            except Exception as e:  # never let the yardstick break the bench line
+                cb["python_api_error"] = repr(e)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="concurrent games per GPU per step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

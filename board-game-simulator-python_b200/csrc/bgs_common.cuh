@@ -1,0 +1,101 @@
+// bgs_common.cuh -- shared device / host helpers for libbgs_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/bgs_b200.h"
+
+namespace bgs {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: nothing throws across the C ABI
+// ---------------------------------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+int cuda_error(cudaError_t e, const char* what);
+int require_device();  // BGS_OK or BGS_ENODEVICE
+
+#define BGS_CUDA_TRY(expr)                                         \
+    do {                                                           \
+        cudaError_t _e = (expr);                                   \
+        if (_e != cudaSuccess) return ::bgs::cuda_error(_e, #expr); \
+    } while (0)
+
+// Number of SMs of the current device (cached per device).
+int sm_count();
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (Salmon et al., SC'11).  One call yields the 4 draws of plies
+// 4b .. 4b+3 of one game: key = seed, counter = (game id lo, game id hi, b, domain).
+// The key schedule is warp-uniform, so ptxas keeps it in uniform registers.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u;
+constexpr uint32_t PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u;
+constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+constexpr uint32_t DOMAIN_CONNECT = 0u;
+constexpr uint32_t DOMAIN_BOUNCE = 1u;
+
+// ---------------------------------------------------------------------------------------------
+// Warp-pooled claim of game indices from a global counter.
+// Each warp owns a private pool [pool_next, pool_end) of CHUNK indices claimed with ONE atomic;
+// lanes that need a game take consecutive indices from it.  All arguments except `need` are
+// warp-uniform.  Returns this lane's index (valid only if `need`); indices >= n mean "no more work".
+// ---------------------------------------------------------------------------------------------
+template <int CHUNK>
+__device__ __forceinline__ unsigned long long warp_claim(bool need, unsigned long long* counter,
+                                                         unsigned long long& pool_next,
+                                                         unsigned long long& pool_end) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    const unsigned want = __popc(m);
+    const unsigned rank = __popc(m & ((1u << lane) - 1u));
+    const unsigned long long avail = pool_end - pool_next;
+    unsigned long long id = pool_next + rank;
+    if (want > avail) {  // warp-uniform
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)CHUNK);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (rank >= avail) id = base + (rank - (unsigned)avail);
+        pool_next = base + (want - (unsigned)avail);
+        pool_end = base + CHUNK;
+    } else {
+        pool_next += want;
+    }
+    return id;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// length-histogram bin of the stats vector
+__device__ __forceinline__ int hist_bin(int length) {
+    return length < (BGS_STATS_LEN - BGS_STAT_HIST0 - 1) ? length : (BGS_STATS_LEN - BGS_STAT_HIST0 - 1);
+}
+
+constexpr int HIST_BINS = BGS_STATS_LEN - BGS_STAT_HIST0;
+
+}  // namespace bgs

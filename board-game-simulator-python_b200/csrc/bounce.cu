@@ -1,0 +1,549 @@
+// bounce.cu -- Bounce kernels for sm_100a and their C-ABI entry points.
+//
+// Replaces, for many games at once, the per-object path of the reference's binding
+// src/simulator/game/bounce.cpp:24-53 (State::get_actions / get_actions_at / get_action_at,
+// Action::sample_next_state, State::has_ended / get_reward / get_grid).  The rules are restated in
+// SURVEY.md 4.4 from tests/test_bounce.py (the engine source is not part of the reference tree).
+//
+// Data layout: a board of H*W <= 64 cells (cell = y*W + x, row 0 = bottom) is held in registers as
+// NP bit-planes of the piece values (plane b, bit cell = bit b of the value; NP = 2 for values <= 3,
+// 4 for values <= 15).  Move generation is bit-parallel reachability, not a recursive search:
+//   * one "segment" of u steps keeps three frontier masks keyed by the last direction
+//     (forward / left / right) and advances all cells at once with a shift + mask per direction;
+//   * a segment whose last step lands on pieces seeds new segments ("bounces"), grouped by the value
+//     of the piece hit, until no unexpanded bounce cell is left (at most #pieces expansions).
+// The per-source target masks of the mover (<= W sources, all in one row) are staged in shared
+// memory so that the uniform draw can be mapped to the k-th (source, target) pair in ascending order.
+#include "bgs_common.cuh"
+
+namespace bgs {
+namespace bounce {
+
+struct Geo {
+    int H, W, rules;
+    uint64_t board;      // low H*W bits
+    uint64_t not_left;   // cells with x > 0
+    uint64_t not_right;  // cells with x < W-1
+    uint64_t far0, far1;  // far goal row of player 0 (row H-1) / player 1 (row 0)
+    uint64_t row0;        // (1 << W) - 1
+    __host__ __device__ uint64_t far(int player) const { return player == 0 ? far0 : far1; }
+};
+
+static Geo make_geo(int H, int W, int rules) {
+    Geo g;
+    g.H = H; g.W = W; g.rules = rules;
+    g.board = (H * W == 64) ? ~0ull : ((1ull << (H * W)) - 1ull);
+    g.not_left = 0; g.not_right = 0;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            if (x > 0) g.not_left |= 1ull << (y * W + x);
+            if (x < W - 1) g.not_right |= 1ull << (y * W + x);
+        }
+    g.row0 = (1ull << W) - 1ull;
+    g.far0 = g.row0 << ((H - 1) * W);
+    g.far1 = g.row0;
+    return g;
+}
+
+template <int NP>
+struct Planes {
+    uint64_t b[NP];
+    __device__ __forceinline__ uint64_t occ() const {
+        uint64_t o = b[0];
+#pragma unroll
+        for (int i = 1; i < NP; ++i) o |= b[i];
+        return o;
+    }
+    __device__ __forceinline__ int value_at(int cell) const {
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v |= (int)((b[i] >> cell) & 1ull) << i;
+        return v;
+    }
+    __device__ __forceinline__ uint64_t cells_with_value(int u) const {
+        uint64_t m = ~0ull;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) m &= ((u >> i) & 1) ? b[i] : ~b[i];
+        return m;
+    }
+};
+
+// Mask of the row holding the movable pieces of `player`: the occupied row nearest to its own side
+// (tests/test_bounce.py:43-48,60).  0 if the board is empty.  *row receives the row index.
+__device__ __forceinline__ uint64_t source_row_mask(const Geo& g, uint64_t occ, int player, int* row) {
+    if (!occ) {
+        *row = -1;
+        return 0;
+    }
+    const int cell = player == 0 ? (__ffsll((long long)occ) - 1) : (63 - __clzll((long long)occ));
+    const int y = cell / g.W;
+    *row = y;
+    return g.row0 << (y * g.W);
+}
+
+// All targets of the piece on `sbit` (value v) for `player` -- SURVEY.md 4.4 rule 3.
+template <int NP>
+__device__ __forceinline__ uint64_t targets_of(const Geo& g, const Planes<NP>& P, uint64_t occ, int player,
+                                               uint64_t sbit, int v) {
+    const int variant = g.rules & 3;
+    const uint64_t occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
+    const uint64_t wall = variant == BGS_BOUNCE_SOURCE_BLOCKED ? sbit : 0ull;
+    const uint64_t open = g.board & ~wall;
+    const uint64_t inter = open & ~occS & ~g.far(player);  // cells a path may pass through
+    uint64_t expanded = sbit, pending = 0, targets = 0;
+    uint64_t S = sbit;
+    int u = v;
+    for (;;) {
+        // one segment of exactly u steps from every cell of S (no direction memory at the start)
+        uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = S, land = 0;
+        for (int step = u; step >= 1; --step) {
+            const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn;  // may go left / right (no reversal)
+            const uint64_t all = fl | Fr;
+            uint64_t nf = player == 0 ? (all << g.W) : (all >> g.W);  // never backwards
+            uint64_t nl = (fl & g.not_left) >> 1;
+            uint64_t nr = (fr & g.not_right) << 1;
+            if (step > 1) {
+                Ff = nf & inter; Fl = nl & inter; Fr = nr & inter; Nn = 0;
+                if (!(Ff | Fl | Fr)) break;
+            } else {
+                land = (nf | nl | nr) & open;
+            }
+        }
+        targets |= land & ~occS;              // final resting cell must be empty (far row included)
+        pending |= land & occS & ~expanded;   // landed exactly on a piece: bounce with its value
+        if (!pending) break;
+        const int c = __ffsll((long long)pending) - 1;
+        u = P.value_at(c);
+        S = pending & P.cells_with_value(u);
+        pending &= ~S;
+        expanded |= S;
+    }
+    if (!(g.rules & BGS_BOUNCE_ALLOW_NULL_MOVE)) targets &= ~sbit;
+    return targets;
+}
+
+// Target masks of every movable piece of `player`, indexed by source column, into T[x*stride].
+// Returns the total number of (source, target) pairs; *row = the source row.
+template <int NP>
+__device__ __forceinline__ int movegen(const Geo& g, const Planes<NP>& P, int player, uint64_t* T, int stride,
+                                       int* row) {
+    const uint64_t occ = P.occ();
+    const uint64_t rowm = source_row_mask(g, occ, player, row);
+    int total = 0;
+    const int base = *row * g.W;
+    for (int x = 0; x < g.W; ++x) {
+        uint64_t t = 0;
+        if (rowm) {
+            const uint64_t sbit = 1ull << (base + x);
+            if (occ & sbit) t = targets_of<NP>(g, P, occ, player, sbit, P.value_at(base + x));
+        }
+        T[x * stride] = t;
+        total += __popcll(t);
+    }
+    return total;
+}
+
+// Does `player` have at least one legal action?  (early exit on the first piece that has a target)
+template <int NP>
+__device__ __forceinline__ bool has_any(const Geo& g, const Planes<NP>& P, int player) {
+    const uint64_t occ = P.occ();
+    int row;
+    uint64_t src = source_row_mask(g, occ, player, &row) & occ;
+    while (src) {
+        const uint64_t sbit = src & (~src + 1ull);
+        src ^= sbit;
+        const int cell = __ffsll((long long)sbit) - 1;
+        if (targets_of<NP>(g, P, occ, player, sbit, P.value_at(cell))) return true;
+    }
+    return false;
+}
+
+template <int NP>
+__device__ __forceinline__ void move_piece(Planes<NP>& P, int scell, int tcell) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const uint64_t bit = (P.b[i] >> scell) & 1ull;
+        P.b[i] &= ~(1ull << scell);
+        P.b[i] |= bit << tcell;
+    }
+}
+
+__device__ __forceinline__ int nth_set_bit(uint64_t m, int k) {
+    for (int i = 0; i < k; ++i) m &= m - 1ull;
+    return __ffsll((long long)m) - 1;
+}
+
+__device__ __forceinline__ float2 reward_of(int winner) {
+    return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
+                       winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
+}
+
+template <int NP>
+__device__ __forceinline__ void store_grid(const Planes<NP>& P, int HW, int8_t* out) {
+    for (int c = 0; c < HW; ++c) out[c] = (int8_t)P.value_at(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rollout kernel: one game per lane, one ply (= one full move generation) per loop iteration
+// ---------------------------------------------------------------------------------------------
+struct RolloutParams {
+    unsigned long long n_games, game_id0;
+    uint32_t seed_lo, seed_hi;
+    int max_plies;
+    uint64_t plane0[4];  // bit-planes of the start position (the Config grid)
+    uint8_t* moves;      // [n, max_plies, 2] pre-filled 0xFF, or null
+    uint16_t* length;
+    int8_t* winner;
+    int8_t* final_grid;  // [n, H*W]
+    float* reward;       // [n, 2]
+    unsigned long long* stats;
+    unsigned long long* counter;
+};
+
+constexpr int ROLLOUT_THREADS = 128;
+constexpr int CLAIM_CHUNK = 32;
+
+template <int NP>
+__global__ void __launch_bounds__(ROLLOUT_THREADS)
+bounce_rollout_kernel(const Geo g, const RolloutParams p) {
+    __shared__ unsigned int s_hist[HIST_BINS];
+    __shared__ uint64_t s_T[8 * ROLLOUT_THREADS];
+    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    uint64_t* T = s_T + threadIdx.x;
+    const int HW = g.H * g.W;
+
+    Planes<NP> P;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) P.b[i] = 0;
+    int player = 0, t = 0, win = BGS_WINNER_DRAW;
+    bool alive = false, has_game = false, retired = false;
+    unsigned long long idx = 0, pool_next = 0, pool_end = 0;
+    uint32_t r[4] = {0, 0, 0, 0};
+    uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
+    unsigned long long acc_steps = 0;
+
+    for (;;) {
+        // ---- warp-convergent: retire finished games, claim new ones -------------------------
+        if (has_game && !alive) {
+            if (p.length) p.length[idx] = (uint16_t)t;
+            if (p.winner) p.winner[idx] = (int8_t)win;
+            if (p.final_grid) store_grid<NP>(P, HW, p.final_grid + idx * (unsigned long long)HW);
+            if (p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(win);
+            acc_w0 += (win == 0);
+            acc_w1 += (win == 1);
+            acc_dr += (win == BGS_WINNER_DRAW);
+            acc_tr += (win == BGS_WINNER_TRUNCATED);
+            acc_steps += (unsigned)t;
+            atomicAdd(&s_hist[hist_bin(t)], 1u);
+            has_game = false;
+        }
+        const bool need = !has_game && !retired;
+        if (__any_sync(0xffffffffu, need)) {
+            const unsigned long long id = warp_claim<CLAIM_CHUNK>(need, p.counter, pool_next, pool_end);
+            if (need) {
+                if (id < p.n_games) {
+                    idx = id;
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) P.b[i] = p.plane0[i];
+                    player = 0; t = 0; win = BGS_WINNER_DRAW;
+                    alive = true;
+                    has_game = true;
+                } else {
+                    retired = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, has_game)) break;
+
+        if (alive) {
+            int row;
+            const int total = movegen<NP>(g, P, player, T, ROLLOUT_THREADS, &row);
+            if (total == 0) {
+                // the side to move is blocked: the previous mover wins unless it would be blocked
+                // too (tests/test_bounce.py:323-362); a blocked start position is a draw
+                if (t > 0 && has_any<NP>(g, P, 1 - player)) win = 1 - player;
+                alive = false;
+            } else if (t >= p.max_plies) {
+                win = BGS_WINNER_TRUNCATED;
+                alive = false;
+            } else {
+                if ((t & 3) == 0) {
+                    const unsigned long long gid = p.game_id0 + idx;
+                    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2, DOMAIN_BOUNCE,
+                                  p.seed_lo, p.seed_hi, r);
+                }
+                const uint32_t rr = (t & 3) == 0 ? r[0] : ((t & 3) == 1 ? r[1] : ((t & 3) == 2 ? r[2] : r[3]));
+                int k = (int)__umulhi(rr, (uint32_t)total);
+                // k-th action in ascending (source x, target cell) order
+                int sx = 0;
+                uint64_t tm = T[0];
+                for (;;) {
+                    const int c = __popcll(tm);
+                    if (k < c) break;
+                    k -= c;
+                    ++sx;
+                    tm = T[sx * ROLLOUT_THREADS];
+                }
+                const int scell = row * g.W + sx;
+                const int tcell = nth_set_bit(tm, k);
+                if (p.moves) {
+                    uint8_t* m = p.moves + (idx * (unsigned long long)p.max_plies + (unsigned)t) * 2ull;
+                    *reinterpret_cast<uchar2*>(m) = make_uchar2((unsigned char)scell, (unsigned char)tcell);
+                }
+                move_piece<NP>(P, scell, tcell);
+                ++t;
+                if ((1ull << tcell) & g.far(player)) {
+                    win = player;
+                    alive = false;
+                }
+                player ^= 1;
+            }
+        }
+    }
+
+    if (p.stats) {
+        const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
+        const unsigned long long tr = warp_sum(acc_tr), st = warp_sum(acc_steps);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr + tr);
+            atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
+            atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
+            atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
+            atomicAdd(&p.stats[BGS_STAT_TRUNCATED], tr);
+            atomicAdd(&p.stats[BGS_STAT_STEPS], st);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&p.stats[BGS_STAT_HIST0 + i], (unsigned long long)s_hist[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched move generation / single step on reference-layout states (int8 grids)
+// ---------------------------------------------------------------------------------------------
+constexpr int STEP_THREADS = 64;
+
+// Returns false if a cell holds a value outside 0..15.
+__device__ __forceinline__ bool load_planes(const int8_t* __restrict__ grid, int HW, Planes<4>& P) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) P.b[i] = 0;
+    for (int c = 0; c < HW; ++c) {
+        const int v = grid[c];
+        if (v < 0 || v > 15) ok = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) P.b[i] |= (uint64_t)((v >> i) & 1) << c;
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+bounce_moves_kernel(const Geo g, unsigned long long n, const int8_t* __restrict__ grid,
+                    const int8_t* __restrict__ player, const uint8_t* __restrict__ ended,
+                    int8_t* source_row, uint64_t* targets, int32_t* count) {
+    __shared__ uint64_t s_T[8 * STEP_THREADS];
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t* T = s_T + threadIdx.x;
+    const int HW = g.H * g.W;
+    Planes<4> P;
+    const bool ok = load_planes(grid + i * HW, HW, P);
+    int row = -1, total = 0;
+    const bool over = (ended && ended[i]) || !ok;
+    const int pl = player[i] & 1;
+    if (!over) total = movegen<4>(g, P, pl, T, STEP_THREADS, &row);
+    for (int x = 0; x < g.W; ++x) targets[i * g.W + x] = over ? 0ull : T[x * STEP_THREADS];
+    if (source_row) source_row[i] = (int8_t)(total > 0 ? row : -1);
+    if (count) count[i] = ok ? total : -1;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS)
+bounce_step_kernel(const Geo g, unsigned long long n, const int8_t* __restrict__ grid,
+                   const int8_t* __restrict__ player, const int8_t* __restrict__ winner,
+                   const uint8_t* __restrict__ ended,
+                   const int32_t* __restrict__ move, int8_t* grid_out, int8_t* player_out,
+                   int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int HW = g.H * g.W;
+    const int8_t* gi = grid + i * HW;
+    int8_t* go = grid_out + i * HW;
+    Planes<4> P;
+    const bool ok = load_planes(gi, HW, P);
+    int pl = player[i] & 1;
+    const bool over = ended && ended[i];
+    const int sx = move[4 * i + 0], sy = move[4 * i + 1], tx = move[4 * i + 2], ty = move[4 * i + 3];
+    bool legal = ok && !over && sx >= 0 && sx < g.W && sy >= 0 && sy < g.H && tx >= 0 && tx < g.W && ty >= 0 && ty < g.H;
+    int win = winner ? (int)winner[i] : -1;
+    bool end_new = over;
+    if (legal) {
+        const uint64_t occ = P.occ();
+        int row;
+        const uint64_t rowm = source_row_mask(g, occ, pl, &row);
+        const int scell = sy * g.W + sx, tcell = ty * g.W + tx;
+        const uint64_t sbit = 1ull << scell;
+        legal = (rowm & occ & sbit) != 0;
+        if (legal) legal = (targets_of<4>(g, P, occ, pl, sbit, P.value_at(scell)) >> tcell) & 1ull;
+        if (legal) {
+            move_piece<4>(P, scell, tcell);
+            if ((1ull << tcell) & g.far(pl)) {
+                win = pl;
+                end_new = true;
+            } else if (!has_any<4>(g, P, 1 - pl)) {
+                end_new = true;
+                if (has_any<4>(g, P, pl)) win = pl;
+            }
+            pl = 1 - pl;
+        }
+    }
+    if (legal) store_grid<4>(P, HW, go);
+    else if (go != gi)
+        for (int c = 0; c < HW; ++c) go[c] = gi[c];
+    player_out[i] = (int8_t)pl;
+    winner_out[i] = (int8_t)win;
+    if (ended_out) ended_out[i] = end_new;
+    if (reward_out) reinterpret_cast<float2*>(reward_out)[i] = reward_of(win);
+    if (status) status[i] = legal ? 0 : 1;
+}
+
+static bool supported(int H, int W, int max_value) {
+    return H >= 1 && W >= 1 && W <= 8 && H * W <= 64 && max_value <= 15;
+}
+
+}  // namespace bounce
+}  // namespace bgs
+
+using namespace bgs;
+using namespace bgs::bounce;
+
+extern "C" int bgs_bounce_supported(int H, int W, int max_value) { return supported(H, W, max_value) ? 1 : 0; }
+
+extern "C" int bgs_bounce_moves(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
+                                const uint8_t* ended, int8_t* source_row, uint64_t* targets, int32_t* count,
+                                void* stream_) {
+    if (!supported(H, W, 0)) return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d", H, W);
+    if (!grid || !player || !targets) return set_error(BGS_EINVAL, "bounce_moves: null required pointer");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    const Geo g = make_geo(H, W, rules);
+    const unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
+    bounce_moves_kernel<<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(g, n, grid, player, ended,
+                                                                                     source_row, targets, count);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+extern "C" int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
+                               const int8_t* winner, const uint8_t* ended, const int32_t* move, int8_t* grid_out, int8_t* player_out,
+                               int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status,
+                               void* stream_) {
+    if (!supported(H, W, 0)) return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d", H, W);
+    if (!grid || !player || !move || !grid_out || !player_out || !winner_out)
+        return set_error(BGS_EINVAL, "bounce_step: null required pointer");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    const Geo g = make_geo(H, W, rules);
+    const unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
+    bounce_step_kernel<<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
+        g, n, grid, player, winner, ended, move, grid_out, player_out, winner_out, ended_out, reward_out, status);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+template <int NP>
+static int launch_bounce_rollout(const Geo& g, const RolloutParams& p, cudaStream_t stream) {
+    auto kern = bounce_rollout_kernel<NP>;
+    int per_sm = 0;
+    BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ROLLOUT_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long want = (p.n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+    unsigned long long blocks = (unsigned long long)sm_count() * per_sm;
+    if (want < blocks) blocks = want ? want : 1;
+    kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(g, p);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+extern "C" int bgs_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n_games,
+                                  uint64_t game_id0, uint64_t seed, uint8_t* moves, uint16_t* length,
+                                  int8_t* winner, int8_t* final_grid, float* reward, int64_t* stats,
+                                  void* stream_) {
+    if (!grid0) return set_error(BGS_EINVAL, "bounce_rollout: null grid0");
+    if (max_plies < 0 || max_plies > 65535) return set_error(BGS_EINVAL, "bounce_rollout: max_plies out of range");
+    int maxv = 0;
+    if (H >= 1 && W >= 1 && H * W <= 64)
+        for (int c = 0; c < H * W; ++c) {
+            if (grid0[c] < 0) return set_error(BGS_EINVAL, "bounce_rollout: negative cell value");
+            if (grid0[c] > maxv) maxv = grid0[c];
+        }
+    if (!supported(H, W, maxv))
+        return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d (max value %d)", H, W, maxv);
+    if (int rc = require_device()) return rc;
+    if (n_games == 0) return BGS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const Geo g = make_geo(H, W, rules);
+    RolloutParams p;
+    p.n_games = n_games; p.game_id0 = game_id0;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+    p.max_plies = max_plies;
+    for (int i = 0; i < 4; ++i) {
+        p.plane0[i] = 0;
+        for (int c = 0; c < H * W; ++c) p.plane0[i] |= (uint64_t)((grid0[c] >> i) & 1) << c;
+    }
+    p.moves = moves; p.length = length; p.winner = winner; p.final_grid = final_grid; p.reward = reward;
+    p.stats = reinterpret_cast<unsigned long long*>(stats);
+    BGS_CUDA_TRY(cudaMallocAsync((void**)&p.counter, sizeof(unsigned long long), stream));
+    BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
+    if (moves) BGS_CUDA_TRY(cudaMemsetAsync(moves, 0xFF, n_games * (size_t)max_plies * 2, stream));
+    int rc = maxv <= 3 ? launch_bounce_rollout<2>(g, p, stream) : launch_bounce_rollout<4>(g, p, stream);
+    cudaError_t e = cudaFreeAsync(p.counter, stream);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_error(e, "cudaFreeAsync");
+    return BGS_OK;
+}
+
+extern "C" int bgs_bounce_rollout_host(int device, const int8_t* grid0, int H, int W, int rules, int max_plies,
+                                       uint64_t n, uint64_t game_id0, uint64_t seed, uint8_t* moves,
+                                       uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward,
+                                       int64_t* stats) {
+    if (int rc = require_device()) return rc;
+    BGS_CUDA_TRY(cudaSetDevice(device));
+    if (n == 0) return BGS_OK;
+    if (H < 1 || W < 1 || H * W > 64) return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d", H, W);
+    const size_t HW = (size_t)H * W;
+    cudaStream_t st;
+    BGS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint8_t* d_moves = nullptr;
+    uint16_t* d_len = nullptr;
+    int8_t *d_win = nullptr, *d_grid = nullptr;
+    float* d_rew = nullptr;
+    int64_t* d_stats = nullptr;
+    int rc = BGS_OK;
+    auto fail = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == BGS_OK) rc = cuda_error(e, what); };
+    if (moves) fail(cudaMallocAsync((void**)&d_moves, n * (size_t)max_plies * 2, st), "alloc moves");
+    if (length) fail(cudaMallocAsync((void**)&d_len, n * sizeof(uint16_t), st), "alloc length");
+    if (winner) fail(cudaMallocAsync((void**)&d_win, n, st), "alloc winner");
+    if (final_grid) fail(cudaMallocAsync((void**)&d_grid, n * HW, st), "alloc grid");
+    if (reward) fail(cudaMallocAsync((void**)&d_rew, n * 2 * sizeof(float), st), "alloc reward");
+    if (stats) {
+        fail(cudaMallocAsync((void**)&d_stats, BGS_STATS_LEN * sizeof(int64_t), st), "alloc stats");
+        if (rc == BGS_OK) fail(cudaMemcpyAsync(d_stats, stats, BGS_STATS_LEN * sizeof(int64_t), cudaMemcpyHostToDevice, st), "h2d stats");
+    }
+    if (rc == BGS_OK)
+        rc = bgs_bounce_rollout(grid0, H, W, rules, max_plies, n, game_id0, seed, d_moves, d_len, d_win, d_grid, d_rew, d_stats, st);
+    if (rc == BGS_OK) {
+        if (moves) fail(cudaMemcpyAsync(moves, d_moves, n * (size_t)max_plies * 2, cudaMemcpyDeviceToHost, st), "d2h moves");
+        if (length) fail(cudaMemcpyAsync(length, d_len, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, st), "d2h length");
+        if (winner) fail(cudaMemcpyAsync(winner, d_win, n, cudaMemcpyDeviceToHost, st), "d2h winner");
+        if (final_grid) fail(cudaMemcpyAsync(final_grid, d_grid, n * HW, cudaMemcpyDeviceToHost, st), "d2h grid");
+        if (reward) fail(cudaMemcpyAsync(reward, d_rew, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st), "d2h reward");
+        if (stats) fail(cudaMemcpyAsync(stats, d_stats, BGS_STATS_LEN * sizeof(int64_t), cudaMemcpyDeviceToHost, st), "d2h stats");
+    }
+    void* bufs[] = {d_moves, d_len, d_win, d_grid, d_rew, d_stats};
+    for (void* b : bufs)
+        if (b) cudaFreeAsync(b, st);
+    fail(cudaStreamSynchronize(st), "sync");
+    cudaStreamDestroy(st);
+    return rc;
+}

@@ -1,0 +1,602 @@
+// connect.cu -- Connect-k kernels for sm_100a and their C-ABI entry points.
+//
+// Replaces, for millions of games at once, the per-object path of the reference's binding
+// src/simulator/game/connect.cpp:24-54 (Config::sample_initial_state, State::get_actions,
+// State::get_action_at, Action::sample_next_state, State::has_ended / get_reward / get_grid).
+//
+// Data layout
+//   * On chip a board is two bitboards (stones of the side to move / of the other side), bit index
+//     = row*W + col (row 0 = bottom), held in registers: one 64-bit word when H*W <= 64 (6x7),
+//     an unsigned __int128 otherwise (8x9 = 72 bits, 10x12 = 120 bits).  There is no sentinel
+//     row/column: k-in-a-row is `AND of K shifted copies` masked with the set of cells from which a
+//     K-run in that direction stays on the board, so wrapped runs can never count.
+//   * Column heights and the ascending list of playable columns are nibble-packed words, so
+//     "k-th legal column" is one shift+mask and there is no per-column loop anywhere.
+//   * In HBM: per-game records only (length u8, winner i8, optional actions u8[H*W], optional
+//     packed final board 16/32 B); grids int8[n,H,W] are produced by connect_export_kernel.
+//
+// Rollout kernel structure (persistent): grid = resident CTAs only; every lane plays one game at a
+// time.  One outer iteration = [retire finished games + claim new game ids, warp-convergent] ->
+// [one Philox4x32-10 call = the 4 draws of plies 4b..4b+3] -> [4 predicated plies].  Games start on
+// 4-ply boundaries so that the Philox call and the game-end bookkeeping are never divergent.
+#include <type_traits>
+
+#include "bgs_common.cuh"
+
+namespace bgs {
+namespace connect {
+
+typedef unsigned __int128 u128;
+
+// ---------------------------------------------------------------------------------------------
+// geometry policies
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__host__ __device__ constexpr T valid_starts(int H, int W, int K, int dc, int dr) {
+    T m = 0;
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+            const int ce = c + (K - 1) * dc, re = r + (K - 1) * dr;
+            if (ce >= 0 && ce < W && re >= 0 && re < H) m |= (T)1 << (r * W + c);
+        }
+    return m;
+}
+
+// the four line directions as (dc, dr) with a positive bit-index delta dr*W + dc
+__host__ __device__ constexpr int dir_dc(int i) { return i == 0 ? 1 : (i == 1 ? 0 : (i == 2 ? 1 : -1)); }
+__host__ __device__ constexpr int dir_dr(int i) { return i == 0 ? 0 : 1; }
+
+template <int H_, int W_, int K_>
+struct StaticGeo {
+    static constexpr int NW = (H_ * W_ <= 64) ? 1 : 2;
+    typedef typename std::conditional<NW == 1, uint64_t, u128>::type bb_t;
+    typedef typename std::conditional<(W_ <= 8), uint32_t, uint64_t>::type nib_t;
+    __host__ __device__ static constexpr int H() { return H_; }
+    __host__ __device__ static constexpr int W() { return W_; }
+    __host__ __device__ static constexpr int K() { return K_; }
+    template <int I>
+    __device__ static constexpr bb_t valid() {
+        return valid_starts<bb_t>(H_, W_, K_, dir_dc(I), dir_dr(I));
+    }
+};
+
+struct DynGeo {
+    static constexpr int NW = 2;
+    typedef u128 bb_t;
+    typedef uint64_t nib_t;
+    int h, w, k;
+    uint64_t v[4][2];
+    __host__ __device__ int H() const { return h; }
+    __host__ __device__ int W() const { return w; }
+    __host__ __device__ int K() const { return k; }
+    template <int I>
+    __device__ bb_t valid() const {
+        return ((u128)v[I][1] << 64) | v[I][0];
+    }
+};
+
+static DynGeo make_dyn_geo(int H, int W, int K) {
+    DynGeo g;
+    g.h = H; g.w = W; g.k = K;
+    for (int i = 0; i < 4; ++i) {
+        const u128 m = valid_starts<u128>(H, W, K, dir_dc(i), dir_dr(i));
+        g.v[i][0] = (uint64_t)m;
+        g.v[i][1] = (uint64_t)(m >> 64);
+    }
+    return g;
+}
+
+template <typename T>
+__device__ __forceinline__ T shr(T x, int s) {
+    return s >= (int)(8 * sizeof(T)) ? (T)0 : (x >> s);
+}
+
+// Does `me` contain K consecutive stones on any line?  Only the newest stone can have created one,
+// but testing the whole board costs the same handful of shift/AND pairs and needs no coordinates.
+template <class G, int I>
+__device__ __forceinline__ typename G::bb_t runs_dir(const G& g, typename G::bb_t me) {
+    const int K = g.K();
+    const int d = dir_dr(I) * g.W() + dir_dc(I);
+    typename G::bb_t m = me;
+    int len = 1;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        if (2 * len <= K) {
+            m &= shr(m, len * d);
+            len *= 2;
+        }
+    }
+    if (len < K) m &= shr(m, (K - len) * d);
+    return m & g.template valid<I>();
+}
+
+template <class G>
+__device__ __forceinline__ bool has_run(const G& g, typename G::bb_t me) {
+    typename G::bb_t acc = runs_dir<G, 0>(g, me);
+    acc |= runs_dir<G, 1>(g, me);
+    acc |= runs_dir<G, 2>(g, me);
+    acc |= runs_dir<G, 3>(g, me);
+    return acc != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rollout kernel
+// ---------------------------------------------------------------------------------------------
+struct RolloutParams {
+    unsigned long long n_games;
+    unsigned long long game_id0;
+    uint32_t seed_lo, seed_hi;
+    uint8_t* actions;        // [n, H*W] pre-filled with 0xFF, or null
+    uint8_t* length;         // [n] or null
+    int8_t* winner;          // [n] or null
+    uint64_t* final_packed;  // [n, 2*NW] or null
+    unsigned long long* stats;    // [BGS_STATS_LEN] or null
+    unsigned long long* counter;  // zero-initialised claim counter
+};
+
+constexpr int ROLLOUT_THREADS = 256;
+constexpr int CLAIM_CHUNK = 64;
+
+template <class G>
+struct Lane {
+    typename G::bb_t cur, oth;  // stones of the side to move / the other side
+    typename G::nib_t hts;      // nibble c = stones in column c
+    typename G::nib_t cols;     // nibble j = j-th playable column (ascending)
+    uint32_t nleg;              // number of playable columns
+    uint32_t t;                 // plies played
+    bool won;                   // the last move completed a K-run
+};
+
+// One ply: pick the k-th playable column, drop, test for a win.  Returns false when the game ended.
+template <class G, bool WRITE_ACTIONS>
+__device__ __forceinline__ bool play_ply(const G& g, Lane<G>& s, uint32_t r, uint8_t* act_row) {
+    typedef typename G::bb_t bb_t;
+    typedef typename G::nib_t nib_t;
+    const uint32_t k = __umulhi(r, s.nleg);
+    const uint32_t sh = 4u * k;
+    const uint32_t c = (uint32_t)(s.cols >> sh) & 15u;
+    const uint32_t sh2 = 4u * c;
+    const uint32_t h = (uint32_t)(s.hts >> sh2) & 15u;
+    s.hts += (nib_t)1 << sh2;
+    if (h + 1u == (uint32_t)g.H()) {  // column is now full: delete nibble k from the list
+        const nib_t low = ((nib_t)1 << sh) - 1;
+        s.cols = (s.cols & low) | ((s.cols >> 4) & ~low);
+        s.nleg -= 1;
+    }
+    if (WRITE_ACTIONS) act_row[s.t] = (uint8_t)c;
+    s.t += 1;
+    const bb_t me = s.cur | ((bb_t)1 << (h * (uint32_t)g.W() + c));
+    s.won = has_run(g, me);
+    const bool over = s.won || s.nleg == 0;
+    // the mover's stones become `oth` for the next ply; at game end keep them in `cur`
+    if (over) {
+        s.cur = me;
+    } else {
+        s.cur = s.oth;
+        s.oth = me;
+    }
+    return !over;
+}
+
+template <class G>
+__device__ __forceinline__ typename G::nib_t initial_cols(const G& g) {
+    typename G::nib_t v = 0;
+    for (int c = g.W() - 1; c >= 0; --c) v = (v << 4) | (typename G::nib_t)c;
+    return v;
+}
+
+template <class G, bool WRITE_ACTIONS>
+__global__ void __launch_bounds__(ROLLOUT_THREADS)
+connect_rollout_kernel(const G g, const RolloutParams p) {
+    typedef typename G::bb_t bb_t;
+    typedef typename G::nib_t nib_t;
+    __shared__ unsigned int s_hist[HIST_BINS];
+    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+
+    const int HW = g.H() * g.W();
+    const nib_t cols0 = initial_cols(g);
+
+    Lane<G> s;
+    s.cur = 0; s.oth = 0; s.hts = 0; s.cols = cols0; s.nleg = g.W(); s.t = 0; s.won = false;
+    bool alive = false;     // a game is in progress on this lane
+    bool has_game = false;  // the lane holds a (running or just finished) game
+    bool retired = false;   // no more game ids for this lane
+    unsigned long long idx = 0;  // index of the lane's game in [0, n)
+    unsigned long long pool_next = 0, pool_end = 0;
+    uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0;
+    unsigned long long acc_steps = 0;
+
+    for (;;) {
+        // ---- warp-convergent: retire finished games, claim new ones -------------------------
+        if (has_game && !alive) {
+            const int win = s.won ? (int)((s.t - 1u) & 1u) : BGS_WINNER_DRAW;
+            if (p.length) p.length[idx] = (uint8_t)s.t;
+            if (p.winner) p.winner[idx] = (int8_t)win;
+            if (p.final_packed) {
+                // `cur` holds the stones of the last mover = player (t-1)&1
+                const bool last_is_p0 = ((s.t - 1u) & 1u) == 0u;
+                const bb_t b0 = last_is_p0 ? s.cur : s.oth;
+                const bb_t b1 = last_is_p0 ? s.oth : s.cur;
+                uint64_t* dst = p.final_packed + idx * (2 * G::NW);
+                if (G::NW == 1) {
+                    *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2((uint64_t)b0, (uint64_t)b1);
+                } else {
+                    reinterpret_cast<ulonglong2*>(dst)[0] =
+                        make_ulonglong2((uint64_t)b0, (uint64_t)((u128)b0 >> 64));
+                    reinterpret_cast<ulonglong2*>(dst)[1] =
+                        make_ulonglong2((uint64_t)b1, (uint64_t)((u128)b1 >> 64));
+                }
+            }
+            acc_w0 += (win == 0);
+            acc_w1 += (win == 1);
+            acc_dr += (win < 0);
+            acc_steps += s.t;
+            atomicAdd(&s_hist[hist_bin((int)s.t)], 1u);
+            has_game = false;
+        }
+        const bool need = !has_game && !retired;
+        if (__any_sync(0xffffffffu, need)) {
+            const unsigned long long id = warp_claim<CLAIM_CHUNK>(need, p.counter, pool_next, pool_end);
+            if (need) {
+                if (id < p.n_games) {
+                    idx = id;
+                    s.cur = 0; s.oth = 0; s.hts = 0; s.cols = cols0; s.nleg = g.W(); s.t = 0; s.won = false;
+                    alive = true;
+                    has_game = true;
+                } else {
+                    retired = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, has_game)) break;
+
+        // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
+        const unsigned long long gid = p.game_id0 + idx;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), s.t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+        uint8_t* act_row = WRITE_ACTIONS ? p.actions + idx * (unsigned long long)HW : nullptr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (alive) alive = play_ply<G, WRITE_ACTIONS>(g, s, r[j], act_row);
+        }
+    }
+
+    // ---- statistics: warp reduce -> global atomics ----------------------------------------------
+    if (p.stats) {
+        const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
+        const unsigned long long st = warp_sum(acc_steps);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr);
+            atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
+            atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
+            atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
+            atomicAdd(&p.stats[BGS_STAT_STEPS], st);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&p.stats[BGS_STAT_HIST0 + i], (unsigned long long)s_hist[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// export: packed boards -> int8[n,H,W] grids (+ rewards).  HBM-bound: reads 16/32 B, writes H*W (+8) B
+// per game.  Each thread produces 16 consecutive output bytes and stores them with one 128-bit store.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+connect_export_grid_kernel(int HW, int NW, unsigned long long n, const uint64_t* __restrict__ packed,
+                           int8_t* __restrict__ grid) {
+    const unsigned long long total = n * (unsigned long long)HW;
+    const unsigned long long nvec = (total + 15ull) / 16ull;
+    for (unsigned long long v = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v < nvec;
+         v += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long b0 = v * 16ull;
+        unsigned long long game = b0 / (unsigned)HW;
+        int cell = (int)(b0 - game * (unsigned)HW);
+        const uint64_t* rec = packed + game * (2 * NW);
+        uint64_t p0 = __ldg(rec + (cell >> 6));
+        uint64_t p1 = __ldg(rec + NW + (cell >> 6));
+        uint32_t out[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int8_t val = 0;
+                if (b0 + 4 * q + j < total) {
+                    const int bit = cell & 63;
+                    val = ((p0 >> bit) & 1ull) ? (int8_t)0 : (((p1 >> bit) & 1ull) ? (int8_t)1 : (int8_t)-1);
+                    ++cell;
+                    if (cell == HW) {
+                        cell = 0;
+                        ++game;
+                        if (game < n) {
+                            rec = packed + game * (2 * NW);
+                            p0 = __ldg(rec);
+                            p1 = __ldg(rec + NW);
+                        }
+                    } else if ((cell & 63) == 0) {
+                        p0 = __ldg(rec + 1);
+                        p1 = __ldg(rec + NW + 1);
+                    }
+                }
+                w |= (uint32_t)(uint8_t)val << (8 * j);
+            }
+            out[q] = w;
+        }
+        if (b0 + 16ull <= total) {
+            reinterpret_cast<uint4*>(grid)[v] = make_uint4(out[0], out[1], out[2], out[3]);
+        } else {
+            for (int j = 0; b0 + j < total; ++j) grid[b0 + j] = (int8_t)(out[j >> 2] >> (8 * (j & 3)));
+        }
+    }
+}
+
+__device__ __forceinline__ float2 reward_of(int winner) {
+    return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
+                       winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
+}
+
+__global__ void __launch_bounds__(256)
+reward_kernel(unsigned long long n, const int8_t* __restrict__ winner, float2* __restrict__ reward) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        reward[i] = reward_of(winner[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched single step / query on reference-layout states (int8 grids)
+// ---------------------------------------------------------------------------------------------
+struct BoardBits {
+    u128 p[2];
+    uint32_t legal;  // bit c set <=> column c not full
+    bool full;
+};
+
+__device__ __forceinline__ BoardBits load_grid(const int8_t* __restrict__ g, int H, int W) {
+    BoardBits b;
+    b.p[0] = 0; b.p[1] = 0; b.legal = 0;
+    const int HW = H * W;
+    for (int i = 0; i < HW; ++i) {
+        const int v = g[i];
+        if (v == 0) b.p[0] |= (u128)1 << i;
+        else if (v == 1) b.p[1] |= (u128)1 << i;
+    }
+    for (int c = 0; c < W; ++c)
+        if (g[(H - 1) * W + c] < 0) b.legal |= 1u << c;
+    b.full = b.legal == 0;
+    return b;
+}
+
+__global__ void __launch_bounds__(128)
+connect_step_kernel(const DynGeo g, unsigned long long n, const int8_t* __restrict__ grid,
+                    const int8_t* __restrict__ player, const int8_t* __restrict__ winner,
+                    const int32_t* __restrict__ action, int8_t* grid_out, int8_t* player_out,
+                    int8_t* winner_out, uint8_t* ended_out, float* reward_out, uint32_t* legal_out,
+                    int32_t* status) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int H = g.H(), W = g.W(), HW = H * W;
+    const int8_t* gi = grid + i * HW;
+    int8_t* go = grid_out + i * HW;
+    BoardBits b = load_grid(gi, H, W);
+    int pl = player[i];
+    int win = winner[i];
+    const int col = action[i];
+    const bool ended = win >= 0 || b.full;
+    const bool legal = !ended && col >= 0 && col < W && ((b.legal >> col) & 1u) && (pl == 0 || pl == 1);
+    int st = 1;
+    int row = 0;
+    if (legal) {
+        st = 0;
+        const u128 occ = b.p[0] | b.p[1];
+        while ((occ >> (row * W + col)) & 1) ++row;  // lowest empty cell of the column
+        b.p[pl] |= (u128)1 << (row * W + col);
+        if (row == H - 1) b.legal &= ~(1u << col);
+        if (has_run(g, b.p[pl])) win = pl;
+        b.full = b.legal == 0;
+        pl = 1 - pl;
+    }
+    if (go != gi)
+        for (int k = 0; k < HW; ++k) go[k] = gi[k];
+    if (legal) go[row * W + col] = (int8_t)(1 - pl);
+    player_out[i] = (int8_t)pl;
+    winner_out[i] = (int8_t)win;
+    const bool ended_new = win >= 0 || b.full;
+    if (ended_out) ended_out[i] = ended_new;
+    if (legal_out) legal_out[i] = ended_new ? 0u : b.legal;
+    if (reward_out) reinterpret_cast<float2*>(reward_out)[i] = reward_of(win);
+    if (status) status[i] = st;
+}
+
+__global__ void __launch_bounds__(128)
+connect_query_kernel(int H, int W, unsigned long long n, const int8_t* __restrict__ grid,
+                     const int8_t* __restrict__ winner, uint8_t* ended_out, uint32_t* legal_out,
+                     float* reward_out) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int8_t* gi = grid + i * (unsigned long long)(H * W);
+    uint32_t legal = 0;
+    for (int c = 0; c < W; ++c)
+        if (gi[(H - 1) * W + c] < 0) legal |= 1u << c;
+    const int win = winner[i];
+    const bool ended = win >= 0 || legal == 0;
+    if (ended_out) ended_out[i] = ended;
+    if (legal_out) legal_out[i] = ended ? 0u : legal;
+    if (reward_out) reinterpret_cast<float2*>(reward_out)[i] = reward_of(win);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool supported(int H, int W, int K) {
+    return H >= 1 && W >= 1 && K >= 1 && H <= 15 && W <= 16 && H * W <= 128;
+}
+
+template <class G, bool WA>
+static int launch_rollout_t(const G& g, const RolloutParams& p, cudaStream_t stream) {
+    auto kern = connect_rollout_kernel<G, WA>;
+    int per_sm = 0;
+    BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ROLLOUT_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    // persistent launch: exactly the resident CTAs, a multiple of the SM count
+    unsigned long long want = (p.n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+    unsigned long long blocks = (unsigned long long)sm_count() * per_sm;
+    if (want < blocks) blocks = want ? want : 1;
+    kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(g, p);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+template <class G>
+static int launch_rollout(const G& g, const RolloutParams& p, cudaStream_t stream) {
+    return p.actions ? launch_rollout_t<G, true>(g, p, stream) : launch_rollout_t<G, false>(g, p, stream);
+}
+
+}  // namespace connect
+}  // namespace bgs
+
+using namespace bgs;
+using namespace bgs::connect;
+
+extern "C" int bgs_connect_supported(int H, int W, int K) { return supported(H, W, K) ? 1 : 0; }
+
+extern "C" int bgs_connect_packed_words(int H, int W) { return 2 * (H * W <= 64 ? 1 : 2); }
+
+extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                                   uint8_t* actions, uint8_t* length, int8_t* winner,
+                                   uint64_t* final_packed, int64_t* stats, void* stream_) {
+    if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
+    if (int rc = require_device()) return rc;
+    if (n_games == 0) return BGS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    RolloutParams p;
+    p.n_games = n_games;
+    p.game_id0 = game_id0;
+    p.seed_lo = (uint32_t)seed;
+    p.seed_hi = (uint32_t)(seed >> 32);
+    p.actions = actions;
+    p.length = length;
+    p.winner = winner;
+    p.final_packed = final_packed;
+    p.stats = reinterpret_cast<unsigned long long*>(stats);
+    BGS_CUDA_TRY(cudaMallocAsync((void**)&p.counter, sizeof(unsigned long long), stream));
+    BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
+    if (actions) BGS_CUDA_TRY(cudaMemsetAsync(actions, 0xFF, n_games * (size_t)(H * W), stream));
+    int rc;
+    if (H == 6 && W == 7 && K == 4) rc = launch_rollout(StaticGeo<6, 7, 4>(), p, stream);
+    else if (H == 8 && W == 9 && K == 5) rc = launch_rollout(StaticGeo<8, 9, 5>(), p, stream);
+    else if (H == 10 && W == 12 && K == 6) rc = launch_rollout(StaticGeo<10, 12, 6>(), p, stream);
+    else rc = launch_rollout(make_dyn_geo(H, W, K), p, stream);
+    cudaError_t e = cudaFreeAsync(p.counter, stream);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_error(e, "cudaFreeAsync");
+    return BGS_OK;
+}
+
+extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,
+                                  int8_t* grid, float* reward, void* stream_) {
+    if (!supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int sms = sm_count();
+    if (grid) {
+        if (!packed) return set_error(BGS_EINVAL, "connect_export: grid requested without packed boards");
+        const int NW = H * W <= 64 ? 1 : 2;
+        const unsigned long long nvec = (n * (unsigned long long)(H * W) + 15ull) / 16ull;
+        unsigned long long blocks = (nvec + 255) / 256;
+        const unsigned long long cap = (unsigned long long)sms * 8 * 4;
+        if (blocks > cap) blocks = cap;
+        connect_export_grid_kernel<<<(unsigned)blocks, 256, 0, stream>>>(H * W, NW, n, packed, grid);
+        BGS_CUDA_TRY(cudaGetLastError());
+    }
+    if (reward) {
+        if (!winner) return set_error(BGS_EINVAL, "connect_export: reward requested without winner");
+        unsigned long long blocks = (n + 255) / 256;
+        const unsigned long long cap = (unsigned long long)sms * 8 * 4;
+        if (blocks > cap) blocks = cap;
+        reward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, winner, reinterpret_cast<float2*>(reward));
+        BGS_CUDA_TRY(cudaGetLastError());
+    }
+    return BGS_OK;
+}
+
+extern "C" int bgs_connect_step(int H, int W, int K, uint64_t n, const int8_t* grid, const int8_t* player,
+                                const int8_t* winner, const int32_t* action, int8_t* grid_out,
+                                int8_t* player_out, int8_t* winner_out, uint8_t* ended_out,
+                                float* reward_out, uint32_t* legal_out, int32_t* status, void* stream_) {
+    if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
+    if (!grid || !player || !winner || !action || !grid_out || !player_out || !winner_out)
+        return set_error(BGS_EINVAL, "connect_step: null required pointer");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    const DynGeo g = make_dyn_geo(H, W, K);
+    const unsigned long long blocks = (n + 127) / 128;
+    connect_step_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(
+        g, n, grid, player, winner, action, grid_out, player_out, winner_out, ended_out, reward_out,
+        legal_out, status);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+extern "C" int bgs_connect_query(int H, int W, uint64_t n, const int8_t* grid, const int8_t* winner,
+                                 uint8_t* ended_out, uint32_t* legal_out, float* reward_out, void* stream_) {
+    if (!supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
+    if (!grid || !winner) return set_error(BGS_EINVAL, "connect_query: null required pointer");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    const unsigned long long blocks = (n + 127) / 128;
+    connect_query_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(H, W, n, grid, winner, ended_out,
+                                                                             legal_out, reward_out);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+extern "C" int bgs_connect_rollout_host(int device, int H, int W, int K, uint64_t n, uint64_t game_id0,
+                                        uint64_t seed, uint8_t* actions, uint8_t* length, int8_t* winner,
+                                        int8_t* final_grid, float* reward, int64_t* stats) {
+    if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
+    if (int rc = require_device()) return rc;
+    BGS_CUDA_TRY(cudaSetDevice(device));
+    if (n == 0) return BGS_OK;
+    const size_t HW = (size_t)H * W;
+    const int PW = bgs_connect_packed_words(H, W);
+    cudaStream_t st;
+    BGS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint8_t *d_act = nullptr, *d_len = nullptr;
+    int8_t *d_win = nullptr, *d_grid = nullptr;
+    uint64_t* d_packed = nullptr;
+    float* d_rew = nullptr;
+    int64_t* d_stats = nullptr;
+    int rc = BGS_OK;
+    auto fail = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == BGS_OK) rc = cuda_error(e, what); };
+    if (actions) fail(cudaMallocAsync((void**)&d_act, n * HW, st), "alloc actions");
+    if (length) fail(cudaMallocAsync((void**)&d_len, n, st), "alloc length");
+    if (winner || reward) fail(cudaMallocAsync((void**)&d_win, n, st), "alloc winner");
+    if (final_grid) {
+        fail(cudaMallocAsync((void**)&d_packed, n * PW * sizeof(uint64_t), st), "alloc packed");
+        fail(cudaMallocAsync((void**)&d_grid, n * HW, st), "alloc grid");
+    }
+    if (reward) fail(cudaMallocAsync((void**)&d_rew, n * 2 * sizeof(float), st), "alloc reward");
+    if (stats) {
+        fail(cudaMallocAsync((void**)&d_stats, BGS_STATS_LEN * sizeof(int64_t), st), "alloc stats");
+        if (rc == BGS_OK) fail(cudaMemcpyAsync(d_stats, stats, BGS_STATS_LEN * sizeof(int64_t), cudaMemcpyHostToDevice, st), "h2d stats");
+    }
+    if (rc == BGS_OK) rc = bgs_connect_rollout(H, W, K, n, game_id0, seed, d_act, d_len, d_win, d_packed, d_stats, st);
+    if (rc == BGS_OK && (final_grid || reward)) rc = bgs_connect_export(H, W, n, d_packed, d_win, d_grid, d_rew, st);
+    if (rc == BGS_OK) {
+        if (actions) fail(cudaMemcpyAsync(actions, d_act, n * HW, cudaMemcpyDeviceToHost, st), "d2h actions");
+        if (length) fail(cudaMemcpyAsync(length, d_len, n, cudaMemcpyDeviceToHost, st), "d2h length");
+        if (winner) fail(cudaMemcpyAsync(winner, d_win, n, cudaMemcpyDeviceToHost, st), "d2h winner");
+        if (final_grid) fail(cudaMemcpyAsync(final_grid, d_grid, n * HW, cudaMemcpyDeviceToHost, st), "d2h grid");
+        if (reward) fail(cudaMemcpyAsync(reward, d_rew, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st), "d2h reward");
+        if (stats) fail(cudaMemcpyAsync(stats, d_stats, BGS_STATS_LEN * sizeof(int64_t), cudaMemcpyDeviceToHost, st), "d2h stats");
+    }
+    void* bufs[] = {d_act, d_len, d_win, d_grid, d_packed, d_rew, d_stats};
+    for (void* b : bufs)
+        if (b) cudaFreeAsync(b, st);
+    fail(cudaStreamSynchronize(st), "sync");
+    cudaStreamDestroy(st);
+    return rc;
+}

@@ -1,0 +1,386 @@
+"""Batched entry points: millions of independent games per call, results as torch tensors.
+
+This is the new surface the B200 build adds on top of the reference's per-object API.  Every tensor
+returned lives on the GPU (export with ``torch.utils.dlpack.to_dlpack`` / ``tensor.__dlpack__()``),
+is allocated by torch and only *filled* by ``libbgs_b200.so``; the ``*_host`` helpers copy the small
+per-game results into pinned host memory.
+
+The loop being replaced is the reference's README.md:49-72::
+
+    state = config.sample_initial_state()
+    while not state.has_ended:
+        action = random.choice(state.actions)
+        state = action.sample_next_state()
+    reward = state.reward
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any
+
+from . import _native as N
+
+
+def _hwk(config) -> tuple[int, int, int]:
+    if isinstance(config, (tuple, list)):
+        h, w, k = config
+    else:
+        h, w, k = config.height, config.width, config.count
+    return int(h), int(w), int(k)
+
+
+@dataclass
+class RolloutResult:
+    """Outputs of a batched rollout. ``stats`` is the int64[256] vector that is summed across GPUs."""
+
+    n_games: int
+    game_id0: int
+    seed: int
+    stats: Any
+    length: Any = None
+    winner: Any = None
+    actions: Any = None  # Connect: uint8[n, H*W] columns; Bounce: uint8[n, max_plies, 2] cells
+    final_grid: Any = None
+    reward: Any = None
+    extra: dict = field(default_factory=dict)
+
+    def stats_dict(self) -> dict[str, int]:
+        s = self.stats.cpu()
+        return {
+            "games": int(s[N.STAT_GAMES]),
+            "wins0": int(s[N.STAT_WIN0]),
+            "wins1": int(s[N.STAT_WIN1]),
+            "draws": int(s[N.STAT_DRAWS]),
+            "steps": int(s[N.STAT_STEPS]),
+            "truncated": int(s[N.STAT_TRUNCATED]),
+        }
+
+    def length_histogram(self):
+        return self.stats[N.STAT_HIST0:].clone()
+
+
+def all_reduce_stats(stats):
+    """Sum the statistics vector over all ranks (NCCL over NVLink; the path's only collective)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous shard [start, start+count) of game ids owned by ``rank``."""
+    base, rem = divmod(int(n_total), int(world))
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+# -------------------------------------------------------------------------------------------------
+# Connect-k
+# -------------------------------------------------------------------------------------------------
+def connect_rollout(
+    config,
+    n_games: int,
+    seed: int = 0,
+    game_id0: int = 0,
+    *,
+    per_game: bool = True,
+    actions: bool = False,
+    final_grid: bool = False,
+    reward: bool = False,
+    stats=None,
+    out: RolloutResult | None = None,
+) -> RolloutResult:
+    """Play ``n_games`` uniform-random Connect-k games to the end on the current CUDA device.
+
+    ``per_game`` returns ``length`` uint8[n] and ``winner`` int8[n] (0 / 1 / -1 draw); ``actions``
+    the trajectories uint8[n, H*W] (0xFF padded); ``final_grid`` int8[n,H,W]; ``reward``
+    float32[n,2].  ``stats`` (int64[256], device) is accumulated into when given.  Pass a previous
+    result as ``out`` to reuse its buffers.  Asynchronous: nothing is synchronised here.
+    """
+    torch = N.require_cuda()
+    L = N.lib()
+    H, W, K = _hwk(config)
+    if not L.bgs_connect_supported(H, W, K):
+        raise RuntimeError(f"Connect {H}x{W} k={K} is not supported by the CUDA kernels")
+    n = int(n_games)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def buf(name, shape, dtype, want):
+        if not want:
+            return None
+        t = getattr(out, name, None) if out is not None else None
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+            t = torch.empty(shape, dtype=dtype, device=dev)
+        return t
+
+    want_winner = per_game or reward
+    res = RolloutResult(n_games=n, game_id0=int(game_id0), seed=int(seed), stats=None)
+    res.length = buf("length", (n,), torch.uint8, per_game)
+    res.winner = buf("winner", (n,), torch.int8, want_winner)
+    res.actions = buf("actions", (n, H * W), torch.uint8, actions)
+    res.final_grid = buf("final_grid", (n, H, W), torch.int8, final_grid)
+    res.reward = buf("reward", (n, 2), torch.float32, reward)
+    packed = None
+    if final_grid:
+        pw = L.bgs_connect_packed_words(H, W)
+        packed = out.extra.get("packed") if out is not None else None
+        if packed is None or tuple(packed.shape) != (n, pw) or packed.device != dev:
+            packed = torch.empty((n, pw), dtype=torch.int64, device=dev)
+        res.extra["packed"] = packed
+    if stats is None:
+        stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
+    res.stats = stats
+    st = N.stream_ptr(torch)
+    N.check(
+        L.bgs_connect_rollout(
+            H, W, K, n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
+            N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
+        )
+    )
+    if final_grid or reward:
+        N.check(
+            L.bgs_connect_export(H, W, n, N.ptr(packed), N.ptr(res.winner), N.ptr(res.final_grid), N.ptr(res.reward), st)
+        )
+    return res
+
+
+class HostRollout:
+    """Reusable pinned host buffers + device buffers for the end-to-end path (what bench.py's
+    ``e2e`` times).  A rollout from the empty board has no tensor input -- its inputs are the scalars
+    (config, n_games, seed, game_id0), which travel in the kernel launch parameters -- so the
+    host->device side is 0 bytes; per-game ``length`` / ``winner`` and the statistics vector come
+    back device->host into pinned memory on every call."""
+
+    def __init__(self, config, n_games: int):
+        torch = N.require_cuda()
+        self.torch = torch
+        self.config = config
+        self.n = int(n_games)
+        self.length_host = torch.empty(self.n, dtype=torch.uint8).pin_memory()
+        self.winner_host = torch.empty(self.n, dtype=torch.int8).pin_memory()
+        self.stats_host = torch.zeros(N.STATS_LEN, dtype=torch.int64).pin_memory()
+        self.stats_dev = torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda")
+        self._res = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = self.n * 2 + N.STATS_LEN * 8
+
+    def run(self, seed: int, game_id0: int = 0):
+        """One end-to-end rollout; returns (stats, length, winner) as pinned host tensors (synchronised)."""
+        self.stats_dev.zero_()
+        self._res = connect_rollout(
+            self.config, self.n, seed, game_id0, per_game=True, stats=self.stats_dev, out=self._res
+        )
+        self.length_host.copy_(self._res.length, non_blocking=True)
+        self.winner_host.copy_(self._res.winner, non_blocking=True)
+        self.stats_host.copy_(self.stats_dev, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        return self.stats_host, self.length_host, self.winner_host
+
+
+class ConnectBatch:
+    """n Connect-k states as tensors: the batched equivalent of the reference's State objects.
+
+    ``grid`` int8[n,H,W] (row 0 bottom; -1 / 0 / 1), ``player`` int8[n], ``winner`` int8[n] (-1 none),
+    ``has_ended`` uint8[n], ``legal`` uint32[n] (bit c = column c playable), ``reward`` float32[n,2].
+    """
+
+    def __init__(self, config, grid, player, winner, has_ended=None, legal=None, reward=None):
+        self.config = config
+        self.grid, self.player, self.winner = grid, player, winner
+        self.has_ended, self.legal, self.reward = has_ended, legal, reward
+        if has_ended is None:
+            self._query()
+
+    @property
+    def n(self) -> int:
+        return self.grid.shape[0]
+
+    @staticmethod
+    def initial(config, n: int) -> "ConnectBatch":
+        """n copies of ``config.sample_initial_state()`` (reference connect.cpp:32)."""
+        torch = N.require_cuda()
+        H, W, _ = _hwk(config)
+        grid = torch.full((n, H, W), -1, dtype=torch.int8, device="cuda")
+        player = torch.zeros(n, dtype=torch.int8, device="cuda")
+        winner = torch.full((n,), -1, dtype=torch.int8, device="cuda")
+        return ConnectBatch(config, grid, player, winner)
+
+    def _query(self):
+        torch = N.require_cuda()
+        H, W, _ = _hwk(self.config)
+        n = self.n
+        self.has_ended = torch.empty(n, dtype=torch.uint8, device=self.grid.device)
+        self.legal = torch.empty(n, dtype=torch.int32, device=self.grid.device)
+        self.reward = torch.empty((n, 2), dtype=torch.float32, device=self.grid.device)
+        N.check(
+            N.lib().bgs_connect_query(
+                H, W, n, N.ptr(self.grid), N.ptr(self.winner), N.ptr(self.has_ended), N.ptr(self.legal),
+                N.ptr(self.reward), N.stream_ptr(torch),
+            )
+        )
+
+    def legal_mask(self):
+        """bool[n, W]: which columns ``state.actions`` would list (reference connect.cpp:43)."""
+        torch = N.require_cuda()
+        W = _hwk(self.config)[1]
+        bits = torch.arange(W, device=self.legal.device, dtype=torch.int32)
+        return ((self.legal.unsqueeze(1) >> bits) & 1).bool()
+
+    def step(self, actions):
+        """``action_at(col).sample_next_state()`` for every state (reference connect.cpp:44,52).
+
+        Returns ``(next_batch, status)``; ``status`` int32[n] is 0, or 1 where the column was illegal
+        or the game had ended (that state is returned unchanged -- the object API raises instead).
+        """
+        torch = N.require_cuda()
+        H, W, K = _hwk(self.config)
+        n = self.n
+        dev = self.grid.device
+        actions = actions.to(device=dev, dtype=torch.int32).contiguous()
+        grid = torch.empty_like(self.grid)
+        player = torch.empty_like(self.player)
+        winner = torch.empty_like(self.winner)
+        ended = torch.empty(n, dtype=torch.uint8, device=dev)
+        legal = torch.empty(n, dtype=torch.int32, device=dev)
+        reward = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        N.check(
+            N.lib().bgs_connect_step(
+                H, W, K, n, N.ptr(self.grid), N.ptr(self.player), N.ptr(self.winner), N.ptr(actions),
+                N.ptr(grid), N.ptr(player), N.ptr(winner), N.ptr(ended), N.ptr(reward), N.ptr(legal),
+                N.ptr(status), N.stream_ptr(torch),
+            )
+        )
+        return ConnectBatch(self.config, grid, player, winner, ended, legal, reward), status
+
+
+# -------------------------------------------------------------------------------------------------
+# Bounce
+# -------------------------------------------------------------------------------------------------
+def _bounce_grid(config):
+    import numpy as np
+
+    g = config if not hasattr(config, "_grid") else config._grid
+    g = np.ascontiguousarray(np.asarray(g), dtype=np.int8)
+    if g.ndim != 2:
+        raise TypeError("Bounce grid must be a 2-D array")
+    return g
+
+
+def _bounce_check(L, g):
+    H, W = g.shape
+    if g.min() < 0 or not L.bgs_bounce_supported(H, W, int(g.max())):
+        raise RuntimeError(
+            f"Bounce {H}x{W} with values up to {int(g.max())} is not supported by the CUDA kernels "
+            "(need H*W <= 64, W <= 8, values 0..15)"
+        )
+
+
+def bounce_rollout(
+    config,
+    n_games: int,
+    seed: int = 0,
+    game_id0: int = 0,
+    *,
+    max_plies: int = 512,
+    rules: int = 0,
+    per_game: bool = True,
+    moves: bool = False,
+    final_grid: bool = False,
+    reward: bool = False,
+    stats=None,
+) -> RolloutResult:
+    """Play ``n_games`` uniform-random Bounce games from ``config`` (a ``bounce.Config`` or an int8
+    grid) on the current CUDA device.  Games still running after ``max_plies`` plies are reported
+    with ``winner == -2`` and counted in ``stats[5]``.  ``moves`` returns uint8[n, max_plies, 2] =
+    (source cell, target cell) with cell = y*W + x."""
+    torch = N.require_cuda()
+    L = N.lib()
+    g = _bounce_grid(config)
+    _bounce_check(L, g)
+    H, W = g.shape
+    n = int(n_games)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    res = RolloutResult(n_games=n, game_id0=int(game_id0), seed=int(seed), stats=None)
+    res.length = torch.empty(n, dtype=torch.int16, device=dev) if per_game else None
+    res.winner = torch.empty(n, dtype=torch.int8, device=dev) if per_game else None
+    res.actions = torch.empty((n, max_plies, 2), dtype=torch.uint8, device=dev) if moves else None
+    res.final_grid = torch.empty((n, H, W), dtype=torch.int8, device=dev) if final_grid else None
+    res.reward = torch.empty((n, 2), dtype=torch.float32, device=dev) if reward else None
+    if stats is None:
+        stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
+    res.stats = stats
+    res.extra["max_plies"] = int(max_plies)
+    N.check(
+        L.bgs_bounce_rollout(
+            g.ctypes.data, H, W, int(rules), int(max_plies), n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
+            N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(res.final_grid), N.ptr(res.reward),
+            N.ptr(stats), N.stream_ptr(torch),
+        )
+    )
+    return res
+
+
+class BounceBatch:
+    """n Bounce states as tensors: ``grid`` int8[n,H,W], ``player`` int8[n], ``winner`` int8[n],
+    ``has_ended`` uint8[n].  ``moves()`` gives the legal actions, ``step()`` the transition."""
+
+    def __init__(self, grid, player, winner, has_ended, rules: int = 0, reward=None):
+        self.grid, self.player, self.winner, self.has_ended = grid, player, winner, has_ended
+        self.rules = int(rules)
+        self.reward = reward
+
+    @property
+    def n(self) -> int:
+        return self.grid.shape[0]
+
+    @staticmethod
+    def initial(config, n: int, rules: int = 0) -> "BounceBatch":
+        torch = N.require_cuda()
+        g = _bounce_grid(config)
+        _bounce_check(N.lib(), g)
+        grid = torch.from_numpy(g).cuda().unsqueeze(0).repeat(n, 1, 1).contiguous()
+        z = torch.zeros(n, dtype=torch.int8, device="cuda")
+        return BounceBatch(grid, z, torch.full_like(z, -1), torch.zeros(n, dtype=torch.uint8, device="cuda"), rules)
+
+    def moves(self):
+        """``(source_row int8[n], targets int64[n,W], count int32[n])``: bit ``y*W+x`` of
+        ``targets[i, sx]`` is set iff ``(sx, source_row[i]) -> (x, y)`` is legal (reference
+        bounce.cpp:40-41).  ``count`` is -1 for a grid with values outside 0..15."""
+        torch = N.require_cuda()
+        n, H, W = self.grid.shape
+        dev = self.grid.device
+        row = torch.empty(n, dtype=torch.int8, device=dev)
+        targets = torch.empty((n, W), dtype=torch.int64, device=dev)
+        count = torch.empty(n, dtype=torch.int32, device=dev)
+        N.check(
+            N.lib().bgs_bounce_moves(
+                H, W, self.rules, n, N.ptr(self.grid), N.ptr(self.player), N.ptr(self.has_ended), N.ptr(row),
+                N.ptr(targets), N.ptr(count), N.stream_ptr(torch),
+            )
+        )
+        return row, targets, count
+
+    def step(self, move):
+        """``action_at(source, target).sample_next_state()`` for every state; ``move`` is
+        int32[n,4] = (sx, sy, tx, ty).  Returns ``(next_batch, status)`` with status 1 = illegal."""
+        torch = N.require_cuda()
+        n, H, W = self.grid.shape
+        dev = self.grid.device
+        move = move.to(device=dev, dtype=torch.int32).contiguous()
+        grid = torch.empty_like(self.grid)
+        player = torch.empty_like(self.player)
+        winner = torch.empty_like(self.winner)
+        ended = torch.empty(n, dtype=torch.uint8, device=dev)
+        reward = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        N.check(
+            N.lib().bgs_bounce_step(
+                H, W, self.rules, n, N.ptr(self.grid), N.ptr(self.player), N.ptr(self.winner), N.ptr(self.has_ended),
+                N.ptr(move),
+                N.ptr(grid), N.ptr(player), N.ptr(winner), N.ptr(ended), N.ptr(reward), N.ptr(status),
+                N.stream_ptr(torch),
+            )
+        )
+        return BounceBatch(grid, player, winner, ended, self.rules, reward), status

@@ -1,0 +1,164 @@
+/*
+ * bgs_b200.h -- C ABI of libbgs_b200.so, the B200 (sm_100a) batched board-game rollout engine.
+ *
+ * This is the drop-in boundary for the reference's one data-parallel hot path: legal-move
+ * generation -> state transition -> terminal / reward evaluation inside a random-rollout loop.
+ * In the reference that path is reached through two nanobind modules,
+ *     src/simulator/game/connect.cpp:24-61   (Config / State / Action of Connect-k)
+ *     src/simulator/game/bounce.cpp:24-60    (Config / State / Action of Bounce)
+ * one Python call per property per game.  Every entry point below cites the binding(s) it replaces;
+ * INTEGRATION.md shows the binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - Every function returns 0 on success and a negative BGS_E* code on failure; the message is in
+ *     bgs_last_error() (thread local).  Nothing throws across the ABI.
+ *   - Pointers are DEVICE pointers on the current CUDA device unless the function name ends in
+ *     `_host`.  `stream` is a cudaStream_t (NULL = legacy default stream).  Device-pointer entry
+ *     points are asynchronous with respect to the host; `_host` entry points synchronise.
+ *   - Output pointers documented as "optional" may be NULL.
+ *   - Grids use the reference's own layout: int8[H][W], row 0 = bottom row
+ *     (tests/test_connect.py:25-30, tests/test_bounce.py:24-31).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     BGS_ENODEVICE.
+ */
+#ifndef BGS_B200_H
+#define BGS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGS_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define BGS_OK 0
+#define BGS_EINVAL (-1)       /* bad argument */
+#define BGS_EUNSUPPORTED (-2) /* configuration outside what the kernels cover */
+#define BGS_ECUDA (-3)        /* CUDA runtime error (message has the cudaError string) */
+#define BGS_ENODEVICE (-4)    /* no CUDA device / driver */
+
+/* statistics vector: int64[BGS_STATS_LEN], ACCUMULATED into (zero it first for a fresh count).
+ * This is the buffer that is all-reduced (sum) across GPUs. */
+#define BGS_STATS_LEN 256
+#define BGS_STAT_GAMES 0
+#define BGS_STAT_WIN0 1
+#define BGS_STAT_WIN1 2
+#define BGS_STAT_DRAWS 3
+#define BGS_STAT_STEPS 4     /* total env-steps (plies) */
+#define BGS_STAT_TRUNCATED 5 /* Bounce only: games cut at max_plies */
+#define BGS_STAT_HIST0 16    /* stats[16 + min(length, 239)] = number of games of that length */
+
+/* per-game `winner` codes in batched outputs */
+#define BGS_WINNER_DRAW (-1)
+#define BGS_WINNER_TRUNCATED (-2)
+
+/* Bounce rule switches left unpinned by the reference's tests. Default 0. */
+#define BGS_BOUNCE_SOURCE_EMPTY 0
+#define BGS_BOUNCE_SOURCE_BLOCKED 1
+#define BGS_BOUNCE_SOURCE_PIECE 2
+#define BGS_BOUNCE_ALLOW_NULL_MOVE 4
+
+int bgs_version(void);
+const char* bgs_last_error(void);
+/* Number of CUDA devices visible (0 if none / no driver). Never fails. */
+int bgs_device_count(void);
+
+/* ----------------------------------------------------------------------------------------------
+ * Connect-k   --  replaces game::connect::{Config,State,Action} as bound in connect.cpp:24-54
+ * -------------------------------------------------------------------------------------------- */
+
+/* 1 if (H, W, K) is covered by the kernels (H*W <= 128, H <= 15, W <= 16, K >= 1), else 0. */
+int bgs_connect_supported(int H, int W, int K);
+
+/* Number of uint64 words per game in the packed board format used by *_packed / export:
+ * [stones of player 0 | stones of player 1], each (H*W <= 64 ? 1 : 2) words, bit index = col*H + row. */
+int bgs_connect_packed_words(int H, int W);
+
+/* The whole rollout loop of README.md:49-72 for n_games independent games from the empty board:
+ *   Config::sample_initial_state (connect.cpp:32) -> while !has_ended (connect.cpp:39):
+ *   actions (connect.cpp:43) -> uniform choice -> sample_next_state (connect.cpp:52) -> reward (connect.cpp:41).
+ * Game i uses global id game_id0 + i; the action at ply t of a game is
+ *   legal_columns_ascending[ mulhi32( philox4x32_10(key=seed, ctr=(id_lo,id_hi,t>>2,0))[t&3], n_legal ) ].
+ * actions      optional uint8[n_games, H*W]  column per ply, 0xFF after the end
+ * length       optional uint8[n_games]       plies played
+ * winner       optional int8[n_games]        0 / 1 / BGS_WINNER_DRAW
+ * final_packed optional uint64[n_games, bgs_connect_packed_words] final boards (feed to bgs_connect_export)
+ * stats        optional int64[BGS_STATS_LEN] accumulated */
+int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                        uint8_t* actions, uint8_t* length, int8_t* winner, uint64_t* final_packed,
+                        int64_t* stats, void* stream);
+
+/* State::get_grid (connect.cpp:42) and State::get_reward (connect.cpp:41) for n packed boards:
+ * grid optional int8[n,H,W] (-1 / 0 / 1); reward optional float[n,2] from winner int8[n]. */
+int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,
+                       int8_t* grid, float* reward, void* stream);
+
+/* Batched single transition on reference-layout states.  Replaces, for n states at once,
+ *   State::get_action_at (connect.cpp:44)  -> status[i] = 0 ok / 1 illegal (state left unchanged)
+ *   Action::sample_next_state (connect.cpp:52) -> grid_out, player_out, winner_out
+ *   State::has_ended / get_reward / get_actions on the NEW state (connect.cpp:39,41,43)
+ * grid int8[n,H,W], player int8[n], winner int8[n] (-1 none), action int32[n] (column).
+ * ended_out uint8[n]; reward_out float[n,2]; legal_out uint32[n] (bit c = column c playable in the
+ * new state, 0 when ended).  grid_out may alias grid.  All outputs optional except grid_out,
+ * player_out, winner_out. */
+int bgs_connect_step(int H, int W, int K, uint64_t n, const int8_t* grid, const int8_t* player,
+                     const int8_t* winner, const int32_t* action, int8_t* grid_out,
+                     int8_t* player_out, int8_t* winner_out, uint8_t* ended_out, float* reward_out,
+                     uint32_t* legal_out, int32_t* status, void* stream);
+
+/* State::has_ended / get_actions / get_reward (connect.cpp:39,41,43) of n existing states. */
+int bgs_connect_query(int H, int W, uint64_t n, const int8_t* grid, const int8_t* winner,
+                      uint8_t* ended_out, uint32_t* legal_out, float* reward_out, void* stream);
+
+/* Host-buffer convenience wrapper of bgs_connect_rollout + bgs_connect_export: allocates device
+ * buffers on `device`, runs, copies the requested outputs back and synchronises.
+ * final_grid optional int8[n,H,W]; reward optional float[n,2]; others as bgs_connect_rollout. */
+int bgs_connect_rollout_host(int device, int H, int W, int K, uint64_t n_games, uint64_t game_id0,
+                             uint64_t seed, uint8_t* actions, uint8_t* length, int8_t* winner,
+                             int8_t* final_grid, float* reward, int64_t* stats);
+
+/* ----------------------------------------------------------------------------------------------
+ * Bounce   --  replaces game::bounce::{Config,State,Action} as bound in bounce.cpp:24-53
+ * Boards with H*W <= 64 cells, W <= 8, piece values 1..15.
+ * -------------------------------------------------------------------------------------------- */
+
+int bgs_bounce_supported(int H, int W, int max_value);
+
+/* State::get_actions / get_actions_at (bounce.cpp:40-41) for n states:
+ * source_row int8[n]  row of the mover's movable pieces (-1: none / ended)
+ * targets uint64[n,W] bit (y*W+x) of targets[i][sx] set <=> (sx, source_row) -> (x, y) is legal
+ * count   optional int32[n] total number of legal actions. `ended` optional uint8[n]. */
+int bgs_bounce_moves(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
+                     const uint8_t* ended, int8_t* source_row, uint64_t* targets, int32_t* count,
+                     void* stream);
+
+/* Batched single transition (Action::sample_next_state bounce.cpp:51, State::get_action_at :42).
+ * move int32[n,4] = (sx, sy, tx, ty). status[i] = 0 ok / 1 illegal (state copied unchanged).
+ * winner (optional int8[n], -1 none) and ended (optional uint8[n]) describe the CURRENT states.
+ * Outputs describe the NEW state; reward_out float[n,2], ended_out uint8[n]. */
+int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
+                    const int8_t* winner, const uint8_t* ended, const int32_t* move, int8_t* grid_out, int8_t* player_out,
+                    int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status,
+                    void* stream);
+
+/* Uniform-random rollouts from grid0 (HOST pointer, int8[H,W]; it is the Config, bounce.cpp:26).
+ * Action order for the uniform choice: ascending (sy, sx, ty, tx); RNG as for Connect with ctr[3]=1.
+ * moves       optional uint8[n, max_plies, 2] (source cell, target cell), cell = y*W+x, 0xFF padded
+ * length      optional uint16[n]; winner optional int8[n] (0/1/DRAW/TRUNCATED)
+ * final_grid  optional int8[n,H,W]; reward optional float[n,2]; stats optional, accumulated. */
+int bgs_bounce_rollout(const int8_t* grid0_host, int H, int W, int rules, int max_plies,
+                       uint64_t n_games, uint64_t game_id0, uint64_t seed, uint8_t* moves,
+                       uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward,
+                       int64_t* stats, void* stream);
+
+int bgs_bounce_rollout_host(int device, const int8_t* grid0_host, int H, int W, int rules,
+                            int max_plies, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                            uint8_t* moves, uint16_t* length, int8_t* winner, int8_t* final_grid,
+                            float* reward, int64_t* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGS_B200_H */

@@ -1,0 +1,110 @@
+"""Parity of the CUDA Bounce path against the oracle and the reference's pictured positions."""
+import numpy as np
+import pytest
+import torch
+
+import golden_replay
+from conftest import DEFAULT_BOUNCE_GRID
+
+pytestmark = pytest.mark.gpu
+
+GRID = np.array(DEFAULT_BOUNCE_GRID, dtype=np.int8)
+SMALL = np.array([[0, 0, 0], [1, 2, 3], [0, 0, 0], [0, 0, 0], [1, 2, 3], [0, 0, 0]], dtype=np.int8)
+BIG_VALUES = np.array(
+    [[0] * 6, [1, 0, 4, 0, 7, 2], [0] * 6, [0, 5, 0, 0, 0, 0], [0] * 6, [0] * 6, [0, 0, 6, 0, 0, 0], [3, 0, 7, 1, 0, 2], [0] * 6],
+    dtype=np.int8,
+)
+
+
+def test_golden_positions_through_the_object_api(golden):
+    """All 16 pictured Bounce positions of the reference (exhaustive target sets, wins, blocked
+    victory, draw, JSON) through simulator.game.bounce on the GPU."""
+    from simulator.game import bounce
+
+    assert golden_replay.replay_bounce(bounce, golden) == 16
+    golden_replay.replay_bounce_json(bounce, golden)
+
+
+@pytest.mark.parametrize("rules", [0, 1, 2, 4, 5, 6])
+@pytest.mark.parametrize("grid0", [GRID, SMALL, BIG_VALUES], ids=["default", "small", "big_values"])
+def test_rollouts_equal_oracle(oracle, grid0, rules):
+    from simulator import batch
+
+    n, cap = 1500, 96
+    res = batch.bounce_rollout(grid0, n, seed=3, game_id0=17, max_plies=cap, rules=rules,
+                               moves=True, final_grid=True, reward=True)
+    ref = oracle.bounce_rollout(grid0, n, max_plies=cap, gid0=17, seed=3, rules=rules)
+    np.testing.assert_array_equal(res.length.cpu().numpy().astype(np.uint16), ref["length"])
+    np.testing.assert_array_equal(res.winner.cpu().numpy(), ref["winner"])
+    np.testing.assert_array_equal(res.actions.cpu().numpy(), ref["moves"])
+    np.testing.assert_array_equal(res.final_grid.cpu().numpy(), ref["final_grid"])
+    np.testing.assert_array_equal(res.reward.cpu().numpy(), ref["reward"])
+    np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"])
+
+
+def test_replay_default_games_through_the_oracle(oracle):
+    from simulator import batch
+
+    n, cap = 50000, 512
+    res = batch.bounce_rollout(GRID, n, seed=1, max_plies=cap, moves=True, final_grid=True, reward=True)
+    bad, first = oracle.bounce_replay(
+        GRID, res.actions.cpu().numpy(), res.length.cpu().numpy().astype(np.uint16), res.winner.cpu().numpy(),
+        res.final_grid.cpu().numpy(), res.reward.cpu().numpy())
+    assert (bad, first) == (0, -1)
+    s = res.stats_dict()
+    assert s["games"] == n and abs(s["steps"] / n - 28.9) < 1.0 and s["truncated"] <= n // 1000
+
+
+def test_moves_and_step_kernels_equal_oracle(oracle):
+    """BounceBatch.moves / step on states sampled from random play, with illegal moves mixed in."""
+    from simulator import batch
+
+    rng = np.random.default_rng(0)
+    H, W = GRID.shape
+    n = 256
+    b = batch.BounceBatch.initial(GRID, n)
+    grids = np.repeat(GRID[None], n, 0)
+    players = np.zeros(n, np.int64)
+    ended = np.zeros(n, bool)
+    winners = np.full(n, -1, np.int64)
+    for _ in range(40):
+        row, targets, count = (t.cpu().numpy() for t in b.moves())
+        moves = np.zeros((n, 4), np.int32)
+        for i in range(n):
+            acts = oracle.bounce_actions(grids[i], players[i], ended[i])
+            assert count[i] == len(acts)
+            got = []
+            for sx in range(W):
+                m = int(targets[i, sx]) & (2**64 - 1)
+                got += [(sx, int(row[i]), c % W, c // W) for c in range(H * W) if (m >> c) & 1]
+            assert got == [tuple(a) for a in acts]
+            if len(acts) and rng.random() < 0.9:
+                moves[i] = acts[rng.integers(len(acts))]
+            else:
+                moves[i] = rng.integers(-1, 10, size=4)
+        nb, status = b.step(torch.from_numpy(moves))
+        status = status.cpu().numpy()
+        for i in range(n):
+            nxt = oracle.bounce_next(grids[i], players[i], ended[i], *[int(v) for v in moves[i]])
+            assert (nxt is None) == (status[i] == 1), (i, moves[i])
+            if nxt is not None:
+                grids[i], players[i], winners[i], ended[i] = nxt
+        np.testing.assert_array_equal(nb.grid.cpu().numpy(), grids)
+        np.testing.assert_array_equal(nb.player.cpu().numpy(), players)
+        np.testing.assert_array_equal(nb.has_ended.cpu().numpy().astype(bool), ended)
+        np.testing.assert_array_equal(nb.winner.cpu().numpy(), winners)
+        b = nb
+    assert ended.mean() > 0.3
+
+
+def test_truncation_and_unsupported_boards():
+    from simulator import batch
+
+    res = batch.bounce_rollout(GRID, 2000, seed=0, max_plies=6)
+    s = res.stats_dict()
+    assert s["truncated"] > 0 and s["truncated"] == int((res.winner == -2).sum())
+    assert int(res.length.max()) == 6
+    with pytest.raises(RuntimeError):
+        batch.bounce_rollout(np.ones((9, 9), np.int8), 10)
+    with pytest.raises(RuntimeError):
+        batch.bounce_rollout(np.full((4, 4), 16, np.int8), 10)

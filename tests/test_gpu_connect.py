@@ -1,0 +1,249 @@
+"""Parity of the CUDA Connect-k path against the oracle (bit-exact: all integer / byte work).
+
+Everything here calls the product through its public Python API, which calls the C ABI of
+libbgs_b200.so; the oracle is only the checker."""
+import numpy as np
+import pytest
+import torch
+
+import golden_replay
+
+pytestmark = pytest.mark.gpu
+
+BOARDS = [(6, 7, 4), (8, 9, 5), (10, 12, 6)]
+ODD_BOARDS = [(2, 3, 2), (1, 1, 1), (1, 5, 2), (5, 1, 3), (4, 4, 5), (7, 8, 4), (3, 16, 3), (15, 8, 4), (8, 16, 7), (6, 7, 1)]
+
+
+def _run(cfg, n, seed=0, gid0=0, **kw):
+    from simulator import batch
+
+    res = batch.connect_rollout(cfg, n, seed, gid0, per_game=True, actions=True, final_grid=True, reward=True, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def _assert_equal_to_oracle(oracle, cfg, res, n, seed, gid0):
+    ref = oracle.connect_rollout(*cfg, n, gid0=gid0, seed=seed)
+    np.testing.assert_array_equal(res.length.cpu().numpy(), ref["length"])
+    np.testing.assert_array_equal(res.winner.cpu().numpy(), ref["winner"])
+    np.testing.assert_array_equal(res.actions.cpu().numpy(), ref["actions"])
+    np.testing.assert_array_equal(res.final_grid.cpu().numpy(), ref["final_grid"])
+    np.testing.assert_array_equal(res.reward.cpu().numpy(), ref["reward"])
+    np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"])
+
+
+def test_native_library_is_the_one_running():
+    from simulator import _native as N
+
+    assert N.lib().bgs_version() == 100 and N.device_count() >= 1
+    import os
+
+    maps = open("/proc/self/maps").read()
+    assert os.path.realpath(N.LIB_PATH) in maps
+
+
+@pytest.mark.parametrize("cfg", BOARDS)
+def test_rollout_trajectories_equal_oracle(oracle, cfg):
+    n = 30000 if cfg == (6, 7, 4) else 6000
+    for seed, gid0 in ((0, 0), (0xDEADBEEFCAFEF00D, 2**40 + 12345)):
+        _assert_equal_to_oracle(oracle, cfg, _run(cfg, n, seed, gid0), n, seed, gid0)
+
+
+@pytest.mark.parametrize("cfg", ODD_BOARDS)
+def test_rollout_generic_boards_equal_oracle(oracle, cfg):
+    _assert_equal_to_oracle(oracle, cfg, _run(cfg, 3000, 5, 77), 3000, 5, 77)
+
+
+def test_ragged_and_tiny_batches(oracle):
+    for n in (1, 2, 31, 33, 255, 257):
+        _assert_equal_to_oracle(oracle, (6, 7, 4), _run((6, 7, 4), n, 9, 3), n, 9, 3)
+    from simulator import batch
+
+    res = batch.connect_rollout((6, 7, 4), 0)
+    assert res.length.numel() == 0 and int(res.stats.sum()) == 0
+
+
+def test_replay_one_million_games_through_the_oracle(oracle):
+    """BASELINE.json: 100% bit-exact replay agreement on >= 1e6 sampled games (6x7x4)."""
+    n = 1_048_576
+    res = _run((6, 7, 4), n, seed=20261018, gid0=0)
+    bad, first = oracle.connect_replay(
+        6, 7, 4, res.actions.cpu().numpy(), res.length.cpu().numpy(), res.winner.cpu().numpy(),
+        res.final_grid.cpu().numpy(), res.reward.cpu().numpy(),
+    )
+    assert (bad, first) == (0, -1)
+    s = res.stats_dict()
+    assert s["games"] == n and s["wins0"] + s["wins1"] + s["draws"] == n
+    assert s["steps"] == int(res.length.sum(dtype=torch.int64))
+    assert abs(s["steps"] / n - 21.35) < 0.15 and abs(s["wins0"] / n - 0.556) < 0.01
+
+
+@pytest.mark.parametrize("cfg", [(8, 9, 5), (10, 12, 6)])
+def test_replay_larger_boards_through_the_oracle(oracle, cfg):
+    n = 60000
+    res = _run(cfg, n, seed=11)
+    bad, first = oracle.connect_replay(
+        *cfg, res.actions.cpu().numpy(), res.length.cpu().numpy(), res.winner.cpu().numpy(),
+        res.final_grid.cpu().numpy(), res.reward.cpu().numpy(),
+    )
+    assert (bad, first) == (0, -1)
+
+
+def test_sharding_is_invisible(oracle):
+    """Per-game streams are keyed by the GLOBAL game id: 1, 2, 4 or 8 shards give the same games,
+    and the summed statistics equal the single-shard statistics (test T4)."""
+    from simulator import batch
+
+    n = 40001
+    full = _run((6, 7, 4), n, seed=4)
+    for world in (2, 8):
+        stats = torch.zeros_like(full.stats)
+        acts = []
+        for r in range(world):
+            start, count = batch.shard_range(n, r, world)
+            part = batch.connect_rollout((6, 7, 4), count, 4, start, actions=True)
+            stats += part.stats
+            acts.append(part.actions)
+        assert torch.equal(torch.cat(acts), full.actions)
+        assert torch.equal(stats, full.stats)
+
+
+def test_full_size_invariants():
+    """16 Mi concurrent games (BASELINE.json configs[1]): size-independent properties."""
+    from simulator import batch
+
+    n = 16 * 2**20
+    res = batch.connect_rollout((6, 7, 4), n, seed=1, per_game=True)
+    torch.cuda.synchronize()
+    s = res.stats.cpu().numpy()
+    assert s[0] == n and s[1] + s[2] + s[3] == n
+    hist = s[16:]
+    assert hist.sum() == n and (hist * np.arange(len(hist))).sum() == s[4]
+    assert hist[:7].sum() == 0 and hist[43:].sum() == 0
+    L = res.length.to(torch.int64)
+    assert int(L.sum()) == s[4]
+    assert torch.equal(torch.bincount(L, minlength=len(hist)).cpu(), torch.from_numpy(hist))
+    w = res.winner
+    assert int((w == 0).sum()) == s[1] and int((w == 1).sum()) == s[2] and int((w == -1).sum()) == s[3]
+    # a win by player 0 takes an odd number of plies, by player 1 an even number; draws fill the board
+    assert bool(((L[w == 0] % 2) == 1).all()) and bool(((L[w == 1] % 2) == 0).all()) and bool((L[w == -1] == 42).all())
+    # determinism + idempotence: the same call gives the same bytes, another seed does not
+    again = batch.connect_rollout((6, 7, 4), n, seed=1, per_game=True)
+    assert torch.equal(again.length, res.length) and torch.equal(again.winner, res.winner)
+    other = batch.connect_rollout((6, 7, 4), 2**20, seed=2, per_game=True)
+    assert not torch.equal(other.length, res.length[: 2**20])
+
+
+def test_stats_accumulate_and_buffers_are_reused():
+    from simulator import batch
+
+    a = batch.connect_rollout((6, 7, 4), 5000, seed=1)
+    b = batch.connect_rollout((6, 7, 4), 5000, seed=1, game_id0=5000, stats=a.stats, out=a)
+    assert b.length.data_ptr() == a.length.data_ptr()
+    assert int(b.stats[0]) == 10000
+    c = batch.connect_rollout((6, 7, 4), 10000, seed=1)
+    assert torch.equal(c.stats, b.stats)
+
+
+@pytest.mark.parametrize("cfg", BOARDS + [(2, 3, 2), (4, 5, 3)])
+def test_batched_step_equals_oracle(oracle, cfg):
+    """ConnectBatch.step / legal / reward vs the oracle's transition on random play, with illegal
+    and post-terminal actions mixed in."""
+    from simulator import batch
+
+    H, W, K = cfg
+    n = 512
+    rng = np.random.default_rng(1)
+    b = batch.ConnectBatch.initial(cfg, n)
+    grids = np.full((n, H, W), -1, dtype=np.int8)
+    players = np.zeros(n, dtype=np.int64)
+    winners = np.full(n, -1, dtype=np.int64)
+    for _ in range(H * W + 2):
+        np.testing.assert_array_equal(b.grid.cpu().numpy(), grids)
+        legal_ref = np.zeros((n, W), dtype=bool)
+        ended_ref = np.zeros(n, dtype=bool)
+        for i in range(n):
+            legal_ref[i, oracle.connect_actions(grids[i], winners[i])] = True
+            ended_ref[i] = oracle.connect_ended(grids[i], winners[i])
+        np.testing.assert_array_equal(b.legal_mask().cpu().numpy(), legal_ref)
+        np.testing.assert_array_equal(b.has_ended.cpu().numpy().astype(bool), ended_ref)
+        np.testing.assert_array_equal(b.reward.cpu().numpy(), np.stack([oracle.reward(w) for w in winners]))
+        acts = rng.integers(-1, W + 1, size=n)
+        nb, status = b.step(torch.from_numpy(acts))
+        status = status.cpu().numpy()
+        for i in range(n):
+            nxt = oracle.connect_next(grids[i], K, players[i], winners[i], int(acts[i]))
+            assert (nxt is None) == (status[i] == 1)
+            if nxt is not None:
+                grids[i], players[i], winners[i] = nxt
+        np.testing.assert_array_equal(nb.player.cpu().numpy(), players)
+        np.testing.assert_array_equal(nb.winner.cpu().numpy(), winners)
+        b = nb
+    assert ended_ref.mean() > 0.3
+
+
+def test_golden_positions_through_the_object_api(golden):
+    """The reference's own pictured positions (tests/test_connect.py) through simulator.game.connect."""
+    from simulator.game import connect
+
+    assert golden_replay.replay_connect(connect, golden) == 4
+    golden_replay.replay_connect_json(connect, golden)
+
+
+def test_object_api_random_games_match_oracle(oracle):
+    import random
+
+    from simulator.game.connect import Config
+
+    random.seed(0)
+    config = Config(6, 7, 4)
+    for _ in range(3):
+        state = config.sample_initial_state()
+        grid, player, winner = np.full((6, 7), -1, np.int8), 0, -1
+        while not state.has_ended:  # the loop of reference README.md:52-69
+            assert state.player == player
+            np.testing.assert_array_equal(state.grid, grid)
+            actions = state.actions
+            assert [a.column for a in actions] == oracle.connect_actions(grid, winner)
+            action = random.choice(actions)
+            grid, player, winner = oracle.connect_next(grid, 4, player, winner, action.column)
+            state = action.sample_next_state()
+        assert oracle.connect_ended(grid, winner) and state.actions == []
+        np.testing.assert_array_equal(state.reward, oracle.reward(winner))
+        with pytest.raises(RuntimeError):
+            state.action_at(0)
+    s = config.sample_initial_state()
+    for bad in (-1, 7, 100):
+        with pytest.raises(RuntimeError):
+            s.action_at(bad)
+
+
+def test_host_buffer_c_abi_entry_point(oracle):
+    """bgs_connect_rollout_host: the call a non-Python FFI user makes (host pointers in, host out)."""
+    import ctypes as C
+
+    from simulator import _native as N
+
+    n, H, W, K = 5000, 6, 7, 4
+    actions = np.zeros((n, H * W), np.uint8)
+    length = np.zeros(n, np.uint8)
+    winner = np.zeros(n, np.int8)
+    grid = np.zeros((n, H, W), np.int8)
+    reward = np.zeros((n, 2), np.float32)
+    stats = np.zeros(256, np.int64)
+    N.check(N.lib().bgs_connect_rollout_host(
+        0, H, W, K, n, 10, 3, actions.ctypes.data, length.ctypes.data, winner.ctypes.data, grid.ctypes.data,
+        reward.ctypes.data, stats.ctypes.data))
+    ref = oracle.connect_rollout(H, W, K, n, gid0=10, seed=3)
+    for got, key in ((actions, "actions"), (length, "length"), (winner, "winner"), (grid, "final_grid"),
+                     (reward, "reward"), (stats, "stats")):
+        np.testing.assert_array_equal(got, ref[key])
+
+
+def test_dlpack_export():
+    from simulator import batch
+
+    res = batch.connect_rollout((6, 7, 4), 1000, actions=True)
+    cap = torch.utils.dlpack.to_dlpack(res.actions)
+    back = torch.utils.dlpack.from_dlpack(cap)
+    assert back.data_ptr() == res.actions.data_ptr() and back.shape == (1000, 42)

@@ -206,7 +206,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.001)
 
     def start(self):
         if self.nv is not None:

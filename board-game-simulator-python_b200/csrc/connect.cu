@@ -218,10 +218,12 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
                 const bool last_is_p0 = ((s.t - 1u) & 1u) == 0u;
                 const bb_t b0 = last_is_p0 ? s.cur : s.oth;
                 const bb_t b1 = last_is_p0 ? s.oth : s.cur;
-                uint64_t* dst = p.final_packed + idx * (2 * G::NW);
-                if (G::NW == 1) {
+                // public record format: (H*W <= 64 ? 1 : 2) words per player, whatever bb_t is
+                if (HW <= 64) {
+                    uint64_t* dst = p.final_packed + idx * 2;
                     *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2((uint64_t)b0, (uint64_t)b1);
                 } else {
+                    uint64_t* dst = p.final_packed + idx * 4;
                     reinterpret_cast<ulonglong2*>(dst)[0] =
                         make_ulonglong2((uint64_t)b0, (uint64_t)((u128)b0 >> 64));
                     reinterpret_cast<ulonglong2*>(dst)[1] =

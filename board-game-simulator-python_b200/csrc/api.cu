@@ -2,6 +2,7 @@
 #include "bgs_common.cuh"
 
 #include <cstring>
+#include <mutex>
 
 namespace bgs {
 
@@ -41,6 +42,56 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     if (dev >= 0 && dev < 64) cached[dev] = n;
     return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-device workspace.  Allocated once with cudaMalloc and never returned: stream-ordered
+// allocations (cudaMallocAsync) hand their memory back to the driver at every synchronisation
+// when the pool's release threshold is 0, which costs milliseconds on the next launch.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int kMaxDevices = 64;
+constexpr int kCounters = 1024;
+struct DeviceWorkspace {
+    unsigned int* counters = nullptr;
+    unsigned next = 0;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+DeviceWorkspace g_ws[kMaxDevices];
+std::mutex g_ws_mutex;
+}  // namespace
+
+// A claim counter for one launch (round-robin over 1024 slots, so launches in flight on different
+// streams never share one).  The caller zeroes it on its stream.
+int next_counter(unsigned int** out) {
+    int dev = 0;
+    BGS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return set_error(BGS_EINVAL, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    DeviceWorkspace& w = g_ws[dev];
+    if (!w.counters) BGS_CUDA_TRY(cudaMalloc((void**)&w.counters, kCounters * sizeof(unsigned int)));
+    *out = w.counters + (w.next++ % kCounters);
+    return BGS_OK;
+}
+
+// Write-only scratch of at least `bytes` bytes (contents are never read, so sharing it between
+// concurrent launches is harmless).
+int scratch_buffer(size_t bytes, void** out) {
+    int dev = 0;
+    BGS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return set_error(BGS_EINVAL, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    DeviceWorkspace& w = g_ws[dev];
+    if (w.scratch_bytes < bytes) {
+        if (w.scratch) BGS_CUDA_TRY(cudaFree(w.scratch));
+        w.scratch = nullptr;
+        w.scratch_bytes = 0;
+        BGS_CUDA_TRY(cudaMalloc(&w.scratch, bytes));
+        w.scratch_bytes = bytes;
+    }
+    *out = w.scratch;
+    return BGS_OK;
 }
 
 }  // namespace bgs

@@ -27,6 +27,10 @@ int require_device();  // BGS_OK or BGS_ENODEVICE
 // Number of SMs of the current device (cached per device).
 int sm_count();
 
+// Per-device workspace (api.cu): a zeroable claim counter for one launch, and write-only scratch.
+int next_counter(unsigned int** out);
+int scratch_buffer(size_t bytes, void** out);
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG (Salmon et al., SC'11).  One call yields the 4 draws of plies
 // 4b .. 4b+3 of one game: key = seed, counter = (game id lo, game id hi, b, domain).
@@ -57,30 +61,29 @@ constexpr uint32_t DOMAIN_CONNECT = 0u;
 constexpr uint32_t DOMAIN_BOUNCE = 1u;
 
 // ---------------------------------------------------------------------------------------------
-// Warp-pooled claim of game indices from a global counter.
-// Each warp owns a private pool [pool_next, pool_end) of CHUNK indices claimed with ONE atomic;
-// lanes that need a game take consecutive indices from it.  All arguments except `need` are
-// warp-uniform.  Returns this lane's index (valid only if `need`); indices >= n mean "no more work".
+// Warp-pooled claim of game indices from a global counter: the warp owns the private pool
+// [pool_next, pool_next + pool_cnt); the lanes in `m` (ballot of lanes that need a game) take
+// consecutive indices from it; ONE atomic per CHUNK (>= 32) indices.  Returns this lane's index
+// (meaningful only for lanes in `m`); indices >= n_games mean "no more work".
 // ---------------------------------------------------------------------------------------------
 template <int CHUNK>
-__device__ __forceinline__ unsigned long long warp_claim(bool need, unsigned long long* counter,
-                                                         unsigned long long& pool_next,
-                                                         unsigned long long& pool_end) {
+__device__ __forceinline__ uint32_t claim_index(unsigned m, unsigned int* counter, uint32_t& pool_next,
+                                                uint32_t& pool_cnt) {
+    static_assert(CHUNK >= 32, "one chunk must cover a whole warp");
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned m = __ballot_sync(0xffffffffu, need);
-    const unsigned want = __popc(m);
-    const unsigned rank = __popc(m & ((1u << lane) - 1u));
-    const unsigned long long avail = pool_end - pool_next;
-    unsigned long long id = pool_next + rank;
-    if (want > avail) {  // warp-uniform
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned long long)CHUNK);
+    const uint32_t want = __popc(m);
+    const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+    uint32_t id = pool_next + rank;
+    if (want > pool_cnt) {  // warp-uniform, once per CHUNK claims
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned)CHUNK);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (rank >= avail) id = base + (rank - (unsigned)avail);
-        pool_next = base + (want - (unsigned)avail);
-        pool_end = base + CHUNK;
+        if (rank >= pool_cnt) id = base + (rank - pool_cnt);
+        pool_next = base + (want - pool_cnt);
+        pool_cnt = CHUNK - (want - pool_cnt);
     } else {
         pool_next += want;
+        pool_cnt -= want;
     }
     return id;
 }

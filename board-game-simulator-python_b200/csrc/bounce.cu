@@ -187,7 +187,8 @@ __device__ __forceinline__ void store_grid(const Planes<NP>& P, int HW, int8_t* 
 // rollout kernel: one game per lane, one ply (= one full move generation) per loop iteration
 // ---------------------------------------------------------------------------------------------
 struct RolloutParams {
-    unsigned long long n_games, game_id0;
+    uint32_t n_games;  // <= 2^31 per launch
+    unsigned long long game_id0;
     uint32_t seed_lo, seed_hi;
     int max_plies;
     uint64_t plane0[4];  // bit-planes of the start position (the Config grid)
@@ -197,7 +198,7 @@ struct RolloutParams {
     int8_t* final_grid;  // [n, H*W]
     float* reward;       // [n, 2]
     unsigned long long* stats;
-    unsigned long long* counter;
+    unsigned int* counter;
 };
 
 constexpr int ROLLOUT_THREADS = 128;
@@ -218,7 +219,7 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
     for (int i = 0; i < NP; ++i) P.b[i] = 0;
     int player = 0, t = 0, win = BGS_WINNER_DRAW;
     bool alive = false, has_game = false, retired = false;
-    unsigned long long idx = 0, pool_next = 0, pool_end = 0;
+    uint32_t idx = 0, pool_next = 0, pool_cnt = 0;
     uint32_t r[4] = {0, 0, 0, 0};
     uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
     unsigned long long acc_steps = 0;
@@ -228,7 +229,7 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
         if (has_game && !alive) {
             if (p.length) p.length[idx] = (uint16_t)t;
             if (p.winner) p.winner[idx] = (int8_t)win;
-            if (p.final_grid) store_grid<NP>(P, HW, p.final_grid + idx * (unsigned long long)HW);
+            if (p.final_grid) store_grid<NP>(P, HW, p.final_grid + (size_t)idx * HW);
             if (p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(win);
             acc_w0 += (win == 0);
             acc_w1 += (win == 1);
@@ -239,8 +240,9 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
             has_game = false;
         }
         const bool need = !has_game && !retired;
-        if (__any_sync(0xffffffffu, need)) {
-            const unsigned long long id = warp_claim<CLAIM_CHUNK>(need, p.counter, pool_next, pool_end);
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
             if (need) {
                 if (id < p.n_games) {
                     idx = id;
@@ -288,7 +290,7 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
                 const int scell = row * g.W + sx;
                 const int tcell = nth_set_bit(tm, k);
                 if (p.moves) {
-                    uint8_t* m = p.moves + (idx * (unsigned long long)p.max_plies + (unsigned)t) * 2ull;
+                    uint8_t* m = p.moves + ((size_t)idx * p.max_plies + (unsigned)t) * 2ull;
                     *reinterpret_cast<uchar2*>(m) = make_uchar2((unsigned char)scell, (unsigned char)tcell);
                 }
                 move_piece<NP>(P, scell, tcell);
@@ -457,7 +459,7 @@ static int launch_bounce_rollout(const Geo& g, const RolloutParams& p, cudaStrea
     int per_sm = 0;
     BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ROLLOUT_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
-    unsigned long long want = (p.n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+    unsigned long long want = ((unsigned long long)p.n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
     unsigned long long blocks = (unsigned long long)sm_count() * per_sm;
     if (want < blocks) blocks = want ? want : 1;
     kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(g, p);
@@ -479,12 +481,13 @@ extern "C" int bgs_bounce_rollout(const int8_t* grid0, int H, int W, int rules, 
         }
     if (!supported(H, W, maxv))
         return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d (max value %d)", H, W, maxv);
+    if (n_games > (1ull << 31)) return set_error(BGS_EINVAL, "bounce_rollout: more than 2^31 games per call");
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const Geo g = make_geo(H, W, rules);
     RolloutParams p;
-    p.n_games = n_games; p.game_id0 = game_id0;
+    p.n_games = (uint32_t)n_games; p.game_id0 = game_id0;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.max_plies = max_plies;
     for (int i = 0; i < 4; ++i) {
@@ -493,14 +496,12 @@ extern "C" int bgs_bounce_rollout(const int8_t* grid0, int H, int W, int rules, 
     }
     p.moves = moves; p.length = length; p.winner = winner; p.final_grid = final_grid; p.reward = reward;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
-    BGS_CUDA_TRY(cudaMallocAsync((void**)&p.counter, sizeof(unsigned long long), stream));
-    BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
+    unsigned int* counter = nullptr;
+    if (int rc = next_counter(&counter)) return rc;
+    p.counter = counter;
+    BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     if (moves) BGS_CUDA_TRY(cudaMemsetAsync(moves, 0xFF, n_games * (size_t)max_plies * 2, stream));
-    int rc = maxv <= 3 ? launch_bounce_rollout<2>(g, p, stream) : launch_bounce_rollout<4>(g, p, stream);
-    cudaError_t e = cudaFreeAsync(p.counter, stream);
-    if (rc) return rc;
-    if (e != cudaSuccess) return cuda_error(e, "cudaFreeAsync");
-    return BGS_OK;
+    return maxv <= 3 ? launch_bounce_rollout<2>(g, p, stream) : launch_bounce_rollout<4>(g, p, stream);
 }
 
 extern "C" int bgs_bounce_rollout_host(int device, const int8_t* grid0, int H, int W, int rules, int max_plies,

@@ -5,20 +5,23 @@
 // State::get_action_at, Action::sample_next_state, State::has_ended / get_reward / get_grid).
 //
 // Data layout
-//   * On chip a board is two bitboards (stones of the side to move / of the other side), bit index
-//     = row*W + col (row 0 = bottom), held in registers: one 64-bit word when H*W <= 64 (6x7),
-//     an unsigned __int128 otherwise (8x9 = 72 bits, 10x12 = 120 bits).  There is no sentinel
+//   * On chip a board is two bitboards (stones of player 0 / player 1), bit index
+//     = (H-1-row)*W + col, i.e. the TOP row is bits 0..W-1 (so "which columns are playable" is one
+//     LOP3 on the low word), held in registers: one 64-bit word when H*W <= 64 (6x7), an
+//     unsigned __int128 otherwise (8x9 = 72 bits, 10x12 = 120 bits).  There is no sentinel
 //     row/column: k-in-a-row is `AND of K shifted copies` masked with the set of cells from which a
 //     K-run in that direction stays on the board, so wrapped runs can never count.
-//   * Column heights and the ascending list of playable columns are nibble-packed words, so
-//     "k-th legal column" is one shift+mask and there is no per-column loop anywhere.
+//   * Generic kernel: column heights and the ascending list of playable columns are nibble-packed
+//     registers.  LUT kernel (H*W <= 64, W <= 8): see connect_rollout_lut_kernel.
 //   * In HBM: per-game records only (length u8, winner i8, optional actions u8[H*W], optional
 //     packed final board 16/32 B); grids int8[n,H,W] are produced by connect_export_kernel.
 //
 // Rollout kernel structure (persistent): grid = resident CTAs only; every lane plays one game at a
 // time.  One outer iteration = [retire finished games + claim new game ids, warp-convergent] ->
 // [one Philox4x32-10 call = the 4 draws of plies 4b..4b+3] -> [4 predicated plies].  Games start on
-// 4-ply boundaries so that the Philox call and the game-end bookkeeping are never divergent.
+// 4-ply boundaries so that the Philox call and the game-end bookkeeping are never divergent, and
+// the mover of ply slot j is statically player j & 1 (no board swap).
+#include <cstdlib>
 #include <type_traits>
 
 #include "bgs_common.cuh"
@@ -31,6 +34,8 @@ typedef unsigned __int128 u128;
 // ---------------------------------------------------------------------------------------------
 // geometry policies
 // ---------------------------------------------------------------------------------------------
+// Cells from which a K-run in direction (dc, dr) stays on the board.  `r` here is the BIT row
+// (bit = r*W + c, bit row 0 = top board row); the set of lines is symmetric under that flip.
 template <typename T>
 __host__ __device__ constexpr T valid_starts(int H, int W, int K, int dc, int dr) {
     T m = 0;
@@ -120,35 +125,78 @@ __device__ __forceinline__ bool has_run(const G& g, typename G::bb_t me) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// rollout kernel
+// rollout kernels
 // ---------------------------------------------------------------------------------------------
 struct RolloutParams {
-    unsigned long long n_games;
+    uint32_t n_games;        // <= 2^31 per launch (the host splits larger batches)
     unsigned long long game_id0;
     uint32_t seed_lo, seed_hi;
-    uint8_t* actions;        // [n, H*W] pre-filled with 0xFF, or null
-    uint8_t* length;         // [n] or null
-    int8_t* winner;          // [n] or null
-    uint64_t* final_packed;  // [n, 2*NW] or null
-    unsigned long long* stats;    // [BGS_STATS_LEN] or null
-    unsigned long long* counter;  // zero-initialised claim counter
+    uint8_t* actions;        // [n, H*W] pre-filled with 0xFF (ACTIONS variants only)
+    uint8_t* length;         // [n]
+    int8_t* winner;          // [n]
+    uint64_t* final_packed;  // [n, 2*words] (PACKED variants only)
+    unsigned long long* stats;  // [BGS_STATS_LEN] or null
+    unsigned int* counter;      // zero-initialised claim counter
+    uint32_t one;               // always 1: an IMAD multiplier ptxas cannot fold (keeps adds on the FMA pipe)
 };
 
 constexpr int ROLLOUT_THREADS = 256;
 constexpr int CLAIM_CHUNK = 64;
 
+// Block-level statistics: every finished game bumps s_hist[length]; draws (only possible on a full
+// board) are counted apart.  A game won at an odd length was won by player 0, at an even length by
+// player 1, so the win counters need no per-game arithmetic at all.
+__device__ __forceinline__ void flush_stats(const unsigned int* s_hist, unsigned int s_draws, int HW,
+                                            unsigned long long* stats) {
+    unsigned long long games = 0, steps = 0, odd = 0, even = 0;
+    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) {
+        const unsigned long long h = s_hist[i];
+        if (h) {
+            atomicAdd(&stats[BGS_STAT_HIST0 + i], h);
+            games += h;
+            steps += h * (unsigned)i;
+            if (i & 1) odd += h; else even += h;
+        }
+    }
+    games = warp_sum(games); steps = warp_sum(steps); odd = warp_sum(odd); even = warp_sum(even);
+    if ((threadIdx.x & 31) == 0 && games) {
+        atomicAdd(&stats[BGS_STAT_GAMES], games);
+        atomicAdd(&stats[BGS_STAT_STEPS], steps);
+        atomicAdd(&stats[BGS_STAT_WIN0], odd);
+        atomicAdd(&stats[BGS_STAT_WIN1], even);
+    }
+    if (threadIdx.x == 0 && s_draws) {  // draws were counted as wins of the parity class of H*W
+        atomicAdd(&stats[BGS_STAT_DRAWS], (unsigned long long)s_draws);
+        atomicAdd(&stats[(HW & 1) ? BGS_STAT_WIN0 : BGS_STAT_WIN1], 0ull - (unsigned long long)s_draws);
+    }
+}
+
+template <typename bb_t>
+__device__ __forceinline__ void store_packed(uint64_t* final_packed, uint32_t idx, int HW, bb_t b0, bb_t b1) {
+    // public record format: (H*W <= 64 ? 1 : 2) words per player, whatever bb_t is
+    if (HW <= 64) {
+        *reinterpret_cast<ulonglong2*>(final_packed + (size_t)idx * 2) = make_ulonglong2((uint64_t)b0, (uint64_t)b1);
+    } else {
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(final_packed + (size_t)idx * 4);
+        dst[0] = make_ulonglong2((uint64_t)b0, (uint64_t)((u128)b0 >> 64));
+        dst[1] = make_ulonglong2((uint64_t)b1, (uint64_t)((u128)b1 >> 64));
+    }
+}
+
+// ---- generic kernel: any supported board; legal columns / heights as nibble-packed registers ----
 template <class G>
 struct Lane {
-    typename G::bb_t cur, oth;  // stones of the side to move / the other side
-    typename G::nib_t hts;      // nibble c = stones in column c
-    typename G::nib_t cols;     // nibble j = j-th playable column (ascending)
-    uint32_t nleg;              // number of playable columns
-    uint32_t t;                 // plies played
-    bool won;                   // the last move completed a K-run
+    typename G::bb_t p[2];   // stones of player 0 / 1 (the mover of ply slot j is player j & 1)
+    typename G::nib_t hts;   // nibble c = stones in column c
+    typename G::nib_t cols;  // nibble j = j-th playable column (ascending)
+    uint32_t nleg;           // number of playable columns
+    uint32_t t;              // plies played
+    int res;                 // winner so far (BGS_WINNER_DRAW while nobody has won)
 };
 
-// One ply: pick the k-th playable column, drop, test for a win.  Returns false when the game ended.
-template <class G, bool WRITE_ACTIONS>
+// One ply of player P: pick the k-th playable column, drop, test for a win.  Returns false when the
+// game ended.
+template <class G, int P, bool ACTIONS>
 __device__ __forceinline__ bool play_ply(const G& g, Lane<G>& s, uint32_t r, uint8_t* act_row) {
     typedef typename G::bb_t bb_t;
     typedef typename G::nib_t nib_t;
@@ -163,19 +211,12 @@ __device__ __forceinline__ bool play_ply(const G& g, Lane<G>& s, uint32_t r, uin
         s.cols = (s.cols & low) | ((s.cols >> 4) & ~low);
         s.nleg -= 1;
     }
-    if (WRITE_ACTIONS) act_row[s.t] = (uint8_t)c;
+    if (ACTIONS) act_row[s.t] = (uint8_t)c;
     s.t += 1;
-    const bb_t me = s.cur | ((bb_t)1 << (h * (uint32_t)g.W() + c));
-    s.won = has_run(g, me);
-    const bool over = s.won || s.nleg == 0;
-    // the mover's stones become `oth` for the next ply; at game end keep them in `cur`
-    if (over) {
-        s.cur = me;
-    } else {
-        s.cur = s.oth;
-        s.oth = me;
-    }
-    return !over;
+    s.p[P] |= (bb_t)1 << (((uint32_t)g.H() - 1u - h) * (uint32_t)g.W() + c);
+    const bool won = has_run(g, s.p[P]);
+    if (won) s.res = P;
+    return !(won || s.nleg == 0);
 }
 
 template <class G>
@@ -185,100 +226,196 @@ __device__ __forceinline__ typename G::nib_t initial_cols(const G& g) {
     return v;
 }
 
-template <class G, bool WRITE_ACTIONS>
+template <class G, bool ACTIONS, bool PACKED>
 __global__ void __launch_bounds__(ROLLOUT_THREADS)
 connect_rollout_kernel(const G g, const RolloutParams p) {
-    typedef typename G::bb_t bb_t;
     typedef typename G::nib_t nib_t;
     __shared__ unsigned int s_hist[HIST_BINS];
+    __shared__ unsigned int s_draws;
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_draws = 0;
     __syncthreads();
 
     const int HW = g.H() * g.W();
     const nib_t cols0 = initial_cols(g);
 
     Lane<G> s;
-    s.cur = 0; s.oth = 0; s.hts = 0; s.cols = cols0; s.nleg = g.W(); s.t = 0; s.won = false;
-    bool alive = false;     // a game is in progress on this lane
-    bool has_game = false;  // the lane holds a (running or just finished) game
-    bool retired = false;   // no more game ids for this lane
-    unsigned long long idx = 0;  // index of the lane's game in [0, n)
-    unsigned long long pool_next = 0, pool_end = 0;
-    uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0;
-    unsigned long long acc_steps = 0;
+    s.p[0] = 0; s.p[1] = 0; s.hts = 0; s.cols = cols0; s.nleg = g.W(); s.t = 0; s.res = BGS_WINNER_DRAW;
+    bool alive = false;    // a game is in progress on this lane
+    bool retired = false;  // no more game indices for this lane
+    uint32_t idx = 0;      // index of the lane's game in [0, n)
+    uint32_t pool_next = 0, pool_cnt = 0;
 
     for (;;) {
         // ---- warp-convergent: retire finished games, claim new ones -------------------------
-        if (has_game && !alive) {
-            const int win = s.won ? (int)((s.t - 1u) & 1u) : BGS_WINNER_DRAW;
-            if (p.length) p.length[idx] = (uint8_t)s.t;
-            if (p.winner) p.winner[idx] = (int8_t)win;
-            if (p.final_packed) {
-                // `cur` holds the stones of the last mover = player (t-1)&1
-                const bool last_is_p0 = ((s.t - 1u) & 1u) == 0u;
-                const bb_t b0 = last_is_p0 ? s.cur : s.oth;
-                const bb_t b1 = last_is_p0 ? s.oth : s.cur;
-                // public record format: (H*W <= 64 ? 1 : 2) words per player, whatever bb_t is
-                if (HW <= 64) {
-                    uint64_t* dst = p.final_packed + idx * 2;
-                    *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2((uint64_t)b0, (uint64_t)b1);
-                } else {
-                    uint64_t* dst = p.final_packed + idx * 4;
-                    reinterpret_cast<ulonglong2*>(dst)[0] =
-                        make_ulonglong2((uint64_t)b0, (uint64_t)((u128)b0 >> 64));
-                    reinterpret_cast<ulonglong2*>(dst)[1] =
-                        make_ulonglong2((uint64_t)b1, (uint64_t)((u128)b1 >> 64));
-                }
-            }
-            acc_w0 += (win == 0);
-            acc_w1 += (win == 1);
-            acc_dr += (win < 0);
-            acc_steps += s.t;
-            atomicAdd(&s_hist[hist_bin((int)s.t)], 1u);
-            has_game = false;
+        if (!alive && s.t != 0) {
+            p.length[idx] = (uint8_t)s.t;
+            p.winner[idx] = (int8_t)s.res;
+            if (PACKED) store_packed(p.final_packed, idx, HW, s.p[0], s.p[1]);
+            atomicAdd(&s_hist[s.t], 1u);
+            if (s.res < 0) atomicAdd(&s_draws, 1u);
+            s.t = 0;
         }
-        const bool need = !has_game && !retired;
-        if (__any_sync(0xffffffffu, need)) {
-            const unsigned long long id = warp_claim<CLAIM_CHUNK>(need, p.counter, pool_next, pool_end);
-            if (need) {
+        const unsigned m = __ballot_sync(0xffffffffu, !alive && !retired);
+        if (m) {
+            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
+            if (!alive && !retired) {
                 if (id < p.n_games) {
                     idx = id;
-                    s.cur = 0; s.oth = 0; s.hts = 0; s.cols = cols0; s.nleg = g.W(); s.t = 0; s.won = false;
+                    s.p[0] = 0; s.p[1] = 0; s.hts = 0; s.cols = cols0; s.nleg = g.W(); s.res = BGS_WINNER_DRAW;
                     alive = true;
-                    has_game = true;
                 } else {
                     retired = true;
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, has_game)) break;
+        if (!__any_sync(0xffffffffu, alive)) break;
 
         // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
         const unsigned long long gid = p.game_id0 + idx;
         uint32_t r[4];
         philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), s.t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
-        uint8_t* act_row = WRITE_ACTIONS ? p.actions + idx * (unsigned long long)HW : nullptr;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (alive) alive = play_ply<G, WRITE_ACTIONS>(g, s, r[j], act_row);
-        }
+        uint8_t* act_row = ACTIONS ? p.actions + (size_t)idx * (unsigned)HW : nullptr;
+        if (alive) alive = play_ply<G, 0, ACTIONS>(g, s, r[0], act_row);
+        if (alive) alive = play_ply<G, 1, ACTIONS>(g, s, r[1], act_row);
+        if (alive) alive = play_ply<G, 0, ACTIONS>(g, s, r[2], act_row);
+        if (alive) alive = play_ply<G, 1, ACTIONS>(g, s, r[3], act_row);
     }
+    __syncthreads();
+    if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
+}
 
-    // ---- statistics: warp reduce -> global atomics ----------------------------------------------
-    if (p.stats) {
-        const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
-        const unsigned long long st = warp_sum(acc_steps);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr);
-            atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
-            atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
-            atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
-            atomicAdd(&p.stats[BGS_STAT_STEPS], st);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
-            if (s_hist[i]) atomicAdd(&p.stats[BGS_STAT_HIST0 + i], (unsigned long long)s_hist[i]);
+// ---- LUT kernel: boards with H*W <= 64 and W <= 8 (the 6x7x4 headline board) ------------------
+// The ALU pipe (LOP3/SHF, 64 lanes/clk/SM) is what bounds the rollout, so everything that is not
+// the k-in-a-row test is moved off it: the playable-column mask is ONE LOP3 (the top row is bits
+// 0..W-1), its population count runs on the XU pipe, "k-th playable column" is a shared-memory
+// table lookup (LSU pipe), column heights live in per-thread shared-memory bytes (LSU pipe) and
+// the arithmetic in between is IMAD (FMA pipe).
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
+// Integer multiply-add on the FMA pipe (IMAD); used where an add / shift-by-constant would otherwise
+// land on the saturated ALU pipe.
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t imad_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// 1 << s, or 0 when s >= 32 (PTX shl clamps the shift amount; one SHF, no compare/select)
+__device__ __forceinline__ uint32_t bit_or_zero(uint32_t s) {
+    uint32_t d;
+    asm volatile("shl.b32 %0, 1, %1;" : "=r"(d) : "r"(s));
+    return d;
+}
+
+// One ply of player P.  `lut` / `ht` are 32-bit shared-memory addresses: lut[free*8 + k] is the
+// bit index of the BOTTOM cell of the k-th playable column ((H-1)*W + c); ht is pre-biased by
+// -(H-1)*W so that ht[that index] is the number of stones in the column.
+template <int H, int W, int K, int P, bool ACTIONS>
+__device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t r, uint32_t& t, int& res,
+                                        uint32_t lut, uint32_t ht, uint8_t* act_row, uint32_t one) {
+    typedef StaticGeo<H, W, K> G;
+    const uint32_t freem = ~top_occ & ((1u << W) - 1u);                   // ALU: one LOP3
+    const uint32_t n = (uint32_t)__popc(freem);                           // XU
+    const uint32_t cb = lds_u8(imad_hi(r, n, imad(freem, 8u * one, lut)));     // FMA, FMA, LSU
+    const uint32_t hp = imad(cb, one, ht);                                // FMA
+    const uint32_t h = lds_u8(hp);                                        // LSU
+    sts_u8(hp, imad(h, one, one));                                         // FMA, LSU
+    if (ACTIONS) act_row[t] = (uint8_t)(cb - (H - 1) * W);
+    t = imad(t, one, one);                                                // FMA
+    const uint32_t cell = imad(h, (uint32_t)(-W), cb);                    // FMA
+    // the cell is empty, so adding the bit is OR-ing it, and no carry can cross the words
+    uint32_t lo = imad(bit_or_zero(cell), one, (uint32_t)me);             // ALU (SHF), FMA
+    uint32_t hi = (uint32_t)(me >> 32);
+    if (H * W > 32) hi = imad(bit_or_zero(imad(cell, one, (uint32_t)-32)), one, hi);
+    me = ((uint64_t)hi << 32) | lo;
+    const bool won = has_run(G(), me);
+    if (won) res = P;
+    return !(won || t == (uint32_t)(H * W));
+}
+
+template <int H, int W, int K, bool ACTIONS, bool PACKED>
+__global__ void __launch_bounds__(ROLLOUT_THREADS)
+connect_rollout_lut_kernel(const RolloutParams p) {
+    static_assert(H * W <= 64 && W <= 8, "LUT kernel: one 64-bit board word, at most 8 columns");
+    __shared__ unsigned int s_hist[HIST_BINS];
+    __shared__ unsigned int s_draws;
+    __shared__ uint8_t s_lut[(1 << W) * 8];                       // [free mask][k] -> k-th set bit
+    __shared__ __align__(8) uint8_t s_ht[ROLLOUT_THREADS * 8];    // [thread][column] -> stones
+    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_draws = 0;
+    for (int i = threadIdx.x; i < (1 << W) * 8; i += blockDim.x) {
+        int mask = i >> 3, k = i & 7, c = 0;
+        for (; c < W; ++c)
+            if ((mask >> c) & 1) {
+                if (k == 0) break;
+                --k;
+            }
+        s_lut[i] = (uint8_t)((H - 1) * W + (c < W ? c : 0));
     }
+    uint2* ht_row = reinterpret_cast<uint2*>(s_ht + threadIdx.x * 8);
+    *ht_row = make_uint2(0u, 0u);
+    __syncthreads();
+    const uint32_t one = p.one;
+    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_lut);
+    const uint32_t ht = (uint32_t)__cvta_generic_to_shared(ht_row) - (uint32_t)((H - 1) * W);
+
+    constexpr int HW = H * W;
+    uint64_t p0 = 0, p1 = 0;
+    uint32_t t = 0;
+    int res = BGS_WINNER_DRAW;
+    bool alive = false, retired = false;
+    uint32_t idx = 0, pool_next = 0, pool_cnt = 0;
+
+    for (;;) {
+        // ---- warp-convergent: retire finished games, claim new ones -------------------------
+        if (!alive && t != 0) {
+            p.length[idx] = (uint8_t)t;
+            p.winner[idx] = (int8_t)res;
+            if (PACKED) store_packed(p.final_packed, idx, HW, p0, p1);
+            atomicAdd(&s_hist[t], 1u);
+            if (res < 0) atomicAdd(&s_draws, 1u);
+            t = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, !alive && !retired);
+        if (m) {
+            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
+            if (!alive && !retired) {
+                if (id < p.n_games) {
+                    idx = id;
+                    p0 = 0; p1 = 0; res = BGS_WINNER_DRAW;
+                    *ht_row = make_uint2(0u, 0u);
+                    alive = true;
+                } else {
+                    retired = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+
+        // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
+        const unsigned long long gid = p.game_id0 + idx;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+        uint8_t* act_row = ACTIONS ? p.actions + (size_t)idx * HW : nullptr;
+        if (alive) alive = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[0], t, res, lut, ht, act_row, one);
+        if (alive) alive = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[1], t, res, lut, ht, act_row, one);
+        if (alive) alive = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[2], t, res, lut, ht, act_row, one);
+        if (alive) alive = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[3], t, res, lut, ht, act_row, one);
+    }
+    __syncthreads();
+    if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,18 +423,19 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
 // per game.  Each thread produces 16 consecutive output bytes and stores them with one 128-bit store.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-connect_export_grid_kernel(int HW, int NW, unsigned long long n, const uint64_t* __restrict__ packed,
+connect_export_grid_kernel(int H, int W, int NW, unsigned long long n, const uint64_t* __restrict__ packed,
                            int8_t* __restrict__ grid) {
+    const int HW = H * W;
     const unsigned long long total = n * (unsigned long long)HW;
     const unsigned long long nvec = (total + 15ull) / 16ull;
     for (unsigned long long v = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v < nvec;
          v += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long b0 = v * 16ull;
         unsigned long long game = b0 / (unsigned)HW;
-        int cell = (int)(b0 - game * (unsigned)HW);
+        const int cell0 = (int)(b0 - game * (unsigned)HW);
+        int col = cell0 % W;
+        int bit = (H - 1 - cell0 / W) * W + col;  // board row r lives in bit row H-1-r
         const uint64_t* rec = packed + game * (2 * NW);
-        uint64_t p0 = __ldg(rec + (cell >> 6));
-        uint64_t p1 = __ldg(rec + NW + (cell >> 6));
         uint32_t out[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -306,20 +444,20 @@ connect_export_grid_kernel(int HW, int NW, unsigned long long n, const uint64_t*
             for (int j = 0; j < 4; ++j) {
                 int8_t val = 0;
                 if (b0 + 4 * q + j < total) {
-                    const int bit = cell & 63;
-                    val = ((p0 >> bit) & 1ull) ? (int8_t)0 : (((p1 >> bit) & 1ull) ? (int8_t)1 : (int8_t)-1);
-                    ++cell;
-                    if (cell == HW) {
-                        cell = 0;
-                        ++game;
-                        if (game < n) {
-                            rec = packed + game * (2 * NW);
-                            p0 = __ldg(rec);
-                            p1 = __ldg(rec + NW);
+                    const uint64_t p0 = __ldg(rec + (bit >> 6));
+                    const uint64_t p1 = __ldg(rec + NW + (bit >> 6));
+                    const int sh = bit & 63;
+                    val = ((p0 >> sh) & 1ull) ? (int8_t)0 : (((p1 >> sh) & 1ull) ? (int8_t)1 : (int8_t)-1);
+                    ++col;
+                    ++bit;
+                    if (col == W) {  // next board row = previous bit row
+                        col = 0;
+                        bit -= 2 * W;
+                        if (bit < 0) {  // next game, bottom row again
+                            bit = (H - 1) * W;
+                            ++game;
+                            rec = packed + (game < n ? game : n - 1) * (2 * NW);
                         }
-                    } else if ((cell & 63) == 0) {
-                        p0 = __ldg(rec + 1);
-                        p1 = __ldg(rec + NW + 1);
                     }
                 }
                 w |= (uint32_t)(uint8_t)val << (8 * j);
@@ -358,12 +496,13 @@ struct BoardBits {
 __device__ __forceinline__ BoardBits load_grid(const int8_t* __restrict__ g, int H, int W) {
     BoardBits b;
     b.p[0] = 0; b.p[1] = 0; b.legal = 0;
-    const int HW = H * W;
-    for (int i = 0; i < HW; ++i) {
-        const int v = g[i];
-        if (v == 0) b.p[0] |= (u128)1 << i;
-        else if (v == 1) b.p[1] |= (u128)1 << i;
-    }
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+            const int v = g[r * W + c];
+            const int bit = (H - 1 - r) * W + c;
+            if (v == 0) b.p[0] |= (u128)1 << bit;
+            else if (v == 1) b.p[1] |= (u128)1 << bit;
+        }
     for (int c = 0; c < W; ++c)
         if (g[(H - 1) * W + c] < 0) b.legal |= 1u << c;
     b.full = b.legal == 0;
@@ -392,8 +531,8 @@ connect_step_kernel(const DynGeo g, unsigned long long n, const int8_t* __restri
     if (legal) {
         st = 0;
         const u128 occ = b.p[0] | b.p[1];
-        while ((occ >> (row * W + col)) & 1) ++row;  // lowest empty cell of the column
-        b.p[pl] |= (u128)1 << (row * W + col);
+        while ((occ >> ((H - 1 - row) * W + col)) & 1) ++row;  // lowest empty cell of the column
+        b.p[pl] |= (u128)1 << ((H - 1 - row) * W + col);
         if (row == H - 1) b.legal &= ~(1u << col);
         if (has_run(g, b.p[pl])) win = pl;
         b.full = b.legal == 0;
@@ -435,24 +574,34 @@ static bool supported(int H, int W, int K) {
     return H >= 1 && W >= 1 && K >= 1 && H <= 15 && W <= 16 && H * W <= 128;
 }
 
-template <class G, bool WA>
-static int launch_rollout_t(const G& g, const RolloutParams& p, cudaStream_t stream) {
-    auto kern = connect_rollout_kernel<G, WA>;
+template <typename Kern, typename... Args>
+static int launch_persistent(Kern kern, const RolloutParams& p, cudaStream_t stream, Args... args) {
     int per_sm = 0;
     BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ROLLOUT_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     // persistent launch: exactly the resident CTAs, a multiple of the SM count
-    unsigned long long want = (p.n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+    unsigned long long want = ((unsigned long long)p.n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
     unsigned long long blocks = (unsigned long long)sm_count() * per_sm;
     if (want < blocks) blocks = want ? want : 1;
-    kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(g, p);
+    kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(args..., p);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }
 
 template <class G>
 static int launch_rollout(const G& g, const RolloutParams& p, cudaStream_t stream) {
-    return p.actions ? launch_rollout_t<G, true>(g, p, stream) : launch_rollout_t<G, false>(g, p, stream);
+    if (p.actions && p.final_packed) return launch_persistent(connect_rollout_kernel<G, true, true>, p, stream, g);
+    if (p.actions) return launch_persistent(connect_rollout_kernel<G, true, false>, p, stream, g);
+    if (p.final_packed) return launch_persistent(connect_rollout_kernel<G, false, true>, p, stream, g);
+    return launch_persistent(connect_rollout_kernel<G, false, false>, p, stream, g);
+}
+
+template <int H, int W, int K>
+static int launch_rollout_lut(const RolloutParams& p, cudaStream_t stream) {
+    if (p.actions && p.final_packed) return launch_persistent(connect_rollout_lut_kernel<H, W, K, true, true>, p, stream);
+    if (p.actions) return launch_persistent(connect_rollout_lut_kernel<H, W, K, true, false>, p, stream);
+    if (p.final_packed) return launch_persistent(connect_rollout_lut_kernel<H, W, K, false, true>, p, stream);
+    return launch_persistent(connect_rollout_lut_kernel<H, W, K, false, false>, p, stream);
 }
 
 }  // namespace connect
@@ -465,6 +614,12 @@ extern "C" int bgs_connect_supported(int H, int W, int K) { return supported(H, 
 
 extern "C" int bgs_connect_packed_words(int H, int W) { return 2 * (H * W <= 64 ? 1 : 2); }
 
+// Set BGS_CONNECT_GENERIC=1 to force the generic kernel on the 6x7x4 board (A/B measurements).
+static bool force_generic() {
+    static const bool v = [] { const char* e = getenv("BGS_CONNECT_GENERIC"); return e && e[0] == '1'; }();
+    return v;
+}
+
 extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
                                    uint8_t* actions, uint8_t* length, int8_t* winner,
                                    uint64_t* final_packed, int64_t* stats, void* stream_) {
@@ -472,28 +627,43 @@ extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    RolloutParams p;
-    p.n_games = n_games;
-    p.game_id0 = game_id0;
-    p.seed_lo = (uint32_t)seed;
-    p.seed_hi = (uint32_t)(seed >> 32);
-    p.actions = actions;
-    p.length = length;
-    p.winner = winner;
-    p.final_packed = final_packed;
-    p.stats = reinterpret_cast<unsigned long long*>(stats);
-    BGS_CUDA_TRY(cudaMallocAsync((void**)&p.counter, sizeof(unsigned long long), stream));
-    BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream));
-    if (actions) BGS_CUDA_TRY(cudaMemsetAsync(actions, 0xFF, n_games * (size_t)(H * W), stream));
-    int rc;
-    if (H == 6 && W == 7 && K == 4) rc = launch_rollout(StaticGeo<6, 7, 4>(), p, stream);
-    else if (H == 8 && W == 9 && K == 5) rc = launch_rollout(StaticGeo<8, 9, 5>(), p, stream);
-    else if (H == 10 && W == 12 && K == 6) rc = launch_rollout(StaticGeo<10, 12, 6>(), p, stream);
-    else rc = launch_rollout(make_dyn_geo(H, W, K), p, stream);
-    cudaError_t e = cudaFreeAsync(p.counter, stream);
-    if (rc) return rc;
-    if (e != cudaSuccess) return cuda_error(e, "cudaFreeAsync");
-    return BGS_OK;
+    const size_t HW = (size_t)H * W;
+    const int PW = bgs_connect_packed_words(H, W);
+    // the kernels always write length and winner: point the unwanted one at write-only scratch
+    uint8_t* scratch = nullptr;
+    const uint64_t max_launch = 1ull << 31;
+    if (!length || !winner) {
+        if (int rc = scratch_buffer((size_t)(n_games < max_launch ? n_games : max_launch), (void**)&scratch)) return rc;
+    }
+    unsigned int* counter = nullptr;
+    int rc = next_counter(&counter);
+    cudaError_t e = cudaSuccess;
+    if (rc == BGS_OK && actions) {
+        e = cudaMemsetAsync(actions, 0xFF, n_games * HW, stream);
+        if (e != cudaSuccess) rc = cuda_error(e, "cudaMemsetAsync");
+    }
+    for (uint64_t off = 0; rc == BGS_OK && off < n_games; off += max_launch) {
+        RolloutParams p;
+        p.n_games = (uint32_t)((n_games - off) < max_launch ? (n_games - off) : max_launch);
+        p.game_id0 = game_id0 + off;
+        p.seed_lo = (uint32_t)seed;
+        p.seed_hi = (uint32_t)(seed >> 32);
+        p.actions = actions ? actions + off * HW : nullptr;
+        p.length = length ? length + off : scratch;
+        p.winner = winner ? winner + off : reinterpret_cast<int8_t*>(scratch);
+        p.final_packed = final_packed ? final_packed + off * PW : nullptr;
+        p.stats = reinterpret_cast<unsigned long long*>(stats);
+        p.counter = counter;
+        p.one = 1u;
+        e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) { rc = cuda_error(e, "cudaMemsetAsync"); break; }
+        if (H == 6 && W == 7 && K == 4 && !force_generic()) rc = launch_rollout_lut<6, 7, 4>(p, stream);
+        else if (H == 6 && W == 7 && K == 4) rc = launch_rollout(StaticGeo<6, 7, 4>(), p, stream);
+        else if (H == 8 && W == 9 && K == 5) rc = launch_rollout(StaticGeo<8, 9, 5>(), p, stream);
+        else if (H == 10 && W == 12 && K == 6) rc = launch_rollout(StaticGeo<10, 12, 6>(), p, stream);
+        else rc = launch_rollout(make_dyn_geo(H, W, K), p, stream);
+    }
+    return rc;
 }
 
 extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,
@@ -510,7 +680,7 @@ extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* pack
         unsigned long long blocks = (nvec + 255) / 256;
         const unsigned long long cap = (unsigned long long)sms * 8 * 4;
         if (blocks > cap) blocks = cap;
-        connect_export_grid_kernel<<<(unsigned)blocks, 256, 0, stream>>>(H * W, NW, n, packed, grid);
+        connect_export_grid_kernel<<<(unsigned)blocks, 256, 0, stream>>>(H, W, NW, n, packed, grid);
         BGS_CUDA_TRY(cudaGetLastError());
     }
     if (reward) {

@@ -73,7 +73,8 @@ int bgs_device_count(void);
 int bgs_connect_supported(int H, int W, int K);
 
 /* Number of uint64 words per game in the packed board format used by *_packed / export:
- * [stones of player 0 | stones of player 1], each (H*W <= 64 ? 1 : 2) words, bit index = col*H + row. */
+ * [stones of player 0 | stones of player 1], each (H*W <= 64 ? 1 : 2) words, little-endian word order,
+ * bit index of cell (row, col) = (H-1-row)*W + col (the top row occupies bits 0..W-1). */
 int bgs_connect_packed_words(int H, int W);
 
 /* The whole rollout loop of README.md:49-72 for n_games independent games from the empty board:

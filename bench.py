@@ -366,7 +366,7 @@ def run_b200(args):
             "roofline": {
                 "bound": "int_issue", "achieved": achieved, "peak": peak, "unit": "G thread-instr/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": "connect_rollout_kernel<StaticGeo<6,7,4>,false>",
+                "kernel": "connect_rollout_lut_kernel<6,7,4,false,false>",
                 "kernel_ms_per_launch": 1e3 * kernel_s / args.steps,
                 "kernel_env_steps_per_s": ksteps / kernel_s,
                 "algorithmic_ops_per_env_step": OPS_PER_STEP,

@@ -81,27 +81,106 @@ __device__ __forceinline__ uint64_t source_row_mask(const Geo& g, uint64_t occ, 
     return g.row0 << (y * g.W);
 }
 
-// All targets of the piece on `sbit` (value v) for `player` -- SURVEY.md 4.4 rule 3.
+// Move generation for `player` -- SURVEY.md 4.4 rules 2-4 -- as ONE flat loop per lane.
+//
+// A lane walks its own work list: for every movable piece (ascending column) a sequence of segments,
+// for every segment `u` frontier steps.  Each loop iteration performs exactly one frontier step of
+// whatever (piece, segment) the lane is at; the bookkeeping between segments / pieces is a short
+// branch at the top.  Lanes of a warp therefore stay busy until the lane with the most steps is
+// done, instead of serialising over columns and bounce rounds (the nested formulation ran at 5 of 32
+// active lanes).
+//
+// ANY = false: writes the target mask of the piece in column x to T[x*stride] (0 where there is no
+//              movable piece) and returns the number of (source, target) pairs; *row = source row.
+// ANY = true : returns 1 as soon as one piece has a target, else 0 (T is not touched).
+template <int NP, bool ANY>
+__device__ __forceinline__ int movegen(const Geo& g, const Planes<NP>& P, int player, uint64_t* T, int stride,
+                                       int* row) {
+    const uint64_t occ = P.occ();
+    const uint64_t rowm = source_row_mask(g, occ, player, row);
+    if (!ANY)
+        for (int x = 0; x < g.W; ++x) T[x * stride] = 0ull;
+    const int base = *row * g.W;
+    const int variant = g.rules & 3;
+    const bool allow_null = (g.rules & BGS_BOUNCE_ALLOW_NULL_MOVE) != 0;
+    const uint64_t farm = g.far(player);
+    uint64_t src_left = rowm & occ;
+    uint64_t sbit = 0, occS = 0, open = 0, inter = 0, expanded = 0, pending = 0, targets = 0;
+    uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = 0;  // frontier by last direction: forward / left / right / none
+    int rem = 0, xs = 0, total = 0;
+    bool have = false;
+    for (;;) {
+        if (rem == 0) {  // between segments
+            int u;
+            uint64_t S;
+            if (pending == 0) {  // between pieces
+                if (have) {
+                    if (!allow_null) targets &= ~sbit;
+                    if (ANY) {
+                        if (targets) return 1;
+                    } else {
+                        T[xs * stride] = targets;
+                        total += __popcll(targets);
+                    }
+                }
+                if (src_left == 0) break;
+                sbit = src_left & (~src_left + 1ull);
+                src_left ^= sbit;
+                have = true;
+                const int cell = __ffsll((long long)sbit) - 1;
+                xs = cell - base;
+                occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
+                open = variant == BGS_BOUNCE_SOURCE_BLOCKED ? (g.board & ~sbit) : g.board;
+                inter = open & ~occS & ~farm;  // cells a path may pass through
+                expanded = sbit;
+                targets = 0;
+                S = sbit;
+                u = P.value_at(cell);
+            } else {  // bounce: all unexpanded landing cells that hold a piece of the same value
+                const int c = __ffsll((long long)pending) - 1;
+                u = P.value_at(c);
+                S = pending & P.cells_with_value(u);
+                pending &= ~S;
+                expanded |= S;
+            }
+            Ff = 0; Fl = 0; Fr = 0; Nn = S;  // no direction memory at the start of a segment
+            rem = u;
+        }
+        // one step of the current segment, all frontier cells at once
+        const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn;  // may go left / right (no reversal)
+        const uint64_t all = fl | Fr;
+        const uint64_t nf = player == 0 ? (all << g.W) : (all >> g.W);  // never backwards
+        const uint64_t nl = (fl & g.not_left) >> 1;
+        const uint64_t nr = (fr & g.not_right) << 1;
+        if (rem > 1) {  // intermediate cells: empty, not the far goal row
+            Ff = nf & inter; Fl = nl & inter; Fr = nr & inter; Nn = 0;
+            rem = (Ff | Fl | Fr) ? rem - 1 : 0;
+        } else {        // last step: rest on an empty cell, or bounce off a piece
+            const uint64_t land = (nf | nl | nr) & open;
+            targets |= land & ~occS;
+            pending |= land & occS & ~expanded;
+            rem = 0;
+        }
+    }
+    return ANY ? 0 : total;
+}
+
+// All targets of the single piece on (cell) -- used by the batched step kernel to validate a move.
 template <int NP>
 __device__ __forceinline__ uint64_t targets_of(const Geo& g, const Planes<NP>& P, uint64_t occ, int player,
                                                uint64_t sbit, int v) {
     const int variant = g.rules & 3;
     const uint64_t occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
-    const uint64_t wall = variant == BGS_BOUNCE_SOURCE_BLOCKED ? sbit : 0ull;
-    const uint64_t open = g.board & ~wall;
-    const uint64_t inter = open & ~occS & ~g.far(player);  // cells a path may pass through
-    uint64_t expanded = sbit, pending = 0, targets = 0;
-    uint64_t S = sbit;
+    const uint64_t open = variant == BGS_BOUNCE_SOURCE_BLOCKED ? (g.board & ~sbit) : g.board;
+    const uint64_t inter = open & ~occS & ~g.far(player);
+    uint64_t expanded = sbit, pending = 0, targets = 0, S = sbit;
     int u = v;
     for (;;) {
-        // one segment of exactly u steps from every cell of S (no direction memory at the start)
         uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = S, land = 0;
         for (int step = u; step >= 1; --step) {
-            const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn;  // may go left / right (no reversal)
-            const uint64_t all = fl | Fr;
-            uint64_t nf = player == 0 ? (all << g.W) : (all >> g.W);  // never backwards
-            uint64_t nl = (fl & g.not_left) >> 1;
-            uint64_t nr = (fr & g.not_right) << 1;
+            const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn, all = fl | Fr;
+            const uint64_t nf = player == 0 ? (all << g.W) : (all >> g.W);
+            const uint64_t nl = (fl & g.not_left) >> 1, nr = (fr & g.not_right) << 1;
             if (step > 1) {
                 Ff = nf & inter; Fl = nl & inter; Fr = nr & inter; Nn = 0;
                 if (!(Ff | Fl | Fr)) break;
@@ -109,8 +188,8 @@ __device__ __forceinline__ uint64_t targets_of(const Geo& g, const Planes<NP>& P
                 land = (nf | nl | nr) & open;
             }
         }
-        targets |= land & ~occS;              // final resting cell must be empty (far row included)
-        pending |= land & occS & ~expanded;   // landed exactly on a piece: bounce with its value
+        targets |= land & ~occS;
+        pending |= land & occS & ~expanded;
         if (!pending) break;
         const int c = __ffsll((long long)pending) - 1;
         u = P.value_at(c);
@@ -122,40 +201,10 @@ __device__ __forceinline__ uint64_t targets_of(const Geo& g, const Planes<NP>& P
     return targets;
 }
 
-// Target masks of every movable piece of `player`, indexed by source column, into T[x*stride].
-// Returns the total number of (source, target) pairs; *row = the source row.
-template <int NP>
-__device__ __forceinline__ int movegen(const Geo& g, const Planes<NP>& P, int player, uint64_t* T, int stride,
-                                       int* row) {
-    const uint64_t occ = P.occ();
-    const uint64_t rowm = source_row_mask(g, occ, player, row);
-    int total = 0;
-    const int base = *row * g.W;
-    for (int x = 0; x < g.W; ++x) {
-        uint64_t t = 0;
-        if (rowm) {
-            const uint64_t sbit = 1ull << (base + x);
-            if (occ & sbit) t = targets_of<NP>(g, P, occ, player, sbit, P.value_at(base + x));
-        }
-        T[x * stride] = t;
-        total += __popcll(t);
-    }
-    return total;
-}
-
-// Does `player` have at least one legal action?  (early exit on the first piece that has a target)
 template <int NP>
 __device__ __forceinline__ bool has_any(const Geo& g, const Planes<NP>& P, int player) {
-    const uint64_t occ = P.occ();
     int row;
-    uint64_t src = source_row_mask(g, occ, player, &row) & occ;
-    while (src) {
-        const uint64_t sbit = src & (~src + 1ull);
-        src ^= sbit;
-        const int cell = __ffsll((long long)sbit) - 1;
-        if (targets_of<NP>(g, P, occ, player, sbit, P.value_at(cell))) return true;
-    }
-    return false;
+    return movegen<NP, true>(g, P, player, nullptr, 0, &row) != 0;
 }
 
 template <int NP>
@@ -260,7 +309,7 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
 
         if (alive) {
             int row;
-            const int total = movegen<NP>(g, P, player, T, ROLLOUT_THREADS, &row);
+            const int total = movegen<NP, false>(g, P, player, T, ROLLOUT_THREADS, &row);
             if (total == 0) {
                 // the side to move is blocked: the previous mover wins unless it would be blocked
                 // too (tests/test_bounce.py:323-362); a blocked start position is a draw
@@ -354,7 +403,7 @@ bounce_moves_kernel(const Geo g, unsigned long long n, const int8_t* __restrict_
     int row = -1, total = 0;
     const bool over = (ended && ended[i]) || !ok;
     const int pl = player[i] & 1;
-    if (!over) total = movegen<4>(g, P, pl, T, STEP_THREADS, &row);
+    if (!over) total = movegen<4, false>(g, P, pl, T, STEP_THREADS, &row);
     for (int x = 0; x < g.W; ++x) targets[i * g.W + x] = over ? 0ull : T[x * STEP_THREADS];
     if (source_row) source_row[i] = (int8_t)(total > 0 ? row : -1);
     if (count) count[i] = ok ? total : -1;

@@ -196,8 +196,12 @@ struct Lane {
 
 // One ply of player P: pick the k-th playable column, drop, test for a win.  Returns false when the
 // game ended.
-template <class G, int P, bool ACTIONS>
-__device__ __forceinline__ bool play_ply(const G& g, Lane<G>& s, uint32_t r, uint8_t* act_row) {
+// ACT: 0 = no trajectory, 1 = one byte per ply straight into the (0xFF pre-filled) row, 2 = four
+// 4-bit columns per 16-bit word, stored once per 4-ply block at the start of the game's own row and
+// expanded in place by connect_export_actions_kernel.
+template <class G, int J, int ACT>
+__device__ __forceinline__ bool play_ply(const G& g, Lane<G>& s, uint32_t r, uint8_t* act_row, uint32_t& blk) {
+    constexpr int P = J & 1;
     typedef typename G::bb_t bb_t;
     typedef typename G::nib_t nib_t;
     const uint32_t k = __umulhi(r, s.nleg);
@@ -211,7 +215,8 @@ __device__ __forceinline__ bool play_ply(const G& g, Lane<G>& s, uint32_t r, uin
         s.cols = (s.cols & low) | ((s.cols >> 4) & ~low);
         s.nleg -= 1;
     }
-    if (ACTIONS) act_row[s.t] = (uint8_t)c;
+    if (ACT == 1) act_row[s.t] = (uint8_t)c;
+    if (ACT == 2) blk |= c << (4 * J);
     s.t += 1;
     s.p[P] |= (bb_t)1 << (((uint32_t)g.H() - 1u - h) * (uint32_t)g.W() + c);
     const bool won = has_run(g, s.p[P]);
@@ -226,7 +231,7 @@ __device__ __forceinline__ typename G::nib_t initial_cols(const G& g) {
     return v;
 }
 
-template <class G, bool ACTIONS, bool PACKED>
+template <class G, int ACT, bool PACKED>
 __global__ void __launch_bounds__(ROLLOUT_THREADS)
 connect_rollout_kernel(const G g, const RolloutParams p) {
     typedef typename G::nib_t nib_t;
@@ -275,11 +280,15 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
         const unsigned long long gid = p.game_id0 + idx;
         uint32_t r[4];
         philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), s.t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
-        uint8_t* act_row = ACTIONS ? p.actions + (size_t)idx * (unsigned)HW : nullptr;
-        if (alive) alive = play_ply<G, 0, ACTIONS>(g, s, r[0], act_row);
-        if (alive) alive = play_ply<G, 1, ACTIONS>(g, s, r[1], act_row);
-        if (alive) alive = play_ply<G, 0, ACTIONS>(g, s, r[2], act_row);
-        if (alive) alive = play_ply<G, 1, ACTIONS>(g, s, r[3], act_row);
+        uint8_t* act_row = ACT ? p.actions + (size_t)idx * (unsigned)HW : nullptr;
+        const bool started = alive;
+        const uint32_t tb = s.t;
+        uint32_t blk = 0;
+        if (alive) alive = play_ply<G, 0, ACT>(g, s, r[0], act_row, blk);
+        if (alive) alive = play_ply<G, 1, ACT>(g, s, r[1], act_row, blk);
+        if (alive) alive = play_ply<G, 2, ACT>(g, s, r[2], act_row, blk);
+        if (alive) alive = play_ply<G, 3, ACT>(g, s, r[3], act_row, blk);
+        if (ACT == 2 && started) *reinterpret_cast<uint16_t*>(act_row + (tb >> 1)) = (uint16_t)blk;
     }
     __syncthreads();
     if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
@@ -322,17 +331,18 @@ __device__ __forceinline__ uint32_t bit_or_zero(uint32_t s) {
 // One ply of player P.  `lut` / `ht` are 32-bit shared-memory addresses: lut[free*8 + k] is the
 // bit index of the BOTTOM cell of the k-th playable column ((H-1)*W + c); ht is pre-biased by
 // -(H-1)*W so that ht[that index] is the number of stones in the column.
-template <int H, int W, int K, int P, bool ACTIONS>
+template <int H, int W, int K, int J, bool ACTIONS>
 __device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t r, uint32_t& t, int& res,
-                                        uint32_t lut, uint32_t ht, uint8_t* act_row, uint32_t one) {
+                                        uint32_t lut, uint32_t ht, uint32_t& blk, uint32_t one) {
     typedef StaticGeo<H, W, K> G;
+    constexpr int P = J & 1;
     const uint32_t freem = ~top_occ & ((1u << W) - 1u);                   // ALU: one LOP3
     const uint32_t n = (uint32_t)__popc(freem);                           // XU
     const uint32_t cb = lds_u8(imad_hi(r, n, imad(freem, 8u * one, lut)));     // FMA, FMA, LSU
     const uint32_t hp = imad(cb, one, ht);                                // FMA
     const uint32_t h = lds_u8(hp);                                        // LSU
     sts_u8(hp, imad(h, one, one));                                         // FMA, LSU
-    if (ACTIONS) act_row[t] = (uint8_t)(cb - (H - 1) * W);
+    if (ACTIONS) blk = imad(cb, (1u << (4 * J)) * one, blk);            // FMA (bias removed at the block end)
     t = imad(t, one, one);                                                // FMA
     const uint32_t cell = imad(h, (uint32_t)(-W), cb);                    // FMA
     // the cell is empty, so adding the bit is OR-ing it, and no carry can cross the words
@@ -408,67 +418,109 @@ connect_rollout_lut_kernel(const RolloutParams p) {
         const unsigned long long gid = p.game_id0 + idx;
         uint32_t r[4];
         philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
-        uint8_t* act_row = ACTIONS ? p.actions + (size_t)idx * HW : nullptr;
-        if (alive) alive = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[0], t, res, lut, ht, act_row, one);
-        if (alive) alive = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[1], t, res, lut, ht, act_row, one);
-        if (alive) alive = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[2], t, res, lut, ht, act_row, one);
-        if (alive) alive = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[3], t, res, lut, ht, act_row, one);
+        // trajectory: the 4 columns of this block as 4-bit fields of one 16-bit word, accumulated with
+        // IMADs; each played slot adds (H-1)*W + c, so the bias of the slots played is subtracted at the end
+        const bool started = alive;
+        const uint32_t tb = t;
+        uint32_t blk = 0;
+        if (alive) alive = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[0], t, res, lut, ht, blk, one);
+        if (alive) alive = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[1], t, res, lut, ht, blk, one);
+        if (alive) alive = lut_ply<H, W, K, 2, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[2], t, res, lut, ht, blk, one);
+        if (alive) alive = lut_ply<H, W, K, 3, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[3], t, res, lut, ht, blk, one);
+        if (ACTIONS && started) {
+            constexpr uint32_t B = (H - 1) * W;  // bias per played slot
+            const uint32_t played = t - tb;      // 1..4
+            const uint32_t bias = played == 4 ? B * 0x1111u : (played == 3 ? B * 0x111u : (played == 2 ? B * 0x11u : B));
+            *reinterpret_cast<uint16_t*>(p.actions + (size_t)idx * HW + (tb >> 1)) = (uint16_t)(blk - bias);
+        }
     }
     __syncthreads();
     if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
 }
 
 // ---------------------------------------------------------------------------------------------
-// export: packed boards -> int8[n,H,W] grids (+ rewards).  HBM-bound: reads 16/32 B, writes H*W (+8) B
-// per game.  Each thread produces 16 consecutive output bytes and stores them with one 128-bit store.
+// export: per-game records -> the reference's row layouts.  HBM-bound.
+//   MODE_GRID    packed boards (16 / 32 B per game)      -> int8[n,H,W] grids (-1 / 0 / 1)
+//   MODE_ACTIONS 16-bit blocks of 4-bit columns, stored by the rollout kernel at the start of each
+//                game's own row of `out`                 -> uint8[n,H*W] columns, 0xFF after the end
+// One warp handles 32 consecutive games: lane l expands game g0+l into the warp's shared-memory
+// stage, then the warp writes the 32*H*W contiguous output bytes with 128-bit stores (32*H*W is a
+// multiple of 16 for every board, so the stores are aligned although a row of 42 bytes is not).
+// The in-place MODE_ACTIONS is safe because every lane reads its row's blocks before the warp
+// writes anything.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-connect_export_grid_kernel(int H, int W, int NW, unsigned long long n, const uint64_t* __restrict__ packed,
-                           int8_t* __restrict__ grid) {
+constexpr int EXPORT_THREADS = 256;
+enum { MODE_GRID = 0, MODE_ACTIONS = 1 };
+
+// 4 one-bit flags (bits 0..3 of x) -> 4 bytes of 0 / 1
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+template <int MODE>
+__global__ void __launch_bounds__(EXPORT_THREADS)
+connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* __restrict__ packed,
+                           const uint8_t* __restrict__ length, uint8_t* out) {
+    extern __shared__ __align__(16) uint8_t s_stage[];
     const int HW = H * W;
-    const unsigned long long total = n * (unsigned long long)HW;
-    const unsigned long long nvec = (total + 15ull) / 16ull;
-    for (unsigned long long v = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v < nvec;
-         v += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long b0 = v * 16ull;
-        unsigned long long game = b0 / (unsigned)HW;
-        const int cell0 = (int)(b0 - game * (unsigned)HW);
-        int col = cell0 % W;
-        int bit = (H - 1 - cell0 / W) * W + col;  // board row r lives in bit row H-1-r
-        const uint64_t* rec = packed + game * (2 * NW);
-        uint32_t out[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int8_t val = 0;
-                if (b0 + 4 * q + j < total) {
-                    const uint64_t p0 = __ldg(rec + (bit >> 6));
-                    const uint64_t p1 = __ldg(rec + NW + (bit >> 6));
-                    const int sh = bit & 63;
-                    val = ((p0 >> sh) & 1ull) ? (int8_t)0 : (((p1 >> sh) & 1ull) ? (int8_t)1 : (int8_t)-1);
-                    ++col;
-                    ++bit;
-                    if (col == W) {  // next board row = previous bit row
-                        col = 0;
-                        bit -= 2 * W;
-                        if (bit < 0) {  // next game, bottom row again
-                            bit = (H - 1) * W;
-                            ++game;
-                            rec = packed + (game < n ? game : n - 1) * (2 * NW);
-                        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* st = s_stage + (size_t)warp * 32 * HW;  // multiple of 32 bytes: 16-byte aligned
+    uint8_t* mine = st + lane * HW;
+    const unsigned long long ngroups = (n + 31ull) / 32ull;
+    constexpr int WARPS = EXPORT_THREADS / 32;
+    for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
+         group += (unsigned long long)gridDim.x * WARPS) {
+        const unsigned long long g = group * 32ull + lane;
+        if (g < n) {
+            if (MODE == MODE_GRID) {
+                uint64_t b0[2] = {0, 0}, b1[2] = {0, 0};
+                if (HW <= 64) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(packed + g * 2);
+                    b0[0] = v.x; b1[0] = v.y;
+                } else {
+                    const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(packed + g * 4);
+                    const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(packed + g * 4 + 2);
+                    b0[0] = v0.x; b0[1] = v0.y; b1[0] = v1.x; b1[1] = v1.y;
+                }
+                // bit row br (bits br*W .. br*W+W-1) is board row H-1-br
+                for (int br = 0; br < H; ++br) {
+                    const int bit = br * W, wd = bit >> 6, sh = bit & 63;
+                    uint64_t r0 = b0[wd] >> sh, r1 = b1[wd] >> sh;
+                    if (sh + W > 64) {
+                        r0 |= b0[1] << (64 - sh);
+                        r1 |= b1[1] << (64 - sh);
+                    }
+                    uint8_t* dst = mine + (H - 1 - br) * W;
+                    for (int c = 0; c < W; c += 4) {
+                        const uint32_t a = spread4((uint32_t)(r0 >> c)), b = spread4((uint32_t)(r1 >> c));
+                        const uint32_t v = (0x01010101u - a - b) * 0xFFu + b;  // 0 / 1 / 0xFF per byte
+                        for (int j = 0; j < 4 && c + j < W; ++j) dst[c + j] = (uint8_t)(v >> (8 * j));
                     }
                 }
-                w |= (uint32_t)(uint8_t)val << (8 * j);
+            } else {
+                const uint8_t* row = out + g * (unsigned)HW;
+                const int len = length[g];
+                for (int t0 = 0; t0 < HW; t0 += 4) {
+                    uint32_t v = 0xFFFFFFFFu;
+                    if (t0 < len) {
+                        const uint32_t w = *reinterpret_cast<const uint16_t*>(row + (t0 >> 1));
+                        v = (w & 0xFu) | ((w & 0xF0u) << 4) | ((w & 0xF00u) << 8) | ((w & 0xF000u) << 12);
+                        const int live = len - t0;  // plies of this block that were played
+                        if (live < 4) v |= 0xFFFFFFFFu << (8 * live);
+                    }
+                    *reinterpret_cast<uint16_t*>(mine + t0) = (uint16_t)v;  // rows are 2-byte aligned (H*W even)
+                    if (t0 + 2 < HW) *reinterpret_cast<uint16_t*>(mine + t0 + 2) = (uint16_t)(v >> 16);
+                }
             }
-            out[q] = w;
         }
-        if (b0 + 16ull <= total) {
-            reinterpret_cast<uint4*>(grid)[v] = make_uint4(out[0], out[1], out[2], out[3]);
-        } else {
-            for (int j = 0; b0 + j < total; ++j) grid[b0 + j] = (int8_t)(out[j >> 2] >> (8 * (j & 3)));
-        }
+        __syncwarp();
+        const unsigned long long g0 = group * 32ull;
+        const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
+        const unsigned span = rows * (unsigned)HW;
+        uint8_t* base = out + g0 * (unsigned)HW;
+        const unsigned nvec = span >> 4;
+        for (unsigned q = lane; q < nvec; q += 32)
+            reinterpret_cast<uint4*>(base)[q] = reinterpret_cast<const uint4*>(st)[q];
+        for (unsigned i = (nvec << 4) + lane; i < span; i += 32) base[i] = st[i];
+        __syncwarp();
     }
 }
 
@@ -588,20 +640,46 @@ static int launch_persistent(Kern kern, const RolloutParams& p, cudaStream_t str
     return BGS_OK;
 }
 
+// trajectory mode for a board: packed 16-bit blocks in the game's own row need an even row length
+// of at least 4 bytes; other boards store one byte per ply into the pre-filled row
+static int actions_mode(int H, int W) { return ((H * W) % 2 == 0 && H * W >= 4) ? 2 : 1; }
+
 template <class G>
 static int launch_rollout(const G& g, const RolloutParams& p, cudaStream_t stream) {
-    if (p.actions && p.final_packed) return launch_persistent(connect_rollout_kernel<G, true, true>, p, stream, g);
-    if (p.actions) return launch_persistent(connect_rollout_kernel<G, true, false>, p, stream, g);
-    if (p.final_packed) return launch_persistent(connect_rollout_kernel<G, false, true>, p, stream, g);
-    return launch_persistent(connect_rollout_kernel<G, false, false>, p, stream, g);
+    const int act = p.actions ? actions_mode(g.H(), g.W()) : 0;
+    if (p.final_packed) {
+        if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, true>, p, stream, g);
+        if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, true>, p, stream, g);
+        return launch_persistent(connect_rollout_kernel<G, 0, true>, p, stream, g);
+    }
+    if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, false>, p, stream, g);
+    if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, false>, p, stream, g);
+    return launch_persistent(connect_rollout_kernel<G, 0, false>, p, stream, g);
 }
 
 template <int H, int W, int K>
 static int launch_rollout_lut(const RolloutParams& p, cudaStream_t stream) {
+    static_assert((H * W) % 2 == 0 && H * W >= 4, "LUT kernel stores packed trajectory blocks");
     if (p.actions && p.final_packed) return launch_persistent(connect_rollout_lut_kernel<H, W, K, true, true>, p, stream);
     if (p.actions) return launch_persistent(connect_rollout_lut_kernel<H, W, K, true, false>, p, stream);
     if (p.final_packed) return launch_persistent(connect_rollout_lut_kernel<H, W, K, false, true>, p, stream);
     return launch_persistent(connect_rollout_lut_kernel<H, W, K, false, false>, p, stream);
+}
+
+template <int MODE>
+static int launch_export_rows(int H, int W, unsigned long long n, const uint64_t* packed, const uint8_t* length,
+                              uint8_t* out, cudaStream_t stream) {
+    const size_t smem = (size_t)(EXPORT_THREADS / 32) * 32 * H * W;
+    auto kern = connect_export_rows_kernel<MODE>;
+    int per_sm = 0;
+    BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EXPORT_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long blocks = (n + 255ull) / 256ull;
+    const unsigned long long cap = (unsigned long long)sm_count() * per_sm;  // one resident wave, grid-stride
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, EXPORT_THREADS, smem, stream>>>(H, W, n, packed, length, out);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
 }
 
 }  // namespace connect
@@ -632,13 +710,16 @@ extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64
     // the kernels always write length and winner: point the unwanted one at write-only scratch
     uint8_t* scratch = nullptr;
     const uint64_t max_launch = 1ull << 31;
+    const uint64_t per_launch = n_games < max_launch ? n_games : max_launch;
+    if (actions && !length) return set_error(BGS_EINVAL, "connect_rollout: `actions` requires `length`");
     if (!length || !winner) {
-        if (int rc = scratch_buffer((size_t)(n_games < max_launch ? n_games : max_launch), (void**)&scratch)) return rc;
+        if (int rc = scratch_buffer((size_t)(2 * per_launch), (void**)&scratch)) return rc;
     }
     unsigned int* counter = nullptr;
     int rc = next_counter(&counter);
     cudaError_t e = cudaSuccess;
-    if (rc == BGS_OK && actions) {
+    const int act_mode = actions ? actions_mode(H, W) : 0;
+    if (rc == BGS_OK && act_mode == 1) {
         e = cudaMemsetAsync(actions, 0xFF, n_games * HW, stream);
         if (e != cudaSuccess) rc = cuda_error(e, "cudaMemsetAsync");
     }
@@ -650,7 +731,7 @@ extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64
         p.seed_hi = (uint32_t)(seed >> 32);
         p.actions = actions ? actions + off * HW : nullptr;
         p.length = length ? length + off : scratch;
-        p.winner = winner ? winner + off : reinterpret_cast<int8_t*>(scratch);
+        p.winner = winner ? winner + off : reinterpret_cast<int8_t*>(scratch + per_launch);
         p.final_packed = final_packed ? final_packed + off * PW : nullptr;
         p.stats = reinterpret_cast<unsigned long long*>(stats);
         p.counter = counter;
@@ -662,6 +743,9 @@ extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64
         else if (H == 8 && W == 9 && K == 5) rc = launch_rollout(StaticGeo<8, 9, 5>(), p, stream);
         else if (H == 10 && W == 12 && K == 6) rc = launch_rollout(StaticGeo<10, 12, 6>(), p, stream);
         else rc = launch_rollout(make_dyn_geo(H, W, K), p, stream);
+        // packed trajectory blocks -> one byte per ply, in place (needs this launch's lengths)
+        if (rc == BGS_OK && act_mode == 2)
+            rc = launch_export_rows<MODE_ACTIONS>(H, W, p.n_games, nullptr, p.length, p.actions, stream);
     }
     return rc;
 }
@@ -675,13 +759,8 @@ extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* pack
     const int sms = sm_count();
     if (grid) {
         if (!packed) return set_error(BGS_EINVAL, "connect_export: grid requested without packed boards");
-        const int NW = H * W <= 64 ? 1 : 2;
-        const unsigned long long nvec = (n * (unsigned long long)(H * W) + 15ull) / 16ull;
-        unsigned long long blocks = (nvec + 255) / 256;
-        const unsigned long long cap = (unsigned long long)sms * 8 * 4;
-        if (blocks > cap) blocks = cap;
-        connect_export_grid_kernel<<<(unsigned)blocks, 256, 0, stream>>>(H, W, NW, n, packed, grid);
-        BGS_CUDA_TRY(cudaGetLastError());
+        if (int rc = launch_export_rows<MODE_GRID>(H, W, n, packed, nullptr, reinterpret_cast<uint8_t*>(grid), stream))
+            return rc;
     }
     if (reward) {
         if (!winner) return set_error(BGS_EINVAL, "connect_export: reward requested without winner");

@@ -116,7 +116,7 @@ def connect_rollout(
 
     want_winner = per_game or reward
     res = RolloutResult(n_games=n, game_id0=int(game_id0), seed=int(seed), stats=None)
-    res.length = buf("length", (n,), torch.uint8, per_game)
+    res.length = buf("length", (n,), torch.uint8, per_game or actions)
     res.winner = buf("winner", (n,), torch.int8, want_winner)
     res.actions = buf("actions", (n, H * W), torch.uint8, actions)
     res.final_grid = buf("final_grid", (n, H, W), torch.int8, final_grid)

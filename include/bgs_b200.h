@@ -82,7 +82,7 @@ int bgs_connect_packed_words(int H, int W);
  *   actions (connect.cpp:43) -> uniform choice -> sample_next_state (connect.cpp:52) -> reward (connect.cpp:41).
  * Game i uses global id game_id0 + i; the action at ply t of a game is
  *   legal_columns_ascending[ mulhi32( philox4x32_10(key=seed, ctr=(id_lo,id_hi,t>>2,0))[t&3], n_legal ) ].
- * actions      optional uint8[n_games, H*W]  column per ply, 0xFF after the end
+ * actions      optional uint8[n_games, H*W]  column per ply, 0xFF after the end (requires `length`)
  * length       optional uint8[n_games]       plies played
  * winner       optional int8[n_games]        0 / 1 / BGS_WINNER_DRAW
  * final_packed optional uint64[n_games, bgs_connect_packed_words] final boards (feed to bgs_connect_export)

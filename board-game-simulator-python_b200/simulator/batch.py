@@ -146,36 +146,77 @@ def connect_rollout(
 
 
 class HostRollout:
-    """Reusable pinned host buffers + device buffers for the end-to-end path (what bench.py's
-    ``e2e`` times).  A rollout from the empty board has no tensor input -- its inputs are the scalars
-    (config, n_games, seed, game_id0), which travel in the kernel launch parameters -- so the
-    host->device side is 0 bytes; per-game ``length`` / ``winner`` and the statistics vector come
-    back device->host into pinned memory on every call."""
+    """End-to-end rollouts with results in pinned host memory (what bench.py's ``e2e`` times).
 
-    def __init__(self, config, n_games: int):
+    A rollout from the empty board has no tensor input -- its inputs are the scalars (config, n_games,
+    seed, game_id0), which travel in the kernel launch parameters -- so the host->device side is 0
+    bytes; per-game ``length`` / ``winner`` and the statistics vector come back device->host into
+    pinned memory for EVERY batch.
+
+    ``run`` is the synchronous call (kernel, then copy).  ``stream`` is the pipelined iterator: the
+    device->host copy of batch i runs on a copy stream while the kernel of batch i+1 runs on the
+    compute stream (two buffer sets), which hides the PCIe time behind the kernel.
+    """
+
+    def __init__(self, config, n_games: int, depth: int = 2):
         torch = N.require_cuda()
         self.torch = torch
         self.config = config
         self.n = int(n_games)
-        self.length_host = torch.empty(self.n, dtype=torch.uint8).pin_memory()
-        self.winner_host = torch.empty(self.n, dtype=torch.int8).pin_memory()
-        self.stats_host = torch.zeros(N.STATS_LEN, dtype=torch.int64).pin_memory()
-        self.stats_dev = torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda")
-        self._res = None
+        self.depth = int(depth)
+        self.sets = []
+        for _ in range(self.depth):
+            self.sets.append({
+                "length_host": torch.empty(self.n, dtype=torch.uint8).pin_memory(),
+                "winner_host": torch.empty(self.n, dtype=torch.int8).pin_memory(),
+                "stats_host": torch.zeros(N.STATS_LEN, dtype=torch.int64).pin_memory(),
+                "stats_dev": torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda"),
+                "res": None,
+                "computed": torch.cuda.Event(),
+                "copied": torch.cuda.Event(),
+            })
+        self.copy_stream = torch.cuda.Stream()
         self.h2d_bytes = 0
         self.d2h_bytes = self.n * 2 + N.STATS_LEN * 8
 
+    def _launch(self, s, seed, game_id0):
+        torch = self.torch
+        s["stats_dev"].zero_()
+        s["res"] = connect_rollout(self.config, self.n, seed, game_id0, per_game=True, stats=s["stats_dev"], out=s["res"])
+        s["computed"].record()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["computed"])
+            s["length_host"].copy_(s["res"].length, non_blocking=True)
+            s["winner_host"].copy_(s["res"].winner, non_blocking=True)
+            s["stats_host"].copy_(s["stats_dev"], non_blocking=True)
+            s["copied"].record()
+
     def run(self, seed: int, game_id0: int = 0):
         """One end-to-end rollout; returns (stats, length, winner) as pinned host tensors (synchronised)."""
-        self.stats_dev.zero_()
-        self._res = connect_rollout(
-            self.config, self.n, seed, game_id0, per_game=True, stats=self.stats_dev, out=self._res
-        )
-        self.length_host.copy_(self._res.length, non_blocking=True)
-        self.winner_host.copy_(self._res.winner, non_blocking=True)
-        self.stats_host.copy_(self.stats_dev, non_blocking=True)
-        self.torch.cuda.current_stream().synchronize()
-        return self.stats_host, self.length_host, self.winner_host
+        s = self.sets[0]
+        self._launch(s, seed, game_id0)
+        s["copied"].synchronize()
+        return s["stats_host"], s["length_host"], s["winner_host"]
+
+    def stream(self, seed: int, game_id0: int, n_batches: int):
+        """Yields ``(stats, length, winner)`` host tensors for ``n_batches`` consecutive batches of
+        ``n_games`` games (global ids ``game_id0 + i*n_games ...``).  A yielded set is valid until the
+        next-but-one ``next()``."""
+        torch = self.torch
+        pending = []
+        for i in range(n_batches):
+            s = self.sets[i % self.depth]
+            # the kernel about to overwrite this set's device buffers must wait for its last copy
+            torch.cuda.current_stream().wait_event(s["copied"])
+            self._launch(s, seed, game_id0 + i * self.n)
+            pending.append(s)
+            if len(pending) == self.depth:
+                done = pending.pop(0)
+                done["copied"].synchronize()
+                yield done["stats_host"], done["length_host"], done["winner_host"]
+        for done in pending:
+            done["copied"].synchronize()
+            yield done["stats_host"], done["length_host"], done["winner_host"]
 
 
 class ConnectBatch:

@@ -240,6 +240,27 @@ def test_host_buffer_c_abi_entry_point(oracle):
         np.testing.assert_array_equal(got, ref[key])
 
 
+def test_pipelined_host_stream_equals_oracle(oracle):
+    """HostRollout.stream (the end-to-end path bench.py times): every batch's host results are the
+    oracle's, although copies and kernels of consecutive batches overlap."""
+    from simulator import batch
+
+    n, k = 20000, 5
+    host = batch.HostRollout((6, 7, 4), n)
+    seen = 0
+    for i, (st, length, winner) in enumerate(host.stream(11, 1000, k)):
+        ref = oracle.connect_rollout(6, 7, 4, n, gid0=1000 + i * n, seed=11, want_actions=False, want_grid=False)
+        np.testing.assert_array_equal(length.numpy(), ref["length"])
+        np.testing.assert_array_equal(winner.numpy(), ref["winner"])
+        np.testing.assert_array_equal(st.numpy(), ref["stats"])
+        seen += 1
+    assert seen == k
+    st, length, winner = host.run(11, 1000)
+    ref = oracle.connect_rollout(6, 7, 4, n, gid0=1000, seed=11, want_actions=False, want_grid=False)
+    np.testing.assert_array_equal(length.numpy(), ref["length"])
+    np.testing.assert_array_equal(st.numpy(), ref["stats"])
+
+
 def test_dlpack_export():
     from simulator import batch
 

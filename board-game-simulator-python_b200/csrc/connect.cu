@@ -355,14 +355,109 @@ __device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t
     return !(won || t == (uint32_t)(H * W));
 }
 
+// A ply that cannot end the game (fewer than K stones of the mover on the board, board not full):
+// the same move selection and bookkeeping as lut_ply without the k-in-a-row test.
+template <int H, int W, int J, bool ACTIONS>
+__device__ __forceinline__ void lut_ply_light(uint64_t& me, uint32_t top_occ, uint32_t r, uint32_t lut, uint32_t ht,
+                                              uint32_t& blk, uint32_t one) {
+    const uint32_t freem = ~top_occ & ((1u << W) - 1u);
+    const uint32_t n = (uint32_t)__popc(freem);
+    const uint32_t cb = lds_u8(imad_hi(r, n, imad(freem, 8u * one, lut)));
+    const uint32_t hp = imad(cb, one, ht);
+    const uint32_t h = lds_u8(hp);
+    sts_u8(hp, imad(h, one, one));
+    if (ACTIONS) blk = imad(cb, (1u << (4 * J)) * one, blk);
+    const uint32_t cell = imad(h, (uint32_t)(-W), cb);
+    uint32_t lo = imad(bit_or_zero(cell), one, (uint32_t)me);
+    uint32_t hi = (uint32_t)(me >> 32);
+    if (H * W > 32) hi = imad(bit_or_zero(imad(cell, one, (uint32_t)-32)), one, hi);
+    me = ((uint64_t)hi << 32) | lo;
+}
+
+// A game that has been played through its opening, waiting in the warp's ring for a free lane.
+struct __align__(16) Prepared {
+    uint32_t p0lo, p0hi, p1lo, p1hi;
+    uint32_t ht_lo, ht_hi;  // the 8 column-height bytes
+    uint32_t idx;           // game index, 0xFFFFFFFF = beyond n_games
+    uint32_t t_res;         // plies played | (winner + 1) << 8 | over << 16
+};
+
+constexpr int RING = 64;        // prepared games per warp (>= 31 + 32)
+constexpr int OPEN_PLIES = 8;   // the opening = the first two Philox blocks
+
+// The opening phase, executed by all 32 lanes of a warp at once: lane l plays the first 8 plies of
+// game base+l.  No player can have K stones before ply 2K-2, so those plies skip the k-in-a-row test
+// entirely -- and because the whole warp is in the same phase, skipping it is not divergent (in the
+// main loop lanes are at arbitrary plies and the test could never be skipped).
+template <int H, int W, int K, bool ACTIONS>
+__device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base, Prepared* ring, uint32_t slot,
+                                           uint32_t lut, uint32_t ht2, uint2* ht2_row, uint32_t one) {
+    constexpr int HW = H * W;
+    static_assert(HW > OPEN_PLIES + 1, "a draw inside the opening is not handled");
+    const uint32_t id = base + (threadIdx.x & 31u);
+    const bool valid = id < p.n_games;
+    const unsigned long long gid = p.game_id0 + id;
+    *ht2_row = make_uint2(0u, 0u);
+    uint64_t q0 = 0, q1 = 0;
+    uint32_t t = 0, blk0 = 0, blk1 = 0;
+    int res = BGS_WINNER_DRAW;
+    bool alive = true;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 0u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+#define BGS_OPEN_PLY(J, T, ME, BLK)                                                                           \
+    if ((T) < 2 * K - 2) {                                                                                    \
+        lut_ply_light<H, W, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], lut, ht2, BLK, one);           \
+        t = (T) + 1;                                                                                          \
+    } else if (alive) {                                                                                       \
+        alive = lut_ply<H, W, K, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], t, res, lut, ht2, BLK, one); \
+    }
+    BGS_OPEN_PLY(0, 0, q0, blk0)
+    BGS_OPEN_PLY(1, 1, q1, blk0)
+    BGS_OPEN_PLY(2, 2, q0, blk0)
+    BGS_OPEN_PLY(3, 3, q1, blk0)
+    const uint32_t t4 = t;
+    if (t4 == 4 && alive) philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 1u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+    if (alive) {
+        BGS_OPEN_PLY(0, 4, q0, blk1)
+        BGS_OPEN_PLY(1, 5, q1, blk1)
+        BGS_OPEN_PLY(2, 6, q0, blk1)
+        BGS_OPEN_PLY(3, 7, q1, blk1)
+    }
+#undef BGS_OPEN_PLY
+    if (ACTIONS && valid) {
+        constexpr uint32_t B = (H - 1) * W;
+        uint16_t* row = reinterpret_cast<uint16_t*>(p.actions + (size_t)id * HW);
+        const uint32_t pl0 = t4;  // plies of block 0 that were played (4 unless K is tiny)
+        const uint32_t b0 = pl0 == 4 ? B * 0x1111u : (pl0 == 3 ? B * 0x111u : (pl0 == 2 ? B * 0x11u : B));
+        row[0] = (uint16_t)(blk0 - b0);
+        if (t > 4) {
+            const uint32_t pl1 = t - 4;
+            const uint32_t b1 = pl1 == 4 ? B * 0x1111u : (pl1 == 3 ? B * 0x111u : (pl1 == 2 ? B * 0x11u : B));
+            row[1] = (uint16_t)(blk1 - b1);
+        }
+    }
+    const uint2 hts = *ht2_row;
+    Prepared e;
+    e.p0lo = (uint32_t)q0; e.p0hi = (uint32_t)(q0 >> 32); e.p1lo = (uint32_t)q1; e.p1hi = (uint32_t)(q1 >> 32);
+    e.ht_lo = hts.x; e.ht_hi = hts.y;
+    e.idx = valid ? id : 0xFFFFFFFFu;
+    e.t_res = t | ((uint32_t)(res + 1) << 8) | (alive ? 0u : 1u << 16);
+    uint4* dst = reinterpret_cast<uint4*>(ring + slot);
+    dst[0] = make_uint4(e.p0lo, e.p0hi, e.p1lo, e.p1hi);
+    dst[1] = make_uint4(e.ht_lo, e.ht_hi, e.idx, e.t_res);
+}
+
 template <int H, int W, int K, bool ACTIONS, bool PACKED>
 __global__ void __launch_bounds__(ROLLOUT_THREADS)
 connect_rollout_lut_kernel(const RolloutParams p) {
     static_assert(H * W <= 64 && W <= 8, "LUT kernel: one 64-bit board word, at most 8 columns");
+    constexpr int WARPS = ROLLOUT_THREADS / 32;
     __shared__ unsigned int s_hist[HIST_BINS];
     __shared__ unsigned int s_draws;
     __shared__ uint8_t s_lut[(1 << W) * 8];                       // [free mask][k] -> k-th set bit
-    __shared__ __align__(8) uint8_t s_ht[ROLLOUT_THREADS * 8];    // [thread][column] -> stones
+    __shared__ __align__(8) uint8_t s_ht[ROLLOUT_THREADS * 8];    // [thread][column] -> stones (main loop)
+    __shared__ __align__(8) uint8_t s_ht2[ROLLOUT_THREADS * 8];   // same, scratch of the opening phase
+    __shared__ Prepared s_ring[WARPS][RING];
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) s_draws = 0;
     for (int i = threadIdx.x; i < (1 << W) * 8; i += blockDim.x) {
@@ -375,21 +470,26 @@ connect_rollout_lut_kernel(const RolloutParams p) {
         s_lut[i] = (uint8_t)((H - 1) * W + (c < W ? c : 0));
     }
     uint2* ht_row = reinterpret_cast<uint2*>(s_ht + threadIdx.x * 8);
+    uint2* ht2_row = reinterpret_cast<uint2*>(s_ht2 + threadIdx.x * 8);
     *ht_row = make_uint2(0u, 0u);
     __syncthreads();
     const uint32_t one = p.one;
     const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_lut);
     const uint32_t ht = (uint32_t)__cvta_generic_to_shared(ht_row) - (uint32_t)((H - 1) * W);
+    const uint32_t ht2 = (uint32_t)__cvta_generic_to_shared(ht2_row) - (uint32_t)((H - 1) * W);
+    Prepared* ring = s_ring[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
 
     constexpr int HW = H * W;
     uint64_t p0 = 0, p1 = 0;
     uint32_t t = 0;
     int res = BGS_WINNER_DRAW;
     bool alive = false, retired = false;
-    uint32_t idx = 0, pool_next = 0, pool_cnt = 0;
+    uint32_t idx = 0;
+    uint32_t ring_head = 0, ring_cnt = 0;  // warp-uniform
 
     for (;;) {
-        // ---- warp-convergent: retire finished games, claim new ones -------------------------
+        // ---- warp-convergent: retire finished games, hand out prepared ones ------------------
         if (!alive && t != 0) {
             p.length[idx] = (uint8_t)t;
             p.winner[idx] = (int8_t)res;
@@ -398,21 +498,40 @@ connect_rollout_lut_kernel(const RolloutParams p) {
             if (res < 0) atomicAdd(&s_draws, 1u);
             t = 0;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, !alive && !retired);
+        const bool need = !alive && !retired;
+        const unsigned m = __ballot_sync(0xffffffffu, need);
         if (m) {
-            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
-            if (!alive && !retired) {
-                if (id < p.n_games) {
-                    idx = id;
-                    p0 = 0; p1 = 0; res = BGS_WINNER_DRAW;
-                    *ht_row = make_uint2(0u, 0u);
-                    alive = true;
-                } else {
+            const uint32_t want = __popc(m);
+            if (ring_cnt < want) {  // warp-uniform: prepare 32 more games (one atomic per 32 ids)
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(p.counter, 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                open_games<H, W, K, ACTIONS>(p, base, ring, (ring_head + ring_cnt + lane) & (RING - 1), lut, ht2,
+                                             ht2_row, one);
+                ring_cnt += 32;
+                __syncwarp();
+            }
+            if (need) {
+                const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                const uint4* src = reinterpret_cast<const uint4*>(ring + ((ring_head + rank) & (RING - 1)));
+                const uint4 a = src[0], b = src[1];
+                if (b.z == 0xFFFFFFFFu) {
                     retired = true;
+                } else {
+                    p0 = ((uint64_t)a.y << 32) | a.x;
+                    p1 = ((uint64_t)a.w << 32) | a.z;
+                    *ht_row = make_uint2(b.x, b.y);
+                    idx = b.z;
+                    t = b.w & 0xFFu;
+                    res = (int)((b.w >> 8) & 0xFFu) - 1;
+                    alive = (b.w >> 16) == 0u;
                 }
             }
+            ring_head = (ring_head + want) & (RING - 1);
+            ring_cnt -= want;
+            __syncwarp();
         }
-        if (!__any_sync(0xffffffffu, alive)) break;
+        if (!__any_sync(0xffffffffu, alive || t != 0)) break;
 
         // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
         const unsigned long long gid = p.game_id0 + idx;

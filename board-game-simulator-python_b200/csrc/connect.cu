@@ -305,6 +305,11 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
@@ -328,12 +333,54 @@ __device__ __forceinline__ uint32_t bit_or_zero(uint32_t s) {
     return d;
 }
 
+// x << S on the FMA pipe (IMAD.SHL) instead of the ALU pipe (SHF)
+template <int S>
+__device__ __forceinline__ uint32_t shl_fma(uint32_t x) {
+    uint32_t d;
+    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "n"(1u << S));
+    return d;
+}
+
+// k-in-a-row test for one-word boards with the first doubling step done by LEFT shifts: the low
+// word's shift is then a plain multiply (FMA pipe) and only the high word needs a funnel shift.
+// m(i) = me(i) & me(i-d) is a pair ENDING at i, i.e. the run starting at i-d, so the remaining
+// right-shift doubling steps are unchanged and the start mask is shifted up by d.
+template <class G, int I>
+__device__ __forceinline__ uint64_t runs_dir_mixed(uint64_t me) {
+    constexpr int K = G::K();
+    constexpr int d = dir_dr(I) * G::W() + dir_dc(I);
+    if (K < 2) return me & G::template valid<I>();
+    const uint32_t lo = (uint32_t)me, hi = (uint32_t)(me >> 32);
+    const uint32_t mlo = lo & shl_fma<d>(lo);
+    const uint32_t mhi = (G::H() * G::W() > 32) ? (hi & __funnelshift_l(lo, hi, d)) : 0u;
+    uint64_t m = ((uint64_t)mhi << 32) | mlo;
+    int len = 2;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        if (2 * len <= K) {
+            m &= shr(m, len * d);
+            len *= 2;
+        }
+    }
+    if (len < K) m &= shr(m, (K - len) * d);
+    return m & (G::template valid<I>() << d);
+}
+
+template <class G>
+__device__ __forceinline__ bool has_run_mixed(uint64_t me) {
+    uint64_t acc = runs_dir_mixed<G, 0>(me);
+    acc |= runs_dir_mixed<G, 1>(me);
+    acc |= runs_dir_mixed<G, 2>(me);
+    acc |= runs_dir_mixed<G, 3>(me);
+    return acc != 0;
+}
+
 // One ply of player P.  `lut` / `ht` are 32-bit shared-memory addresses: lut[free*8 + k] is the
 // bit index of the BOTTOM cell of the k-th playable column ((H-1)*W + c); ht is pre-biased by
 // -(H-1)*W so that ht[that index] is the number of stones in the column.
 template <int H, int W, int K, int J, bool ACTIONS>
 __device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t r, uint32_t& t, int& res,
-                                        uint32_t lut, uint32_t ht, uint32_t& blk, uint32_t one) {
+                                        uint32_t lut, uint32_t ht, uint32_t& blk, uint32_t one, uint32_t bitlut) {
     typedef StaticGeo<H, W, K> G;
     constexpr int P = J & 1;
     const uint32_t freem = ~top_occ & ((1u << W) - 1u);                   // ALU: one LOP3
@@ -345,12 +392,13 @@ __device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t
     if (ACTIONS) blk = imad(cb, (1u << (4 * J)) * one, blk);            // FMA (bias removed at the block end)
     t = imad(t, one, one);                                                // FMA
     const uint32_t cell = imad(h, (uint32_t)(-W), cb);                    // FMA
-    // the cell is empty, so adding the bit is OR-ing it, and no carry can cross the words
-    uint32_t lo = imad(bit_or_zero(cell), one, (uint32_t)me);             // ALU (SHF), FMA
-    uint32_t hi = (uint32_t)(me >> 32);
-    if (H * W > 32) hi = imad(bit_or_zero(imad(cell, one, (uint32_t)-32)), one, hi);
+    // the cell is empty, so adding the bit is OR-ing it, and no carry can cross the words; the bit
+    // itself comes from a 64-bit shared-memory table (LSU pipe) instead of two ALU shifts
+    const uint2 bit = lds_u64(imad(cell, 8u * one, bitlut));              // FMA, LSU
+    const uint32_t lo = imad(bit.x, one, (uint32_t)me);                   // FMA
+    const uint32_t hi = (H * W > 32) ? imad(bit.y, one, (uint32_t)(me >> 32)) : 0u;
     me = ((uint64_t)hi << 32) | lo;
-    const bool won = has_run(G(), me);
+    const bool won = has_run_mixed<G>(me);
     if (won) res = P;
     return !(won || t == (uint32_t)(H * W));
 }
@@ -359,7 +407,7 @@ __device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t
 // the same move selection and bookkeeping as lut_ply without the k-in-a-row test.
 template <int H, int W, int J, bool ACTIONS>
 __device__ __forceinline__ void lut_ply_light(uint64_t& me, uint32_t top_occ, uint32_t r, uint32_t lut, uint32_t ht,
-                                              uint32_t& blk, uint32_t one) {
+                                              uint32_t& blk, uint32_t one, uint32_t bitlut) {
     const uint32_t freem = ~top_occ & ((1u << W) - 1u);
     const uint32_t n = (uint32_t)__popc(freem);
     const uint32_t cb = lds_u8(imad_hi(r, n, imad(freem, 8u * one, lut)));
@@ -368,9 +416,9 @@ __device__ __forceinline__ void lut_ply_light(uint64_t& me, uint32_t top_occ, ui
     sts_u8(hp, imad(h, one, one));
     if (ACTIONS) blk = imad(cb, (1u << (4 * J)) * one, blk);
     const uint32_t cell = imad(h, (uint32_t)(-W), cb);
-    uint32_t lo = imad(bit_or_zero(cell), one, (uint32_t)me);
-    uint32_t hi = (uint32_t)(me >> 32);
-    if (H * W > 32) hi = imad(bit_or_zero(imad(cell, one, (uint32_t)-32)), one, hi);
+    const uint2 bit = lds_u64(imad(cell, 8u * one, bitlut));
+    const uint32_t lo = imad(bit.x, one, (uint32_t)me);
+    const uint32_t hi = (H * W > 32) ? imad(bit.y, one, (uint32_t)(me >> 32)) : 0u;
     me = ((uint64_t)hi << 32) | lo;
 }
 
@@ -391,7 +439,7 @@ constexpr int OPEN_PLIES = 8;   // the opening = the first two Philox blocks
 // main loop lanes are at arbitrary plies and the test could never be skipped).
 template <int H, int W, int K, bool ACTIONS>
 __device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base, Prepared* ring, uint32_t slot,
-                                           uint32_t lut, uint32_t ht2, uint2* ht2_row, uint32_t one) {
+                                           uint32_t lut, uint32_t ht2, uint2* ht2_row, uint32_t one, uint32_t bitlut) {
     constexpr int HW = H * W;
     static_assert(HW > OPEN_PLIES + 1, "a draw inside the opening is not handled");
     const uint32_t id = base + (threadIdx.x & 31u);
@@ -406,10 +454,10 @@ __device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base
     philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 0u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
 #define BGS_OPEN_PLY(J, T, ME, BLK)                                                                           \
     if ((T) < 2 * K - 2) {                                                                                    \
-        lut_ply_light<H, W, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], lut, ht2, BLK, one);           \
+        lut_ply_light<H, W, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], lut, ht2, BLK, one, bitlut);   \
         t = (T) + 1;                                                                                          \
     } else if (alive) {                                                                                       \
-        alive = lut_ply<H, W, K, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], t, res, lut, ht2, BLK, one); \
+        alive = lut_ply<H, W, K, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], t, res, lut, ht2, BLK, one, bitlut); \
     }
     BGS_OPEN_PLY(0, 0, q0, blk0)
     BGS_OPEN_PLY(1, 1, q1, blk0)
@@ -458,6 +506,9 @@ connect_rollout_lut_kernel(const RolloutParams p) {
     __shared__ __align__(8) uint8_t s_ht[ROLLOUT_THREADS * 8];    // [thread][column] -> stones (main loop)
     __shared__ __align__(8) uint8_t s_ht2[ROLLOUT_THREADS * 8];   // same, scratch of the opening phase
     __shared__ Prepared s_ring[WARPS][RING];
+    __shared__ uint2 s_bit[64];                                   // [cell] -> 1 << cell as two words
+    if (threadIdx.x < 64)
+        s_bit[threadIdx.x] = make_uint2(threadIdx.x < 32 ? 1u << threadIdx.x : 0u, threadIdx.x >= 32 ? 1u << (threadIdx.x - 32) : 0u);
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) s_draws = 0;
     for (int i = threadIdx.x; i < (1 << W) * 8; i += blockDim.x) {
@@ -477,6 +528,7 @@ connect_rollout_lut_kernel(const RolloutParams p) {
     const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_lut);
     const uint32_t ht = (uint32_t)__cvta_generic_to_shared(ht_row) - (uint32_t)((H - 1) * W);
     const uint32_t ht2 = (uint32_t)__cvta_generic_to_shared(ht2_row) - (uint32_t)((H - 1) * W);
+    const uint32_t bitlut = (uint32_t)__cvta_generic_to_shared(s_bit);
     Prepared* ring = s_ring[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
 
@@ -507,7 +559,7 @@ connect_rollout_lut_kernel(const RolloutParams p) {
                 if (lane == 0) base = atomicAdd(p.counter, 32u);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 open_games<H, W, K, ACTIONS>(p, base, ring, (ring_head + ring_cnt + lane) & (RING - 1), lut, ht2,
-                                             ht2_row, one);
+                                             ht2_row, one, bitlut);
                 ring_cnt += 32;
                 __syncwarp();
             }
@@ -542,10 +594,10 @@ connect_rollout_lut_kernel(const RolloutParams p) {
         const bool started = alive;
         const uint32_t tb = t;
         uint32_t blk = 0;
-        if (alive) alive = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[0], t, res, lut, ht, blk, one);
-        if (alive) alive = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[1], t, res, lut, ht, blk, one);
-        if (alive) alive = lut_ply<H, W, K, 2, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[2], t, res, lut, ht, blk, one);
-        if (alive) alive = lut_ply<H, W, K, 3, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[3], t, res, lut, ht, blk, one);
+        if (alive) alive = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[0], t, res, lut, ht, blk, one, bitlut);
+        if (alive) alive = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[1], t, res, lut, ht, blk, one, bitlut);
+        if (alive) alive = lut_ply<H, W, K, 2, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[2], t, res, lut, ht, blk, one, bitlut);
+        if (alive) alive = lut_ply<H, W, K, 3, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[3], t, res, lut, ht, blk, one, bitlut);
         if (ACTIONS && started) {
             constexpr uint32_t B = (H - 1) * W;  // bias per played slot
             const uint32_t played = t - tb;      // 1..4

@@ -233,7 +233,16 @@ __device__ __forceinline__ void store_grid(const Planes<NP>& P, int HW, int8_t* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// rollout kernel: one game per lane, one ply (= one full move generation) per loop iteration
+// rollout kernel: one game per lane, ONE flat loop.
+//
+// Every loop iteration performs one frontier step of the lane's current move generation; the
+// bookkeeping between segments / pieces is a short branch.  A lane whose move generation is complete
+// waits until PLY_BATCH lanes of its warp are in the same state; then the (long) ply transition --
+// draw, k-th action, move, goal test, blocked test, game end + next game -- runs once for all of
+// them.  Lanes never wait for the slowest move generation of the warp (a formulation with one move
+// generation per outer iteration ran at 5 of 32 active lanes), and the transition does not execute
+// on nearly every iteration with a handful of lanes either.  Game indices are claimed with one atomic per game (games last ~28 plies of ~1.4k
+// instructions, so the counter is not contended).
 // ---------------------------------------------------------------------------------------------
 struct RolloutParams {
     uint32_t n_games;  // <= 2^31 per launch
@@ -251,7 +260,28 @@ struct RolloutParams {
 };
 
 constexpr int ROLLOUT_THREADS = 128;
-constexpr int CLAIM_CHUNK = 32;
+#ifndef BGS_BOUNCE_PLY_BATCH
+#define BGS_BOUNCE_PLY_BATCH 12
+#endif
+constexpr int PLY_BATCH = BGS_BOUNCE_PLY_BATCH;  // lanes that must be ready before the ply transition runs
+
+// index of the k-th (0-based) set bit of m, by binary search on population counts
+__device__ __forceinline__ int kth_set_bit(uint64_t m, int k) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 32; w >= 1; w >>= 1) {
+        const uint64_t low = m & ((1ull << w) - 1ull);
+        const int c = __popcll(low);
+        if (k >= c) {
+            k -= c;
+            m >>= w;
+            pos += w;
+        } else {
+            m = low;
+        }
+    }
+    return pos;
+}
 
 template <int NP>
 __global__ void __launch_bounds__(ROLLOUT_THREADS)
@@ -260,98 +290,177 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
     __shared__ uint64_t s_T[8 * ROLLOUT_THREADS];
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    uint64_t* T = s_T + threadIdx.x;
+    uint64_t* T = s_T + threadIdx.x;  // T[x * ROLLOUT_THREADS] = target mask of the piece in column x
     const int HW = g.H * g.W;
+    const int variant = g.rules & 3;
+    const bool allow_null = (g.rules & BGS_BOUNCE_ALLOW_NULL_MOVE) != 0;
 
+    // ---- game state ---------------------------------------------------------------------------
     Planes<NP> P;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) P.b[i] = 0;
     int player = 0, t = 0, win = BGS_WINNER_DRAW;
-    bool alive = false, has_game = false, retired = false;
-    uint32_t idx = 0, pool_next = 0, pool_cnt = 0;
     uint32_t r[4] = {0, 0, 0, 0};
     uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
     unsigned long long acc_steps = 0;
+    // ---- move-generation state ------------------------------------------------------------------
+    int mg_player = 0;      // whose moves are being generated (differs from `player` while probing)
+    bool probe = false;     // true: only "does mg_player have any action?" (blocked test)
+    bool found = false, have = false;
+    uint64_t occ = 0, src_left = 0, sbit = 0, occS = 0, open = 0, inter = 0, expanded = 0, pending = 0, targets = 0;
+    uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = 0;
+    int rem = 0, xs = 0, total = 0, row = 0;
+
+    auto begin_movegen = [&](int pl, bool prb) {
+        mg_player = pl;
+        probe = prb;
+        occ = P.occ();
+        src_left = source_row_mask(g, occ, pl, &row) & occ;
+        have = false; found = false;
+        pending = 0; rem = 0; total = 0;
+        if (!prb)
+            for (int x = 0; x < g.W; ++x) T[x * ROLLOUT_THREADS] = 0ull;
+    };
+    auto begin_game = [&]() {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) P.b[i] = p.plane0[i];
+        player = 0; t = 0; win = BGS_WINNER_DRAW;
+        begin_movegen(0, false);
+    };
+
+    uint32_t idx = atomicAdd(p.counter, 1u);
+    bool active = idx < p.n_games;
+    bool waiting = false;  // move generation complete, ply transition not yet executed
+    if (active) begin_game();
 
     for (;;) {
-        // ---- warp-convergent: retire finished games, claim new ones -------------------------
-        if (has_game && !alive) {
-            if (p.length) p.length[idx] = (uint16_t)t;
-            if (p.winner) p.winner[idx] = (int8_t)win;
-            if (p.final_grid) store_grid<NP>(P, HW, p.final_grid + (size_t)idx * HW);
-            if (p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(win);
-            acc_w0 += (win == 0);
-            acc_w1 += (win == 1);
-            acc_dr += (win == BGS_WINNER_DRAW);
-            acc_tr += (win == BGS_WINNER_TRUNCATED);
-            acc_steps += (unsigned)t;
-            atomicAdd(&s_hist[hist_bin(t)], 1u);
-            has_game = false;
-        }
-        const bool need = !has_game && !retired;
-        const unsigned m = __ballot_sync(0xffffffffu, need);
-        if (m) {
-            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
-            if (need) {
-                if (id < p.n_games) {
-                    idx = id;
-#pragma unroll
-                    for (int i = 0; i < NP; ++i) P.b[i] = p.plane0[i];
-                    player = 0; t = 0; win = BGS_WINNER_DRAW;
-                    alive = true;
-                    has_game = true;
+        // ---- warp-convergent: run the (long) ply transition only when enough lanes are ready for it,
+        // so that it executes with many lanes at once instead of on nearly every iteration with a few
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        if (!am) break;
+        const unsigned wm = __ballot_sync(0xffffffffu, waiting);
+        if (__popc(wm) >= PLY_BATCH || wm == am) {
+            if (waiting) {
+                waiting = false;
+                bool over = false;
+                if (probe) {
+                    // `player` is blocked; the previous mover wins unless blocked too (draw)
+                    win = found ? 1 - player : BGS_WINNER_DRAW;
+                    over = true;
+                } else if (total == 0) {
+                    if (t == 0) over = true;  // a blocked start position: ended, no winner
+                    else begin_movegen(1 - player, true);
+                } else if (t >= p.max_plies) {
+                    win = BGS_WINNER_TRUNCATED;
+                    over = true;
                 } else {
-                    retired = true;
+                    if ((t & 3) == 0) {
+                        const unsigned long long gid = p.game_id0 + idx;
+                        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2, DOMAIN_BOUNCE,
+                                      p.seed_lo, p.seed_hi, r);
+                    }
+                    const uint32_t rr = (t & 3) == 0 ? r[0] : ((t & 3) == 1 ? r[1] : ((t & 3) == 2 ? r[2] : r[3]));
+                    int k = (int)__umulhi(rr, (uint32_t)total);
+                    // k-th action in ascending (source column, target cell) order
+                    int sx = 0;
+                    uint64_t tm = T[0];
+                    for (;;) {
+                        const int c = __popcll(tm);
+                        if (k < c) break;
+                        k -= c;
+                        ++sx;
+                        tm = T[sx * ROLLOUT_THREADS];
+                    }
+                    const int scell = row * g.W + sx;
+                    const int tcell = kth_set_bit(tm, k);
+                    if (p.moves) {
+                        uint8_t* m = p.moves + ((size_t)idx * p.max_plies + (unsigned)t) * 2ull;
+                        *reinterpret_cast<uchar2*>(m) = make_uchar2((unsigned char)scell, (unsigned char)tcell);
+                    }
+                    move_piece<NP>(P, scell, tcell);
+                    ++t;
+                    if ((1ull << tcell) & g.far(player)) {
+                        win = player;
+                        over = true;
+                    }
+                    player ^= 1;
+                    if (!over) begin_movegen(player, false);
+                }
+                if (over) {
+                    if (p.length) p.length[idx] = (uint16_t)t;
+                    if (p.winner) p.winner[idx] = (int8_t)win;
+                    if (p.final_grid) store_grid<NP>(P, HW, p.final_grid + (size_t)idx * HW);
+                    if (p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(win);
+                    acc_w0 += (win == 0);
+                    acc_w1 += (win == 1);
+                    acc_dr += (win == BGS_WINNER_DRAW);
+                    acc_tr += (win == BGS_WINNER_TRUNCATED);
+                    acc_steps += (unsigned)t;
+                    atomicAdd(&s_hist[hist_bin(t)], 1u);
+                    idx = atomicAdd(p.counter, 1u);
+                    if (idx < p.n_games) begin_game();
+                    else active = false;
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, has_game)) break;
-
-        if (alive) {
-            int row;
-            const int total = movegen<NP, false>(g, P, player, T, ROLLOUT_THREADS, &row);
-            if (total == 0) {
-                // the side to move is blocked: the previous mover wins unless it would be blocked
-                // too (tests/test_bounce.py:323-362); a blocked start position is a draw
-                if (t > 0 && has_any<NP>(g, P, 1 - player)) win = 1 - player;
-                alive = false;
-            } else if (t >= p.max_plies) {
-                win = BGS_WINNER_TRUNCATED;
-                alive = false;
-            } else {
-                if ((t & 3) == 0) {
-                    const unsigned long long gid = p.game_id0 + idx;
-                    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2, DOMAIN_BOUNCE,
-                                  p.seed_lo, p.seed_hi, r);
+        if (active && !waiting) {
+            if (rem == 0) {
+                if (pending != 0) {
+                    // bounce: all unexpanded landing cells that hold a piece of the same value
+                    const int c = __ffsll((long long)pending) - 1;
+                    const int u = P.value_at(c);
+                    const uint64_t S = pending & P.cells_with_value(u);
+                    pending &= ~S;
+                    expanded |= S;
+                    Ff = 0; Fl = 0; Fr = 0; Nn = S;
+                    rem = u;
+                } else {
+                    if (have) {  // the piece on sbit is done
+                        if (!allow_null) targets &= ~sbit;
+                        if (probe) {
+                            found = targets != 0;
+                        } else {
+                            T[xs * ROLLOUT_THREADS] = targets;
+                            total += __popcll(targets);
+                        }
+                        have = false;
+                    }
+                    if (src_left != 0 && !found) {  // next movable piece (ascending column)
+                        sbit = src_left & (~src_left + 1ull);
+                        src_left ^= sbit;
+                        have = true;
+                        const int cell = __ffsll((long long)sbit) - 1;
+                        xs = cell - row * g.W;
+                        occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
+                        open = variant == BGS_BOUNCE_SOURCE_BLOCKED ? (g.board & ~sbit) : g.board;
+                        inter = open & ~occS & ~g.far(mg_player);
+                        expanded = sbit;
+                        targets = 0;
+                        Ff = 0; Fl = 0; Fr = 0; Nn = sbit;
+                        rem = P.value_at(cell);
+                    } else {
+                        waiting = true;  // move generation complete
+                    }
                 }
-                const uint32_t rr = (t & 3) == 0 ? r[0] : ((t & 3) == 1 ? r[1] : ((t & 3) == 2 ? r[2] : r[3]));
-                int k = (int)__umulhi(rr, (uint32_t)total);
-                // k-th action in ascending (source x, target cell) order
-                int sx = 0;
-                uint64_t tm = T[0];
-                for (;;) {
-                    const int c = __popcll(tm);
-                    if (k < c) break;
-                    k -= c;
-                    ++sx;
-                    tm = T[sx * ROLLOUT_THREADS];
+            }
+            if (!waiting) {
+                // ---- one step of the current segment, all frontier cells at once ------------------------
+                const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn;  // may go left / right (no reversal)
+                const uint64_t all = fl | Fr;
+                const uint64_t nf = mg_player == 0 ? (all << g.W) : (all >> g.W);  // never backwards
+                const uint64_t nl = (fl & g.not_left) >> 1;
+                const uint64_t nr = (fr & g.not_right) << 1;
+                if (rem > 1) {  // intermediate cells: empty, not the far goal row
+                    Ff = nf & inter; Fl = nl & inter; Fr = nr & inter; Nn = 0;
+                    rem = (Ff | Fl | Fr) ? rem - 1 : 0;
+                } else {        // last step: rest on an empty cell, or bounce off a piece
+                    const uint64_t land = (nf | nl | nr) & open;
+                    targets |= land & ~occS;
+                    pending |= land & occS & ~expanded;
+                    rem = 0;
                 }
-                const int scell = row * g.W + sx;
-                const int tcell = nth_set_bit(tm, k);
-                if (p.moves) {
-                    uint8_t* m = p.moves + ((size_t)idx * p.max_plies + (unsigned)t) * 2ull;
-                    *reinterpret_cast<uchar2*>(m) = make_uchar2((unsigned char)scell, (unsigned char)tcell);
-                }
-                move_piece<NP>(P, scell, tcell);
-                ++t;
-                if ((1ull << tcell) & g.far(player)) {
-                    win = player;
-                    alive = false;
-                }
-                player ^= 1;
             }
         }
     }
+    __syncwarp();
 
     if (p.stats) {
         const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);

@@ -97,6 +97,32 @@ def test_moves_and_step_kernels_equal_oracle(oracle):
     assert ended.mean() > 0.3
 
 
+def test_outputs_stay_inside_their_buffers():
+    """Hand-made bounds check (compute-sanitizer is closed on this pool): canaries around every output."""
+    from simulator import _native as N
+
+    H, W = GRID.shape
+    n, cap, pad = 1003, 40, 4096
+    L = N.lib()
+    sizes = {"moves": n * cap * 2, "length": n * 2, "winner": n, "grid": n * H * W, "reward": n * 8}
+    off, total = {}, pad
+    for k, v in sizes.items():
+        off[k] = total
+        total += (v + pad + 255) // 256 * 256
+    buf = torch.full((total,), 0x5A, dtype=torch.uint8, device="cuda")
+    base = buf.data_ptr()
+    stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda")
+    N.check(L.bgs_bounce_rollout(GRID.ctypes.data, H, W, 0, cap, n, 3, 7, base + off["moves"], base + off["length"],
+                                 base + off["winner"], base + off["grid"], base + off["reward"], N.ptr(stats),
+                                 N.stream_ptr(torch)))
+    torch.cuda.synchronize()
+    used = torch.zeros(total, dtype=torch.bool, device="cuda")
+    for k, v in sizes.items():
+        used[off[k]: off[k] + v] = True
+    assert bool((buf[~used] == 0x5A).all()), "a kernel wrote outside its output buffer"
+    assert int(stats[0]) == n
+
+
 def test_truncation_and_unsupported_boards():
     from simulator import batch
 

@@ -261,6 +261,42 @@ def test_pipelined_host_stream_equals_oracle(oracle):
     np.testing.assert_array_equal(st.numpy(), ref["stats"])
 
 
+@pytest.mark.parametrize("cfg", [(6, 7, 4), (8, 9, 5), (5, 5, 3), (2, 3, 2), (1, 5, 2)])
+def test_outputs_stay_inside_their_buffers(cfg):
+    """compute-sanitizer is closed on this pool, so bounds are checked by hand: every output lives
+    between two canary regions of one allocation, the C ABI gets raw interior pointers, and the
+    canaries must come back untouched (this covers the in-place trajectory expansion, the packed
+    board records and the tail group of the row export)."""
+    from simulator import _native as N
+
+    H, W, K = cfg
+    n, HW, pad = 1003, H * W, 4096
+    L = N.lib()
+    pw = L.bgs_connect_packed_words(H, W)
+    sizes = {"actions": n * HW, "length": n, "winner": n, "packed": n * pw * 8, "grid": n * HW, "reward": n * 8}
+    off, total = {}, pad
+    for k, v in sizes.items():
+        off[k] = total
+        total += (v + pad + 255) // 256 * 256
+    buf = torch.full((total,), 0x5A, dtype=torch.uint8, device="cuda")
+    base = buf.data_ptr()
+    stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda")
+    st = N.stream_ptr(torch)
+    N.check(L.bgs_connect_rollout(H, W, K, n, 5, 9, base + off["actions"], base + off["length"], base + off["winner"],
+                                  base + off["packed"], N.ptr(stats), st))
+    N.check(L.bgs_connect_export(H, W, n, base + off["packed"], base + off["winner"], base + off["grid"],
+                                 base + off["reward"], st))
+    torch.cuda.synchronize()
+    used = torch.zeros(total, dtype=torch.bool, device="cuda")
+    for k, v in sizes.items():
+        used[off[k]: off[k] + v] = True
+    assert bool((buf[~used] == 0x5A).all()), "a kernel wrote outside its output buffer"
+    assert int(stats[0]) == n
+    acts = buf[off["actions"]: off["actions"] + n * HW].view(n, HW)
+    length = buf[off["length"]: off["length"] + n].to(torch.int64)
+    assert bool(((acts != 0xFF).sum(dim=1) == length).all())
+
+
 def test_dlpack_export():
     from simulator import batch
 

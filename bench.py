@@ -151,7 +151,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
@@ -406,11 +406,20 @@ def run_b200(args):
             except Exception as e:  # never let the yardstick break the bench line
                 cb["python_api_error"] = repr(e)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner to stdout) get
+    stderr instead.  Returns a file object on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -424,6 +433,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.out = _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -137,6 +137,7 @@ struct RolloutParams {
     uint64_t* final_packed;  // [n, 2*words] (PACKED variants only)
     unsigned long long* stats;  // [BGS_STATS_LEN] or null
     unsigned int* counter;      // zero-initialised claim counter
+    const uint64_t* start;      // START variants: [n, start_words] records written by connect_import_kernel
     uint32_t one;               // always 1: an IMAD multiplier ptxas cannot fold (keeps adds on the FMA pipe)
 };
 
@@ -146,6 +147,7 @@ constexpr int CLAIM_CHUNK = 64;
 // Block-level statistics: every finished game bumps s_hist[length]; draws (only possible on a full
 // board) are counted apart.  A game won at an odd length was won by player 0, at an even length by
 // player 1, so the win counters need no per-game arithmetic at all.
+template <bool PARITY_WINS = true>
 __device__ __forceinline__ void flush_stats(const unsigned int* s_hist, unsigned int s_draws, int HW,
                                             unsigned long long* stats) {
     unsigned long long games = 0, steps = 0, odd = 0, even = 0;
@@ -162,10 +164,12 @@ __device__ __forceinline__ void flush_stats(const unsigned int* s_hist, unsigned
     if ((threadIdx.x & 31) == 0 && games) {
         atomicAdd(&stats[BGS_STAT_GAMES], games);
         atomicAdd(&stats[BGS_STAT_STEPS], steps);
-        atomicAdd(&stats[BGS_STAT_WIN0], odd);
-        atomicAdd(&stats[BGS_STAT_WIN1], even);
+        if (PARITY_WINS) {
+            atomicAdd(&stats[BGS_STAT_WIN0], odd);
+            atomicAdd(&stats[BGS_STAT_WIN1], even);
+        }
     }
-    if (threadIdx.x == 0 && s_draws) {  // draws were counted as wins of the parity class of H*W
+    if (PARITY_WINS && threadIdx.x == 0 && s_draws) {  // draws were counted as wins of the parity class of H*W
         atomicAdd(&stats[BGS_STAT_DRAWS], (unsigned long long)s_draws);
         atomicAdd(&stats[(HW & 1) ? BGS_STAT_WIN0 : BGS_STAT_WIN1], 0ull - (unsigned long long)s_draws);
     }
@@ -231,9 +235,15 @@ __device__ __forceinline__ typename G::nib_t initial_cols(const G& g) {
     return v;
 }
 
-template <class G, int ACT, bool PACKED>
+// Start-position record of the START variants (rollouts from caller-supplied states), written by
+// connect_import_kernel: [p0 words | p1 words | nibble-packed column heights | meta], where meta bit 0
+// = side to move, bit 1 = already ended, bits 8..15 = winner so far + 1.
+__host__ __device__ constexpr int start_words(int HW) { return HW <= 64 ? 4 : 6; }
+
+template <class G, int ACT, bool PACKED, bool START>
 __global__ void __launch_bounds__(ROLLOUT_THREADS)
 connect_rollout_kernel(const G g, const RolloutParams p) {
+    typedef typename G::bb_t bb_t;
     typedef typename G::nib_t nib_t;
     __shared__ unsigned int s_hist[HIST_BINS];
     __shared__ unsigned int s_draws;
@@ -250,31 +260,70 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
     bool retired = false;  // no more game indices for this lane
     uint32_t idx = 0;      // index of the lane's game in [0, n)
     uint32_t pool_next = 0, pool_cnt = 0;
+    // START only: a game is held (it may have length 0), who moves first, explicit outcome counters
+    bool has_game = false;
+    uint32_t first = 0, acc_w0 = 0, acc_w1 = 0, acc_dr = 0;
 
     for (;;) {
         // ---- warp-convergent: retire finished games, claim new ones -------------------------
-        if (!alive && s.t != 0) {
+        if (START ? (has_game && !alive) : (!alive && s.t != 0)) {
+            // slot parity is relative to the side that moved first: undo that for the outputs
+            const int win = (START && s.res >= 0) ? (int)((uint32_t)s.res ^ first) : s.res;
             p.length[idx] = (uint8_t)s.t;
-            p.winner[idx] = (int8_t)s.res;
-            if (PACKED) store_packed(p.final_packed, idx, HW, s.p[0], s.p[1]);
+            p.winner[idx] = (int8_t)win;
+            if (PACKED) store_packed(p.final_packed, idx, HW, s.p[START ? first : 0], s.p[START ? (first ^ 1u) : 1]);
             atomicAdd(&s_hist[s.t], 1u);
-            if (s.res < 0) atomicAdd(&s_draws, 1u);
+            if (START) {
+                acc_w0 += (win == 0); acc_w1 += (win == 1); acc_dr += (win < 0);
+                has_game = false;
+            } else if (s.res < 0) {
+                atomicAdd(&s_draws, 1u);
+            }
             s.t = 0;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, !alive && !retired);
+        const bool need = START ? (!has_game && !retired) : (!alive && !retired);
+        const unsigned m = __ballot_sync(0xffffffffu, need);
         if (m) {
             const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
-            if (!alive && !retired) {
+            if (need) {
                 if (id < p.n_games) {
                     idx = id;
-                    s.p[0] = 0; s.p[1] = 0; s.hts = 0; s.cols = cols0; s.nleg = g.W(); s.res = BGS_WINNER_DRAW;
-                    alive = true;
+                    if (START) {
+                        const uint64_t* rec = p.start + (size_t)id * start_words(HW);
+                        uint64_t meta;
+                        bb_t b0, b1;
+                        if (HW <= 64) {
+                            b0 = (bb_t)rec[0]; b1 = (bb_t)rec[1];
+                            s.hts = (nib_t)rec[2]; meta = rec[3];
+                        } else {
+                            b0 = (bb_t)(((u128)rec[1] << 64) | rec[0]);
+                            b1 = (bb_t)(((u128)rec[3] << 64) | rec[2]);
+                            s.hts = (nib_t)rec[4]; meta = rec[5];
+                        }
+                        first = (uint32_t)meta & 1u;
+                        s.p[0] = first ? b1 : b0;  // p[0] = stones of the side that moves at even plies
+                        s.p[1] = first ? b0 : b1;
+                        const int w_in = (int)((meta >> 8) & 0xFFu) - 1;
+                        s.res = w_in < 0 ? BGS_WINNER_DRAW : (int)((uint32_t)w_in ^ first);
+                        // ascending list of the columns that are not full
+                        s.cols = 0; s.nleg = 0;
+                        for (int c = g.W() - 1; c >= 0; --c)
+                            if ((uint32_t)((s.hts >> (4 * c)) & 15u) < (uint32_t)g.H()) {
+                                s.cols = (s.cols << 4) | (nib_t)c;
+                                s.nleg += 1;
+                            }
+                        alive = ((meta >> 1) & 1ull) == 0ull && s.nleg != 0;
+                        has_game = true;
+                    } else {
+                        s.p[0] = 0; s.p[1] = 0; s.hts = 0; s.cols = cols0; s.nleg = g.W(); s.res = BGS_WINNER_DRAW;
+                        alive = true;
+                    }
                 } else {
                     retired = true;
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, alive)) break;
+        if (!__any_sync(0xffffffffu, alive || (START && has_game))) break;
 
         // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
         const unsigned long long gid = p.game_id0 + idx;
@@ -291,7 +340,46 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
         if (ACT == 2 && started) *reinterpret_cast<uint16_t*>(act_row + (tb >> 1)) = (uint16_t)blk;
     }
     __syncthreads();
-    if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
+    if (p.stats) {
+        flush_stats<!START>(s_hist, s_draws, HW, p.stats);
+        if (START) {
+            const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
+                atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
+                atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
+            }
+        }
+    }
+}
+
+// Start positions in the reference layout (int8 grids) -> start records of the START rollout.
+__global__ void __launch_bounds__(128)
+connect_import_kernel(int H, int W, unsigned long long n, const int8_t* __restrict__ grid,
+                      const int8_t* __restrict__ player, const int8_t* __restrict__ winner_in, uint64_t* rec) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int HW = H * W;
+    const int8_t* gi = grid + i * (unsigned)HW;
+    u128 b0 = 0, b1 = 0;
+    uint64_t hts = 0;
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+            const int v = gi[r * W + c];
+            const int bit = (H - 1 - r) * W + c;
+            if (v == 0) b0 |= (u128)1 << bit;
+            else if (v == 1) b1 |= (u128)1 << bit;
+            if (v >= 0) hts += 1ull << (4 * c);
+        }
+    const int w_in = winner_in ? (int)winner_in[i] : -1;
+    const uint64_t meta = (uint64_t)(player[i] & 1) | (w_in >= 0 ? 2ull : 0ull) | ((uint64_t)((w_in + 1) & 0xFF) << 8);
+    uint64_t* out = rec + i * start_words(HW);
+    if (HW <= 64) {
+        out[0] = (uint64_t)b0; out[1] = (uint64_t)b1; out[2] = hts; out[3] = meta;
+    } else {
+        out[0] = (uint64_t)b0; out[1] = (uint64_t)(b0 >> 64); out[2] = (uint64_t)b1; out[3] = (uint64_t)(b1 >> 64);
+        out[4] = hts; out[5] = meta;
+    }
 }
 
 // ---- LUT kernel: boards with H*W <= 64 and W <= 8 (the 6x7x4 headline board) ------------------
@@ -815,17 +903,22 @@ static int launch_persistent(Kern kern, const RolloutParams& p, cudaStream_t str
 // of at least 4 bytes; other boards store one byte per ply into the pre-filled row
 static int actions_mode(int H, int W) { return ((H * W) % 2 == 0 && H * W >= 4) ? 2 : 1; }
 
-template <class G>
-static int launch_rollout(const G& g, const RolloutParams& p, cudaStream_t stream) {
+template <class G, bool START>
+static int launch_rollout_s(const G& g, const RolloutParams& p, cudaStream_t stream) {
     const int act = p.actions ? actions_mode(g.H(), g.W()) : 0;
     if (p.final_packed) {
-        if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, true>, p, stream, g);
-        if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, true>, p, stream, g);
-        return launch_persistent(connect_rollout_kernel<G, 0, true>, p, stream, g);
+        if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, true, START>, p, stream, g);
+        if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, true, START>, p, stream, g);
+        return launch_persistent(connect_rollout_kernel<G, 0, true, START>, p, stream, g);
     }
-    if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, false>, p, stream, g);
-    if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, false>, p, stream, g);
-    return launch_persistent(connect_rollout_kernel<G, 0, false>, p, stream, g);
+    if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, false, START>, p, stream, g);
+    if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, false, START>, p, stream, g);
+    return launch_persistent(connect_rollout_kernel<G, 0, false, START>, p, stream, g);
+}
+
+template <class G>
+static int launch_rollout(const G& g, const RolloutParams& p, cudaStream_t stream) {
+    return p.start ? launch_rollout_s<G, true>(g, p, stream) : launch_rollout_s<G, false>(g, p, stream);
 }
 
 template <int H, int W, int K>
@@ -869,9 +962,9 @@ static bool force_generic() {
     return v;
 }
 
-extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
-                                   uint8_t* actions, uint8_t* length, int8_t* winner,
-                                   uint64_t* final_packed, int64_t* stats, void* stream_) {
+static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                        const uint64_t* start, uint8_t* actions, uint8_t* length, int8_t* winner,
+                        uint64_t* final_packed, int64_t* stats, void* stream_) {
     if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
@@ -907,9 +1000,10 @@ extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64
         p.stats = reinterpret_cast<unsigned long long*>(stats);
         p.counter = counter;
         p.one = 1u;
+        p.start = start ? start + off * start_words((int)HW) : nullptr;
         e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) { rc = cuda_error(e, "cudaMemsetAsync"); break; }
-        if (H == 6 && W == 7 && K == 4 && !force_generic()) rc = launch_rollout_lut<6, 7, 4>(p, stream);
+        if (H == 6 && W == 7 && K == 4 && !force_generic() && !start) rc = launch_rollout_lut<6, 7, 4>(p, stream);
         else if (H == 6 && W == 7 && K == 4) rc = launch_rollout(StaticGeo<6, 7, 4>(), p, stream);
         else if (H == 8 && W == 9 && K == 5) rc = launch_rollout(StaticGeo<8, 9, 5>(), p, stream);
         else if (H == 10 && W == 12 && K == 6) rc = launch_rollout(StaticGeo<10, 12, 6>(), p, stream);
@@ -919,6 +1013,29 @@ extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64
             rc = launch_export_rows<MODE_ACTIONS>(H, W, p.n_games, nullptr, p.length, p.actions, stream);
     }
     return rc;
+}
+
+extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                                   uint8_t* actions, uint8_t* length, int8_t* winner,
+                                   uint64_t* final_packed, int64_t* stats, void* stream_) {
+    return rollout_impl(H, W, K, n_games, game_id0, seed, nullptr, actions, length, winner, final_packed, stats, stream_);
+}
+
+extern "C" int bgs_connect_start_words(int H, int W) { return start_words(H * W); }
+
+extern "C" int bgs_connect_rollout_from(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                                        const int8_t* grid, const int8_t* player, const int8_t* winner_in,
+                                        uint64_t* workspace, uint8_t* actions, uint8_t* length, int8_t* winner,
+                                        uint64_t* final_packed, int64_t* stats, void* stream_) {
+    if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
+    if (!grid || !player || !workspace) return set_error(BGS_EINVAL, "connect_rollout_from: null required pointer");
+    if (int rc = require_device()) return rc;
+    if (n_games == 0) return BGS_OK;
+    const unsigned long long blocks = (n_games + 127) / 128;
+    connect_import_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(H, W, n_games, grid, player, winner_in,
+                                                                              workspace);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return rollout_impl(H, W, K, n_games, game_id0, seed, workspace, actions, length, winner, final_packed, stats, stream_);
 }
 
 extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,

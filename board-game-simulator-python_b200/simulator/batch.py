@@ -90,8 +90,14 @@ def connect_rollout(
     reward: bool = False,
     stats=None,
     out: RolloutResult | None = None,
+    start: "ConnectBatch | None" = None,
 ) -> RolloutResult:
     """Play ``n_games`` uniform-random Connect-k games to the end on the current CUDA device.
+
+    With ``start`` (a :class:`ConnectBatch` of ``n_games`` positions) the games continue from those
+    positions instead of the empty board -- the leaf evaluation of a tree search: ``length`` and
+    ``actions`` then cover only the plies played by the rollout, and game ``i`` draws from the stream of
+    global id ``game_id0 + i`` starting at draw 0.
 
     ``per_game`` returns ``length`` uint8[n] and ``winner`` int8[n] (0 / 1 / -1 draw); ``actions``
     the trajectories uint8[n, H*W] (0xFF padded); ``final_grid`` int8[n,H,W]; ``reward``
@@ -132,12 +138,26 @@ def connect_rollout(
         stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
     res.stats = stats
     st = N.stream_ptr(torch)
-    N.check(
-        L.bgs_connect_rollout(
-            H, W, K, n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
-            N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
+    if start is None:
+        N.check(
+            L.bgs_connect_rollout(
+                H, W, K, n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
+            )
         )
-    )
+    else:
+        if start.n != n or tuple(start.grid.shape[1:]) != (H, W):
+            raise ValueError("start must hold n_games positions of this configuration")
+        work = torch.empty((n, L.bgs_connect_start_words(H, W)), dtype=torch.int64, device=dev)
+        grid0 = start.grid.contiguous()
+        N.check(
+            L.bgs_connect_rollout_from(
+                H, W, K, n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                N.ptr(grid0), N.ptr(start.player.contiguous()), N.ptr(start.winner.contiguous()), N.ptr(work),
+                N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
+            )
+        )
+        res.extra["workspace"] = work
     if final_grid or reward:
         N.check(
             L.bgs_connect_export(H, W, n, N.ptr(packed), N.ptr(res.winner), N.ptr(res.final_grid), N.ptr(res.reward), st)

@@ -91,6 +91,18 @@ int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64_t game_id0
                         uint8_t* actions, uint8_t* length, int8_t* winner, uint64_t* final_packed,
                         int64_t* stats, void* stream);
 
+/* The same loop from caller-supplied positions (the State objects of connect.cpp:36-46 as tensors:
+ * grid int8[n,H,W], player int8[n] = side to move, winner_in optional int8[n], -1 = nobody has won):
+ * State::from_json -> while !has_ended: actions -> uniform choice -> sample_next_state.
+ * The draw index t counts the plies played in THIS rollout; `length` is that count (0 for a position
+ * that has already ended) and `actions` lists only those plies.
+ * workspace: uint64[n_games * bgs_connect_start_words(H, W)] device scratch (overwritten). */
+int bgs_connect_start_words(int H, int W);
+int bgs_connect_rollout_from(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                             const int8_t* grid, const int8_t* player, const int8_t* winner_in,
+                             uint64_t* workspace, uint8_t* actions, uint8_t* length, int8_t* winner,
+                             uint64_t* final_packed, int64_t* stats, void* stream);
+
 /* State::get_grid (connect.cpp:42) and State::get_reward (connect.cpp:41) for n packed boards:
  * grid optional int8[n,H,W] (-1 / 0 / 1); reward optional float[n,2] from winner int8[n]. */
 int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,

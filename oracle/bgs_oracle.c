@@ -155,6 +155,39 @@ int bgso_connect_rollout(int H, int W, int K, uint64_t n, uint64_t gid0, uint64_
     return 0;
 }
 
+int bgso_connect_rollout_from(int H, int W, int K, uint64_t n, uint64_t gid0, uint64_t seed,
+                              const int8_t* grid, const int8_t* player_in, const int8_t* winner_in,
+                              uint8_t* actions, uint8_t* length, int8_t* winner, int8_t* final_grid,
+                              float* reward, int64_t* stats) {
+    if (H < 1 || W < 1 || K < 1 || H * W > 255) return -1;
+    const int HW = H * W;
+    int8_t* g = (int8_t*)malloc((size_t)HW);
+    int32_t* cols = (int32_t*)malloc(sizeof(int32_t) * (size_t)W);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t gid = gid0 + i;
+        memcpy(g, grid + i * HW, (size_t)HW);
+        int player = player_in[i], win = winner_in ? winner_in[i] : -1, t = 0;
+        if (actions) memset(actions + i * HW, 0xFF, (size_t)HW);
+        for (;;) {
+            int nl = bgso_connect_actions(g, H, W, win, cols);
+            if (nl == 0) break;
+            uint32_t r = bgso_draw(seed, gid, (uint32_t)t, BGSO_DOMAIN_CONNECT);
+            int col = cols[pick(r, (uint32_t)nl)];
+            bgso_connect_next(g, H, W, K, player, win, col, g, &player, &win);
+            if (actions) actions[i * HW + t] = (uint8_t)col;
+            ++t;
+        }
+        if (length) length[i] = (uint8_t)t;
+        if (winner) winner[i] = (int8_t)win;
+        if (final_grid) memcpy(final_grid + i * HW, g, (size_t)HW);
+        if (reward) bgso_reward(win, reward + 2 * i);
+        stats_game(stats, win, t, 0);
+    }
+    free(g);
+    free(cols);
+    return 0;
+}
+
 int64_t bgso_connect_replay(int H, int W, int K, uint64_t n, const uint8_t* actions,
                             const uint8_t* length, const int8_t* winner, const int8_t* final_grid,
                             const float* reward, int64_t* first_bad) {

@@ -67,6 +67,14 @@ void bgso_reward(int winner, float* reward2);
 int bgso_connect_rollout(int H, int W, int K, uint64_t n, uint64_t gid0, uint64_t seed,
                          uint8_t* actions, uint8_t* length, int8_t* winner, int8_t* final_grid,
                          float* reward, int64_t* stats);
+/* Uniform-random rollouts from caller-supplied positions: grid int8[n,H,W], player int8[n] (side to
+ * move), winner_in int8[n] (-1 = nobody has won yet).  Draw t of game i is bgso_draw(seed, gid0+i, t, 0)
+ * with t = plies played IN THIS ROLLOUT.  length = plies played in the rollout (0 for a position that
+ * has already ended); the other outputs as bgso_connect_rollout. */
+int bgso_connect_rollout_from(int H, int W, int K, uint64_t n, uint64_t gid0, uint64_t seed,
+                              const int8_t* grid, const int8_t* player, const int8_t* winner_in,
+                              uint8_t* actions, uint8_t* length, int8_t* winner, int8_t* final_grid,
+                              float* reward, int64_t* stats);
 /* Replays recorded trajectories through bgso_connect_next, checking at every ply that the move is
  * legal and the game has not ended, and at the end that it HAS ended exactly at `length`, and that
  * winner / final_grid / reward (each optional) are identical.  Returns the number of games with any

@@ -135,6 +135,31 @@ def connect_rollout(H, W, K, n, gid0=0, seed=0, want_actions=True, want_grid=Tru
     return res
 
 
+def connect_rollout_from(K, grid, player, winner_in, gid0=0, seed=0):
+    """Rollouts from supplied positions: grid int8[n,H,W], player int8[n], winner_in int8[n]."""
+    grid = np.ascontiguousarray(grid, dtype=np.int8)
+    player = np.ascontiguousarray(player, dtype=np.int8)
+    winner_in = np.ascontiguousarray(winner_in, dtype=np.int8)
+    n, H, W = grid.shape
+    res = {
+        "actions": np.empty((n, H * W), dtype=np.uint8),
+        "length": np.empty(n, dtype=np.uint8),
+        "winner": np.empty(n, dtype=np.int8),
+        "final_grid": np.empty((n, H, W), dtype=np.int8),
+        "reward": np.empty((n, 2), dtype=np.float32),
+        "stats": np.zeros(STATS_LEN, dtype=np.int64),
+    }
+    rc = lib().bgso_connect_rollout_from(
+        C.c_int(H), C.c_int(W), C.c_int(K), C.c_uint64(n), C.c_uint64(gid0), C.c_uint64(seed),
+        _p(grid, C.c_int8), _p(player, C.c_int8), _p(winner_in, C.c_int8), _p(res["actions"], C.c_uint8),
+        _p(res["length"], C.c_uint8), _p(res["winner"], C.c_int8), _p(res["final_grid"], C.c_int8),
+        _p(res["reward"], C.c_float), _p(res["stats"], C.c_int64),
+    )
+    if rc != 0:
+        raise ValueError("oracle: unsupported Connect configuration")
+    return res
+
+
 def connect_replay(H, W, K, actions, length, winner=None, final_grid=None, reward=None):
     """Replays trajectories through the oracle's transition; returns (n_bad, first_bad)."""
     actions = np.ascontiguousarray(actions, dtype=np.uint8)

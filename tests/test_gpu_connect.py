@@ -261,6 +261,36 @@ def test_pipelined_host_stream_equals_oracle(oracle):
     np.testing.assert_array_equal(st.numpy(), ref["stats"])
 
 
+@pytest.mark.parametrize("cfg", [(6, 7, 4), (8, 9, 5), (10, 12, 6), (4, 5, 3), (5, 5, 4)])
+def test_rollouts_from_supplied_positions_equal_oracle(oracle, cfg):
+    """Leaf-evaluation mode: rollouts that continue from arbitrary positions (either side to move,
+    some already won, some full) are bit-identical to the oracle's."""
+    from simulator import batch
+
+    H, W, K = cfg
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(5)
+    b = batch.ConnectBatch.initial(cfg, n)
+    plies = torch.randint(0, H * W + 1, (n,), device="cuda", generator=g)
+    for t in range(H * W):  # random play for a per-state number of plies; illegal / post-end moves are no-ops
+        acts = torch.randint(0, W, (n,), device="cuda", generator=g)
+        acts = torch.where(plies > t, acts, torch.full_like(acts, -1))
+        b, _ = b.step(acts)
+    assert int(b.has_ended.sum()) > 0 and int((b.player == 1).sum()) > 0
+    res = batch.connect_rollout(cfg, n, 21, 1000, per_game=True, actions=True, final_grid=True, reward=True, start=b)
+    torch.cuda.synchronize()
+    ref = oracle.connect_rollout_from(K, b.grid.cpu().numpy(), b.player.cpu().numpy(), b.winner.cpu().numpy(),
+                                      gid0=1000, seed=21)
+    for got, key in ((res.length, "length"), (res.winner, "winner"), (res.actions, "actions"),
+                     (res.final_grid, "final_grid"), (res.reward, "reward"), (res.stats, "stats")):
+        np.testing.assert_array_equal(got.cpu().numpy(), ref[key], err_msg=key)
+    # from the empty board it is the ordinary rollout
+    e = batch.ConnectBatch.initial(cfg, 2000)
+    a = batch.connect_rollout(cfg, 2000, 3, 7, actions=True, start=e)
+    c = batch.connect_rollout(cfg, 2000, 3, 7, actions=True)
+    assert torch.equal(a.actions, c.actions) and torch.equal(a.stats, c.stats)
+
+
 @pytest.mark.parametrize("cfg", [(6, 7, 4), (8, 9, 5), (5, 5, 3), (2, 3, 2), (1, 5, 2)])
 def test_outputs_stay_inside_their_buffers(cfg):
     """compute-sanitizer is closed on this pool, so bounds are checked by hand: every output lives

@@ -353,35 +353,6 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
     }
 }
 
-// Start positions in the reference layout (int8 grids) -> start records of the START rollout.
-__global__ void __launch_bounds__(128)
-connect_import_kernel(int H, int W, unsigned long long n, const int8_t* __restrict__ grid,
-                      const int8_t* __restrict__ player, const int8_t* __restrict__ winner_in, uint64_t* rec) {
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int HW = H * W;
-    const int8_t* gi = grid + i * (unsigned)HW;
-    u128 b0 = 0, b1 = 0;
-    uint64_t hts = 0;
-    for (int r = 0; r < H; ++r)
-        for (int c = 0; c < W; ++c) {
-            const int v = gi[r * W + c];
-            const int bit = (H - 1 - r) * W + c;
-            if (v == 0) b0 |= (u128)1 << bit;
-            else if (v == 1) b1 |= (u128)1 << bit;
-            if (v >= 0) hts += 1ull << (4 * c);
-        }
-    const int w_in = winner_in ? (int)winner_in[i] : -1;
-    const uint64_t meta = (uint64_t)(player[i] & 1) | (w_in >= 0 ? 2ull : 0ull) | ((uint64_t)((w_in + 1) & 0xFF) << 8);
-    uint64_t* out = rec + i * start_words(HW);
-    if (HW <= 64) {
-        out[0] = (uint64_t)b0; out[1] = (uint64_t)b1; out[2] = hts; out[3] = meta;
-    } else {
-        out[0] = (uint64_t)b0; out[1] = (uint64_t)(b0 >> 64); out[2] = (uint64_t)b1; out[3] = (uint64_t)(b1 >> 64);
-        out[4] = hts; out[5] = meta;
-    }
-}
-
 // ---- LUT kernel: boards with H*W <= 64 and W <= 8 (the 6x7x4 headline board) ------------------
 // The ALU pipe (LOP3/SHF, 64 lanes/clk/SM) is what bounds the rollout, so everything that is not
 // the k-in-a-row test is moved off it: the playable-column mask is ONE LOP3 (the top row is bits
@@ -711,13 +682,27 @@ connect_rollout_lut_kernel(const RolloutParams p) {
 constexpr int EXPORT_THREADS = 256;
 enum { MODE_GRID = 0, MODE_ACTIONS = 1 };
 
+// Warp-cooperative copy of `span` contiguous bytes; 128-bit accesses when both sides are 16-byte
+// aligned (`vec`), which they are for torch allocations because 32 rows of any board are a multiple
+// of 32 bytes.
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, unsigned span, unsigned lane, bool vec) {
+    unsigned done = 0;
+    if (vec) {
+        const unsigned nvec = span >> 4;
+        for (unsigned q = lane; q < nvec; q += 32)
+            reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(src)[q];
+        done = nvec << 4;
+    }
+    for (unsigned i = done + lane; i < span; i += 32) dst[i] = src[i];
+}
+
 // 4 one-bit flags (bits 0..3 of x) -> 4 bytes of 0 / 1
 __device__ __forceinline__ uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
 
 template <int MODE>
 __global__ void __launch_bounds__(EXPORT_THREADS)
 connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* __restrict__ packed,
-                           const uint8_t* __restrict__ length, uint8_t* out) {
+                           const uint8_t* __restrict__ length, uint8_t* out, bool vec) {
     extern __shared__ __align__(16) uint8_t s_stage[];
     const int HW = H * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -774,11 +759,7 @@ connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* _
         const unsigned long long g0 = group * 32ull;
         const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
         const unsigned span = rows * (unsigned)HW;
-        uint8_t* base = out + g0 * (unsigned)HW;
-        const unsigned nvec = span >> 4;
-        for (unsigned q = lane; q < nvec; q += 32)
-            reinterpret_cast<uint4*>(base)[q] = reinterpret_cast<const uint4*>(st)[q];
-        for (unsigned i = (nvec << 4) + lane; i < span; i += 32) base[i] = st[i];
+        warp_copy(out + g0 * (unsigned)HW, st, span, lane, vec);
         __syncwarp();
     }
 }
@@ -801,64 +782,119 @@ reward_kernel(unsigned long long n, const int8_t* __restrict__ winner, float2* _
 struct BoardBits {
     u128 p[2];
     uint32_t legal;  // bit c set <=> column c not full
+    uint64_t hts;    // nibble c = stones in column c
     bool full;
 };
 
-__device__ __forceinline__ BoardBits load_grid(const int8_t* __restrict__ g, int H, int W) {
+__device__ __forceinline__ BoardBits load_grid(const uint8_t* g, int H, int W) {
     BoardBits b;
-    b.p[0] = 0; b.p[1] = 0; b.legal = 0;
+    b.p[0] = 0; b.p[1] = 0; b.legal = 0; b.hts = 0;
     for (int r = 0; r < H; ++r)
         for (int c = 0; c < W; ++c) {
-            const int v = g[r * W + c];
+            const int v = (int8_t)g[r * W + c];
             const int bit = (H - 1 - r) * W + c;
             if (v == 0) b.p[0] |= (u128)1 << bit;
             else if (v == 1) b.p[1] |= (u128)1 << bit;
+            if (v >= 0) b.hts += 1ull << (4 * c);
         }
     for (int c = 0; c < W; ++c)
-        if (g[(H - 1) * W + c] < 0) b.legal |= 1u << c;
+        if ((int8_t)g[(H - 1) * W + c] < 0) b.legal |= 1u << c;
     b.full = b.legal == 0;
     return b;
 }
 
-__global__ void __launch_bounds__(128)
+// One warp per 32 consecutive states: the 32*H*W grid bytes are staged through shared memory with
+// 128-bit loads / stores (a row of 42 bytes is not 16-byte aligned, 32 rows are); lane l then works on
+// state g0+l out of shared memory.
+constexpr int STEP_THREADS = 256;
+
+__global__ void __launch_bounds__(STEP_THREADS)
 connect_step_kernel(const DynGeo g, unsigned long long n, const int8_t* __restrict__ grid,
                     const int8_t* __restrict__ player, const int8_t* __restrict__ winner,
                     const int32_t* __restrict__ action, int8_t* grid_out, int8_t* player_out,
                     int8_t* winner_out, uint8_t* ended_out, float* reward_out, uint32_t* legal_out,
-                    int32_t* status) {
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                    int32_t* status, bool vec) {
+    extern __shared__ __align__(16) uint8_t s_stage[];
     const int H = g.H(), W = g.W(), HW = H * W;
-    const int8_t* gi = grid + i * HW;
-    int8_t* go = grid_out + i * HW;
-    BoardBits b = load_grid(gi, H, W);
-    int pl = player[i];
-    int win = winner[i];
-    const int col = action[i];
-    const bool ended = win >= 0 || b.full;
-    const bool legal = !ended && col >= 0 && col < W && ((b.legal >> col) & 1u) && (pl == 0 || pl == 1);
-    int st = 1;
-    int row = 0;
-    if (legal) {
-        st = 0;
-        const u128 occ = b.p[0] | b.p[1];
-        while ((occ >> ((H - 1 - row) * W + col)) & 1) ++row;  // lowest empty cell of the column
-        b.p[pl] |= (u128)1 << ((H - 1 - row) * W + col);
-        if (row == H - 1) b.legal &= ~(1u << col);
-        if (has_run(g, b.p[pl])) win = pl;
-        b.full = b.legal == 0;
-        pl = 1 - pl;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* st_ = s_stage + (size_t)warp * 32 * HW;
+    uint8_t* mine = st_ + lane * HW;
+    const unsigned long long ngroups = (n + 31ull) / 32ull;
+    constexpr int WARPS = STEP_THREADS / 32;
+    for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
+         group += (unsigned long long)gridDim.x * WARPS) {
+        const unsigned long long g0 = group * 32ull;
+        const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
+        const unsigned span = rows * (unsigned)HW;
+        warp_copy(st_, reinterpret_cast<const uint8_t*>(grid) + g0 * (unsigned)HW, span, lane, vec);
+        __syncwarp();
+        const unsigned long long i = g0 + lane;
+        if (i < n) {
+            BoardBits b = load_grid(mine, H, W);
+            int pl = player[i];
+            int win = winner[i];
+            const int col = action[i];
+            const bool ended = win >= 0 || b.full;
+            const bool legal = !ended && col >= 0 && col < W && ((b.legal >> col) & 1u) && (pl == 0 || pl == 1);
+            if (legal) {
+                const int row = (int)((b.hts >> (4 * col)) & 15ull);  // lowest empty cell of the column
+                const u128 me = (pl == 0 ? b.p[0] : b.p[1]) | ((u128)1 << ((H - 1 - row) * W + col));
+                if (row == H - 1) b.legal &= ~(1u << col);
+                if (has_run(g, me)) win = pl;
+                b.full = b.legal == 0;
+                mine[row * W + col] = (uint8_t)pl;
+                pl = 1 - pl;
+            }
+            player_out[i] = (int8_t)pl;
+            winner_out[i] = (int8_t)win;
+            const bool ended_new = win >= 0 || b.full;
+            if (ended_out) ended_out[i] = ended_new;
+            if (legal_out) legal_out[i] = ended_new ? 0u : b.legal;
+            if (reward_out) reinterpret_cast<float2*>(reward_out)[i] = reward_of(win);
+            if (status) status[i] = legal ? 0 : 1;
+        }
+        __syncwarp();
+        warp_copy(reinterpret_cast<uint8_t*>(grid_out) + g0 * (unsigned)HW, st_, span, lane, vec);
+        __syncwarp();
     }
-    if (go != gi)
-        for (int k = 0; k < HW; ++k) go[k] = gi[k];
-    if (legal) go[row * W + col] = (int8_t)(1 - pl);
-    player_out[i] = (int8_t)pl;
-    winner_out[i] = (int8_t)win;
-    const bool ended_new = win >= 0 || b.full;
-    if (ended_out) ended_out[i] = ended_new;
-    if (legal_out) legal_out[i] = ended_new ? 0u : b.legal;
-    if (reward_out) reinterpret_cast<float2*>(reward_out)[i] = reward_of(win);
-    if (status) status[i] = st;
+}
+
+// Start positions in the reference layout (int8 grids) -> start records of the START rollout.
+__global__ void __launch_bounds__(STEP_THREADS)
+connect_import_kernel(int H, int W, unsigned long long n, const int8_t* __restrict__ grid,
+                      const int8_t* __restrict__ player, const int8_t* __restrict__ winner_in, uint64_t* rec,
+                      bool vec) {
+    extern __shared__ __align__(16) uint8_t s_stage[];
+    const int HW = H * W;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* st_ = s_stage + (size_t)warp * 32 * HW;
+    const uint8_t* mine = st_ + lane * HW;
+    const unsigned long long ngroups = (n + 31ull) / 32ull;
+    constexpr int WARPS = STEP_THREADS / 32;
+    for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
+         group += (unsigned long long)gridDim.x * WARPS) {
+        const unsigned long long g0 = group * 32ull;
+        const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
+        warp_copy(st_, reinterpret_cast<const uint8_t*>(grid) + g0 * (unsigned)HW, rows * (unsigned)HW, lane, vec);
+        __syncwarp();
+        const unsigned long long i = g0 + lane;
+        if (i < n) {
+            const BoardBits b = load_grid(mine, H, W);
+            const int w_in = winner_in ? (int)winner_in[i] : -1;
+            const uint64_t meta =
+                (uint64_t)(player[i] & 1) | (w_in >= 0 ? 2ull : 0ull) | ((uint64_t)((w_in + 1) & 0xFF) << 8);
+            uint64_t* out = rec + i * start_words(HW);
+            if (HW <= 64) {
+                reinterpret_cast<ulonglong2*>(out)[0] = make_ulonglong2((uint64_t)b.p[0], (uint64_t)b.p[1]);
+                reinterpret_cast<ulonglong2*>(out)[1] = make_ulonglong2(b.hts, meta);
+            } else {
+                reinterpret_cast<ulonglong2*>(out)[0] = make_ulonglong2((uint64_t)b.p[0], (uint64_t)(b.p[0] >> 64));
+                reinterpret_cast<ulonglong2*>(out)[1] = make_ulonglong2((uint64_t)b.p[1], (uint64_t)(b.p[1] >> 64));
+                reinterpret_cast<ulonglong2*>(out)[2] = make_ulonglong2(b.hts, meta);
+            }
+        }
+        __syncwarp();
+    }
 }
 
 __global__ void __launch_bounds__(128)
@@ -941,7 +977,7 @@ static int launch_export_rows(int H, int W, unsigned long long n, const uint64_t
     unsigned long long blocks = (n + 255ull) / 256ull;
     const unsigned long long cap = (unsigned long long)sm_count() * per_sm;  // one resident wave, grid-stride
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, EXPORT_THREADS, smem, stream>>>(H, W, n, packed, length, out);
+    kern<<<(unsigned)blocks, EXPORT_THREADS, smem, stream>>>(H, W, n, packed, length, out, ((uintptr_t)out & 15u) == 0);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }
@@ -1031,10 +1067,15 @@ extern "C" int bgs_connect_rollout_from(int H, int W, int K, uint64_t n_games, u
     if (!grid || !player || !workspace) return set_error(BGS_EINVAL, "connect_rollout_from: null required pointer");
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
-    const unsigned long long blocks = (n_games + 127) / 128;
-    connect_import_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(H, W, n_games, grid, player, winner_in,
-                                                                              workspace);
-    BGS_CUDA_TRY(cudaGetLastError());
+    {
+        const size_t smem = (size_t)(STEP_THREADS / 32) * 32 * H * W;
+        unsigned long long blocks = (n_games + STEP_THREADS - 1) / STEP_THREADS;
+        const unsigned long long cap = (unsigned long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        connect_import_kernel<<<(unsigned)blocks, STEP_THREADS, smem, (cudaStream_t)stream_>>>(
+            H, W, n_games, grid, player, winner_in, workspace, ((uintptr_t)grid & 15u) == 0);
+        BGS_CUDA_TRY(cudaGetLastError());
+    }
     return rollout_impl(H, W, K, n_games, game_id0, seed, workspace, actions, length, winner, final_packed, stats, stream_);
 }
 
@@ -1071,10 +1112,13 @@ extern "C" int bgs_connect_step(int H, int W, int K, uint64_t n, const int8_t* g
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
     const DynGeo g = make_dyn_geo(H, W, K);
-    const unsigned long long blocks = (n + 127) / 128;
-    connect_step_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream_>>>(
+    const size_t smem = (size_t)(STEP_THREADS / 32) * 32 * H * W;
+    unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    connect_step_kernel<<<(unsigned)blocks, STEP_THREADS, smem, (cudaStream_t)stream_>>>(
         g, n, grid, player, winner, action, grid_out, player_out, winner_out, ended_out, reward_out,
-        legal_out, status);
+        legal_out, status, (((uintptr_t)grid | (uintptr_t)grid_out) & 15u) == 0);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }

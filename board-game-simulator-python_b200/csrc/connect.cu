@@ -699,11 +699,41 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, unsi
 // 4 one-bit flags (bits 0..3 of x) -> 4 bytes of 0 / 1
 __device__ __forceinline__ uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
 
-template <int MODE>
+// Compile-time board: output bytes 4q..4q+3 of a game (cells in the reference's row-major order)
+// come from at most two runs of consecutive board bits, so each 32-bit output word costs a couple of
+// constant shifts and two multiplies; the words go to the (2-byte aligned) stage row as 16-bit stores.
+template <int SH, int SW>
+__device__ __forceinline__ void expand_grid_static(u128 v0, u128 v1, uint8_t* mine) {
+    constexpr int HW = SH * SW;
+    static_assert(HW % 2 == 0, "16-bit stage stores need an even row length");
+#pragma unroll
+    for (int q = 0; q < (HW + 3) / 4; ++q) {
+        constexpr int dummy = 0; (void)dummy;
+        const int c0 = 4 * q;                                   // first cell of this word
+        const int n = (HW - c0) < 4 ? (HW - c0) : 4;            // cells in this word
+        const int r0 = c0 / SW, x0 = c0 % SW;
+        const int n1 = (SW - x0) < n ? (SW - x0) : n;           // cells still in board row r0
+        const int bitA = (SH - 1 - r0) * SW + x0;               // their first bit
+        uint32_t a = (uint32_t)(v0 >> bitA) & ((1u << n1) - 1u);
+        uint32_t b = (uint32_t)(v1 >> bitA) & ((1u << n1) - 1u);
+        if (n1 < n) {                                           // the rest starts board row r0+1
+            const int bitB = (SH - 2 - r0) * SW;
+            a |= ((uint32_t)(v0 >> bitB) & ((1u << (n - n1)) - 1u)) << n1;
+            b |= ((uint32_t)(v1 >> bitB) & ((1u << (n - n1)) - 1u)) << n1;
+        }
+        const uint32_t A = spread4(a), B = spread4(b);
+        const uint32_t v = (0x01010101u - A - B) * 0xFFu + B;  // 0 / 1 / 0xFF per byte
+        *reinterpret_cast<uint16_t*>(mine + c0) = (uint16_t)v;
+        if (n > 2) *reinterpret_cast<uint16_t*>(mine + c0 + 2) = (uint16_t)(v >> 16);
+    }
+}
+
+template <int MODE, int SH = 0, int SW = 0>
 __global__ void __launch_bounds__(EXPORT_THREADS)
 connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* __restrict__ packed,
                            const uint8_t* __restrict__ length, uint8_t* out, bool vec) {
     extern __shared__ __align__(16) uint8_t s_stage[];
+    if (SH) { H = SH; W = SW; }
     const int HW = H * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* st = s_stage + (size_t)warp * 32 * HW;  // multiple of 32 bytes: 16-byte aligned
@@ -724,6 +754,9 @@ connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* _
                     const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(packed + g * 4 + 2);
                     b0[0] = v0.x; b0[1] = v0.y; b1[0] = v1.x; b1[1] = v1.y;
                 }
+                if (SH) {
+                    expand_grid_static<SH ? SH : 2, SW ? SW : 2>(((u128)b0[1] << 64) | b0[0], ((u128)b1[1] << 64) | b1[0], mine);
+                } else
                 // bit row br (bits br*W .. br*W+W-1) is board row H-1-br
                 for (int br = 0; br < H; ++br) {
                     const int bit = br * W, wd = bit >> 6, sh = bit & 63;
@@ -966,11 +999,16 @@ static int launch_rollout_lut(const RolloutParams& p, cudaStream_t stream) {
     return launch_persistent(connect_rollout_lut_kernel<H, W, K, false, false>, p, stream);
 }
 
-template <int MODE>
+template <int MODE, int SH = 0, int SW = 0>
 static int launch_export_rows(int H, int W, unsigned long long n, const uint64_t* packed, const uint8_t* length,
                               uint8_t* out, cudaStream_t stream) {
+    if (MODE == MODE_GRID && SH == 0) {  // compile-time boards of the BASELINE configurations
+        if (H == 6 && W == 7) return launch_export_rows<MODE, 6, 7>(H, W, n, packed, length, out, stream);
+        if (H == 8 && W == 9) return launch_export_rows<MODE, 8, 9>(H, W, n, packed, length, out, stream);
+        if (H == 10 && W == 12) return launch_export_rows<MODE, 10, 12>(H, W, n, packed, length, out, stream);
+    }
     const size_t smem = (size_t)(EXPORT_THREADS / 32) * 32 * H * W;
-    auto kern = connect_export_rows_kernel<MODE>;
+    auto kern = connect_export_rows_kernel<MODE, SH, SW>;
     int per_sm = 0;
     BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EXPORT_THREADS, smem));
     if (per_sm < 1) per_sm = 1;

@@ -203,7 +203,7 @@ struct Lane {
 // ACT: 0 = no trajectory, 1 = one byte per ply straight into the (0xFF pre-filled) row, 2 = four
 // 4-bit columns per 16-bit word, stored once per 4-ply block at the start of the game's own row and
 // expanded in place by connect_export_actions_kernel.
-template <class G, int J, int ACT>
+template <class G, int J, int ACT, bool CHECK = true>
 __device__ __forceinline__ bool play_ply(const G& g, Lane<G>& s, uint32_t r, uint8_t* act_row, uint32_t& blk) {
     constexpr int P = J & 1;
     typedef typename G::bb_t bb_t;
@@ -223,6 +223,7 @@ __device__ __forceinline__ bool play_ply(const G& g, Lane<G>& s, uint32_t r, uin
     if (ACT == 2) blk |= c << (4 * J);
     s.t += 1;
     s.p[P] |= (bb_t)1 << (((uint32_t)g.H() - 1u - h) * (uint32_t)g.W() + c);
+    if (!CHECK) return true;  // opening plies: nobody can own K stones yet and the board cannot be full
     const bool won = has_run(g, s.p[P]);
     if (won) s.res = P;
     return !(won || s.nleg == 0);
@@ -235,18 +236,85 @@ __device__ __forceinline__ typename G::nib_t initial_cols(const G& g) {
     return v;
 }
 
+// ---- opening phase of the generic kernel (same idea as open_games of the LUT kernel below) ----------
+// Lane l of a warp plays the first 8 plies of game base+l; plies before 2K-2 skip the k-in-a-row test
+// (nobody can own K stones yet), and since the whole warp is in the same phase nothing is divergent.
+// The positions are parked in a per-warp shared-memory ring from which free lanes pick up games.
+constexpr int GRING = 64;  // prepared games per warp (>= 31 + 32)
+struct __align__(16) PreparedG {
+    uint64_t b[4];      // p0 lo/hi, p1 lo/hi
+    uint64_t hts, cols;
+    uint32_t nleg, idx, t_res, pad;
+};
+
+template <class G, int ACT>
+__device__ __forceinline__ void open_games_generic(const G& g, const RolloutParams& p, uint32_t base, PreparedG* slot) {
+    typedef typename G::nib_t nib_t;
+    const int HW = g.H() * g.W();
+    const int first_check = 2 * g.K() - 2;  // first ply (0-based) at which the mover can own K stones
+    const uint32_t id = base + (threadIdx.x & 31u);
+    const bool valid = id < p.n_games;
+    const unsigned long long gid = p.game_id0 + id;
+    Lane<G> s;
+    s.p[0] = 0; s.p[1] = 0; s.hts = 0; s.cols = initial_cols(g); s.nleg = g.W(); s.t = 0; s.res = BGS_WINNER_DRAW;
+    bool alive = true;
+    // invalid lanes still play (their results are discarded) but must not write trajectories
+    uint8_t* act_row = (ACT && valid) ? p.actions + (size_t)id * (unsigned)HW : nullptr;
+    uint32_t r[4];
+#define BGS_GOPEN_PLY(J, T, BLK)                                                                      \
+    if ((T) < first_check) {                                                                          \
+        if (ACT == 1 && !act_row) { uint32_t dump = 0; play_ply<G, J, 0, false>(g, s, r[J], nullptr, dump); } \
+        else play_ply<G, J, ACT, false>(g, s, r[J], act_row, BLK);                                    \
+    } else if (alive) {                                                                               \
+        if (ACT == 1 && !act_row) { uint32_t dump = 0; alive = play_ply<G, J, 0, true>(g, s, r[J], nullptr, dump); } \
+        else alive = play_ply<G, J, ACT, true>(g, s, r[J], act_row, BLK);                             \
+    }
+    uint32_t blk0 = 0, blk1 = 0;
+    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 0u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+    BGS_GOPEN_PLY(0, 0, blk0)
+    BGS_GOPEN_PLY(1, 1, blk0)
+    BGS_GOPEN_PLY(2, 2, blk0)
+    BGS_GOPEN_PLY(3, 3, blk0)
+    const uint32_t t4 = s.t;
+    if (alive) {
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 1u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+        BGS_GOPEN_PLY(0, 4, blk1)
+        BGS_GOPEN_PLY(1, 5, blk1)
+        BGS_GOPEN_PLY(2, 6, blk1)
+        BGS_GOPEN_PLY(3, 7, blk1)
+    }
+#undef BGS_GOPEN_PLY
+    if (ACT == 2 && valid) {
+        uint16_t* row = reinterpret_cast<uint16_t*>(p.actions + (size_t)id * (unsigned)HW);
+        row[0] = (uint16_t)blk0;
+        if (s.t > t4) row[1] = (uint16_t)blk1;
+    }
+    const u128 b0 = (u128)s.p[0], b1 = (u128)s.p[1];
+    uint4* dst = reinterpret_cast<uint4*>(slot);
+    dst[0] = make_uint4((uint32_t)b0, (uint32_t)(b0 >> 32), (uint32_t)(b0 >> 64), (uint32_t)(b0 >> 96));
+    dst[1] = make_uint4((uint32_t)b1, (uint32_t)(b1 >> 32), (uint32_t)(b1 >> 64), (uint32_t)(b1 >> 96));
+    const uint64_t hts = (uint64_t)s.hts, cols = (uint64_t)s.cols;
+    dst[2] = make_uint4((uint32_t)hts, (uint32_t)(hts >> 32), (uint32_t)cols, (uint32_t)(cols >> 32));
+    dst[3] = make_uint4(s.nleg, valid ? id : 0xFFFFFFFFu,
+                        s.t | ((uint32_t)(s.res + 1) << 8) | (alive ? 0u : 1u << 16), 0u);
+}
+
 // Start-position record of the START variants (rollouts from caller-supplied states), written by
 // connect_import_kernel: [p0 words | p1 words | nibble-packed column heights | meta], where meta bit 0
 // = side to move, bit 1 = already ended, bits 8..15 = winner so far + 1.
 __host__ __device__ constexpr int start_words(int HW) { return HW <= 64 ? 4 : 6; }
 
-template <class G, int ACT, bool PACKED, bool START>
+template <class G, int ACT, bool PACKED, bool START, bool OPEN>
 __global__ void __launch_bounds__(ROLLOUT_THREADS)
 connect_rollout_kernel(const G g, const RolloutParams p) {
     typedef typename G::bb_t bb_t;
     typedef typename G::nib_t nib_t;
+    static_assert(!(START && OPEN), "rollouts from supplied positions have no opening phase");
     __shared__ unsigned int s_hist[HIST_BINS];
     __shared__ unsigned int s_draws;
+    __shared__ PreparedG s_gring[OPEN ? ROLLOUT_THREADS / 32 : 1][OPEN ? GRING : 1];
+    PreparedG* ring = s_gring[OPEN ? (threadIdx.x >> 5) : 0];
+    uint32_t ring_head = 0, ring_cnt = 0;  // warp-uniform
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) s_draws = 0;
     __syncthreads();
@@ -283,7 +351,41 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
         }
         const bool need = START ? (!has_game && !retired) : (!alive && !retired);
         const unsigned m = __ballot_sync(0xffffffffu, need);
-        if (m) {
+        if (OPEN) {
+            if (m) {
+                const unsigned lane = threadIdx.x & 31u;
+                const uint32_t want = __popc(m);
+                if (ring_cnt < want) {  // warp-uniform: prepare 32 more games (one atomic per 32 ids)
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(p.counter, 32u);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    open_games_generic<G, ACT>(g, p, base, ring + ((ring_head + ring_cnt + lane) & (GRING - 1)));
+                    ring_cnt += 32;
+                    __syncwarp();
+                }
+                if (need) {
+                    const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                    const uint4* src = reinterpret_cast<const uint4*>(ring + ((ring_head + rank) & (GRING - 1)));
+                    const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+                    if (d.y == 0xFFFFFFFFu) {
+                        retired = true;
+                    } else {
+                        s.p[0] = (bb_t)(((u128)a.w << 96) | ((u128)a.z << 64) | ((u128)a.y << 32) | a.x);
+                        s.p[1] = (bb_t)(((u128)b.w << 96) | ((u128)b.z << 64) | ((u128)b.y << 32) | b.x);
+                        s.hts = (nib_t)(((uint64_t)c.y << 32) | c.x);
+                        s.cols = (nib_t)(((uint64_t)c.w << 32) | c.z);
+                        s.nleg = d.x;
+                        idx = d.y;
+                        s.t = d.z & 0xFFu;
+                        s.res = (int)((d.z >> 8) & 0xFFu) - 1;
+                        alive = (d.z >> 16) == 0u;
+                    }
+                }
+                ring_head = (ring_head + want) & (GRING - 1);
+                ring_cnt -= want;
+                __syncwarp();
+            }
+        } else if (m) {
             const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
             if (need) {
                 if (id < p.n_games) {
@@ -323,7 +425,7 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, alive || (START && has_game))) break;
+        if (!__any_sync(0xffffffffu, alive || (START && has_game) || (OPEN && s.t != 0))) break;
 
         // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
         const unsigned long long gid = p.game_id0 + idx;
@@ -972,22 +1074,31 @@ static int launch_persistent(Kern kern, const RolloutParams& p, cudaStream_t str
 // of at least 4 bytes; other boards store one byte per ply into the pre-filled row
 static int actions_mode(int H, int W) { return ((H * W) % 2 == 0 && H * W >= 4) ? 2 : 1; }
 
-template <class G, bool START>
+// BGS_CONNECT_NO_OPENING=1 disables the opening phase of the generic kernel (A/B measurements).
+static bool no_opening() {
+    static const bool v = [] { const char* e = getenv("BGS_CONNECT_NO_OPENING"); return e && e[0] == '1'; }();
+    return v;
+}
+
+template <class G, bool START, bool OPEN>
 static int launch_rollout_s(const G& g, const RolloutParams& p, cudaStream_t stream) {
     const int act = p.actions ? actions_mode(g.H(), g.W()) : 0;
     if (p.final_packed) {
-        if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, true, START>, p, stream, g);
-        if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, true, START>, p, stream, g);
-        return launch_persistent(connect_rollout_kernel<G, 0, true, START>, p, stream, g);
+        if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, true, START, OPEN>, p, stream, g);
+        if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, true, START, OPEN>, p, stream, g);
+        return launch_persistent(connect_rollout_kernel<G, 0, true, START, OPEN>, p, stream, g);
     }
-    if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, false, START>, p, stream, g);
-    if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, false, START>, p, stream, g);
-    return launch_persistent(connect_rollout_kernel<G, 0, false, START>, p, stream, g);
+    if (act == 2) return launch_persistent(connect_rollout_kernel<G, 2, false, START, OPEN>, p, stream, g);
+    if (act == 1) return launch_persistent(connect_rollout_kernel<G, 1, false, START, OPEN>, p, stream, g);
+    return launch_persistent(connect_rollout_kernel<G, 0, false, START, OPEN>, p, stream, g);
 }
 
 template <class G>
 static int launch_rollout(const G& g, const RolloutParams& p, cudaStream_t stream) {
-    return p.start ? launch_rollout_s<G, true>(g, p, stream) : launch_rollout_s<G, false>(g, p, stream);
+    if (p.start) return launch_rollout_s<G, true, false>(g, p, stream);
+    // the opening phase plays 8 plies unconditionally: the board must not be able to fill up in them
+    if (g.H() * g.W() >= 12 && !no_opening()) return launch_rollout_s<G, false, true>(g, p, stream);
+    return launch_rollout_s<G, false, false>(g, p, stream);
 }
 
 template <int H, int W, int K>

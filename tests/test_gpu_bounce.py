@@ -42,6 +42,67 @@ def test_rollouts_equal_oracle(oracle, grid0, rules):
     np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"])
 
 
+def test_rollouts_from_random_start_grids_equal_oracle(oracle):
+    """Random start positions of many shapes (H*W <= 64, W <= 8, values up to 15, pieces anywhere but
+    the goal rows): GPU rollouts equal the oracle's, under the default and one alternative rule set."""
+    from simulator import batch
+
+    rng = np.random.default_rng(3)
+    done = 0
+    for trial in range(40):
+        W = int(rng.integers(1, 9))
+        H = int(rng.integers(3, min(64 // W, 12) + 1))
+        grid0 = np.zeros((H, W), dtype=np.int8)
+        maxv = int(rng.choice([2, 3, 3, 5, 7, 15]))
+        cells = rng.random((H - 2, W)) < rng.uniform(0.1, 0.5)
+        grid0[1:-1][cells] = rng.integers(1, maxv + 1, size=int(cells.sum()))
+        rules = int(rng.choice([0, 0, 1, 2, 4, 6]))
+        n, cap = 400, 48
+        res = batch.bounce_rollout(grid0, n, seed=trial, game_id0=9 * trial, max_plies=cap, rules=rules,
+                                   moves=True, final_grid=True, reward=True)
+        ref = oracle.bounce_rollout(grid0, n, max_plies=cap, gid0=9 * trial, seed=trial, rules=rules)
+        np.testing.assert_array_equal(res.actions.cpu().numpy(), ref["moves"], err_msg=f"trial {trial}")
+        np.testing.assert_array_equal(res.winner.cpu().numpy(), ref["winner"], err_msg=f"trial {trial}")
+        np.testing.assert_array_equal(res.final_grid.cpu().numpy(), ref["final_grid"], err_msg=f"trial {trial}")
+        np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"], err_msg=f"trial {trial}")
+        done += 1
+    assert done == 40
+
+
+def test_object_api_random_games_match_oracle(oracle):
+    """The reference's loop (textual/examples/arena.py:60-69) through simulator.game.bounce on the GPU,
+    checked state by state against the oracle."""
+    import random
+
+    from simulator.game.bounce import Config
+
+    random.seed(1)
+    config = Config(GRID)
+    for _ in range(2):
+        state = config.sample_initial_state()
+        grid, player, ended, winner = GRID.copy(), 0, False, -1
+        plies = 0
+        while not state.has_ended and plies < 60:
+            assert state.player == player
+            np.testing.assert_array_equal(state.grid, grid)
+            ref = [tuple(a) for a in oracle.bounce_actions(grid, player, ended)]
+            actions = state.actions
+            assert [(*a.source.tolist(), *a.target.tolist()) for a in actions] == ref
+            action = random.choice(actions)
+            grid, player, winner, ended = oracle.bounce_next(grid, player - 0, ended, *action.source.tolist(), *action.target.tolist())
+            state = action.sample_next_state()
+            plies += 1
+        assert state.has_ended == ended
+        if ended:
+            assert state.actions == [] and state.reward.tolist() == oracle.reward(winner).tolist()
+    s0 = config.sample_initial_state()
+    with pytest.raises(RuntimeError):
+        s0.action_at(np.array([0, 1]), np.array([5, 5]))
+    assert s0.actions_at(np.array([0, 0])) == []  # not a movable piece
+    with pytest.raises(RuntimeError):
+        s0.actions_at(np.array([9, 9]))  # outside the board
+
+
 def test_replay_default_games_through_the_oracle(oracle):
     from simulator import batch
 

@@ -54,6 +54,27 @@ def test_rollout_generic_boards_equal_oracle(oracle, cfg):
     _assert_equal_to_oracle(oracle, cfg, _run(cfg, 3000, 5, 77), 3000, 5, 77)
 
 
+def test_rollout_board_sweep(oracle):
+    """Every board shape from 1x1 to 8x8 (plus wide / tall extremes) with several K, through the
+    run-time-geometry kernel (with and without the opening phase, packed and per-byte trajectories,
+    one- and two-word boards): trajectories and outcomes equal to the oracle's."""
+    from simulator import batch
+
+    shapes = [(h, w) for h in range(1, 9) for w in range(1, 9)] + [(2, 16), (15, 2), (8, 16), (15, 8), (11, 11), (9, 14)]
+    checked = 0
+    for i, (h, w) in enumerate(shapes):
+        for k in sorted({1 + (i % 3), 4, max(h, w)}):
+            n = 300
+            res = batch.connect_rollout((h, w, k), n, 7 + i, 50 * i, per_game=True, actions=True, final_grid=True)
+            ref = oracle.connect_rollout(h, w, k, n, gid0=50 * i, seed=7 + i)
+            np.testing.assert_array_equal(res.actions.cpu().numpy(), ref["actions"], err_msg=str((h, w, k)))
+            np.testing.assert_array_equal(res.winner.cpu().numpy(), ref["winner"], err_msg=str((h, w, k)))
+            np.testing.assert_array_equal(res.final_grid.cpu().numpy(), ref["final_grid"], err_msg=str((h, w, k)))
+            np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"], err_msg=str((h, w, k)))
+            checked += 1
+    assert checked >= 190
+
+
 def test_ragged_and_tiny_batches(oracle):
     for n in (1, 2, 31, 33, 255, 257):
         _assert_equal_to_oracle(oracle, (6, 7, 4), _run((6, 7, 4), n, 9, 3), n, 9, 3)

@@ -441,8 +441,11 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
                     }
                 }
             }
-            if (!waiting) {
-                // ---- one step of the current segment, all frontier cells at once ------------------------
+            // ---- the steps of the current segment (1..value of the piece), all frontier cells at once.
+            // The whole segment runs inside one iteration: a frontier step is ~50 instructions, the
+            // bookkeeping above ~130, so lanes with a short segment idling here costs far less than
+            // running the bookkeeping branches once per step.
+            while (rem != 0) {
                 const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn;  // may go left / right (no reversal)
                 const uint64_t all = fl | Fr;
                 const uint64_t nf = mg_player == 0 ? (all << g.W) : (all >> g.W);  // never backwards

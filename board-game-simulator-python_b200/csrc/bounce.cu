@@ -305,7 +305,11 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
     int mg_player = 0;      // whose moves are being generated (differs from `player` while probing)
     bool probe = false;     // true: only "does mg_player have any action?" (blocked test)
     bool found = false, have = false;
-    uint64_t occ = 0, src_left = 0, sbit = 0, occS = 0, open = 0, inter = 0, expanded = 0, pending = 0, targets = 0;
+    uint64_t occ = 0, sbit = 0, occS = 0, open = 0, inter = 0, expanded = 0, pending = 0, targets = 0;
+    uint32_t src8 = 0;      // movable pieces not yet expanded: bit x = column x of the source row
+    uint32_t rb[NP];        // the source row of every value plane (bit x = column x)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) rb[i] = 0;
     uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = 0;
     int rem = 0, xs = 0, total = 0, row = 0;
 
@@ -313,7 +317,15 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
         mg_player = pl;
         probe = prb;
         occ = P.occ();
-        src_left = source_row_mask(g, occ, pl, &row) & occ;
+        src8 = 0;
+        if (source_row_mask(g, occ, pl, &row)) {
+            const int base = row * g.W;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                rb[i] = (uint32_t)(P.b[i] >> base) & (uint32_t)g.row0;
+                src8 |= rb[i];
+            }
+        }
         have = false; found = false;
         pending = 0; rem = 0; total = 0;
         if (!prb)
@@ -404,10 +416,18 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
         if (active && !waiting) {
             if (rem == 0) {
                 if (pending != 0) {
-                    // bounce: all unexpanded landing cells that hold a piece of the same value
-                    const int c = __ffsll((long long)pending) - 1;
-                    const int u = P.value_at(c);
-                    const uint64_t S = pending & P.cells_with_value(u);
+                    // bounce: all unexpanded landing cells that hold a piece of the same value as the
+                    // lowest one (membership of that cell in each value plane selects the plane or
+                    // its complement)
+                    const uint64_t low = pending & (~pending + 1ull);
+                    uint64_t S = pending;
+                    int u = 0;
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        const bool in = (P.b[i] & low) != 0;
+                        S &= in ? P.b[i] : ~P.b[i];
+                        u |= in ? (1 << i) : 0;
+                    }
                     pending &= ~S;
                     expanded |= S;
                     Ff = 0; Fl = 0; Fr = 0; Nn = S;
@@ -423,19 +443,21 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
                         }
                         have = false;
                     }
-                    if (src_left != 0 && !found) {  // next movable piece (ascending column)
-                        sbit = src_left & (~src_left + 1ull);
-                        src_left ^= sbit;
+                    if (src8 != 0 && !found) {  // next movable piece (ascending column)
+                        xs = __ffs((int)src8) - 1;
+                        src8 &= src8 - 1u;
                         have = true;
-                        const int cell = __ffsll((long long)sbit) - 1;
-                        xs = cell - row * g.W;
+                        sbit = 1ull << (row * g.W + xs);
                         occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
                         open = variant == BGS_BOUNCE_SOURCE_BLOCKED ? (g.board & ~sbit) : g.board;
                         inter = open & ~occS & ~g.far(mg_player);
                         expanded = sbit;
                         targets = 0;
                         Ff = 0; Fl = 0; Fr = 0; Nn = sbit;
-                        rem = P.value_at(cell);
+                        int u = 0;
+#pragma unroll
+                        for (int i = 0; i < NP; ++i) u |= (int)((rb[i] >> xs) & 1u) << i;
+                        rem = u;
                     } else {
                         waiting = true;  // move generation complete
                     }

@@ -353,6 +353,52 @@ def run_b200(args):
         sync_steps += int(st[N.STAT_STEPS])
     e2e_sync_value = sync_steps / (time.perf_counter() - t0)
 
+    # ---- end to end with REAL tensor inputs: rollouts that continue from caller-supplied positions
+    # (leaf evaluation of a tree search).  Every step copies 4 Mi positions host->device from pinned
+    # memory (grid int8[n,6,7] + player + winner = 44 B each) and the results device->host.
+    fp = None
+    if world == 1:
+        try:
+            n_pos = 4 * 2**20
+            b0 = batch.ConnectBatch.initial(CONFIG, n_pos)
+            gen = torch.Generator(device="cuda").manual_seed(1)
+            for _ in range(10):  # 10 random plies: mid-game positions
+                b0, _ = b0.step(torch.randint(0, CONFIG[1], (n_pos,), device="cuda", generator=gen))
+            h_grid, h_player, h_winner = (t.cpu().pin_memory() for t in (b0.grid, b0.player, b0.winner))
+            d_grid, d_player, d_winner = torch.empty_like(b0.grid), torch.empty_like(b0.player), torch.empty_like(b0.winner)
+            o_len = torch.empty(n_pos, dtype=torch.uint8).pin_memory()
+            o_win = torch.empty(n_pos, dtype=torch.int8).pin_memory()
+            o_stats = torch.zeros(N.STATS_LEN, dtype=torch.int64).pin_memory()
+            fstats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
+            fres, fsteps = None, 0
+            reps = max(3, min(args.steps, 10))
+            for i in range(reps + 2):
+                if i == 2:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    fsteps = 0
+                d_grid.copy_(h_grid, non_blocking=True)
+                d_player.copy_(h_player, non_blocking=True)
+                d_winner.copy_(h_winner, non_blocking=True)
+                fstats.zero_()
+                start = batch.ConnectBatch(CONFIG, d_grid, d_player, d_winner, has_ended=False)
+                fres = batch.connect_rollout(CONFIG, n_pos, SEED, 50_000 * total + i * n_pos, per_game=True,
+                                             stats=fstats, out=fres, start=start)
+                o_len.copy_(fres.length, non_blocking=True)
+                o_win.copy_(fres.winner, non_blocking=True)
+                o_stats.copy_(fstats, non_blocking=True)
+                torch.cuda.synchronize()
+                fsteps += int(o_stats[N.STAT_STEPS])
+            dt = time.perf_counter() - t0
+            fp = {
+                "value": fsteps / dt, "unit": UNIT, "positions_per_step": n_pos,
+                "h2d_bytes_per_step": n_pos * (CONFIG[0] * CONFIG[1] + 2), "d2h_bytes_per_step": n_pos * 2 + N.STATS_LEN * 8,
+                "ms_per_step": 1e3 * dt / reps,
+                "api": "simulator.batch.connect_rollout(start=ConnectBatch) -> bgs_connect_rollout_from, synchronous",
+            }
+        except Exception as e:  # an auxiliary figure must never break the bench line
+            fp = {"error": repr(e)}
+
     if rank == 0:
         props = torch.cuda.get_device_properties(local)
         sms = props.multi_processor_count
@@ -382,6 +428,7 @@ def run_b200(args):
                 "api": "simulator.batch.HostRollout.stream -> bgs_connect_rollout; every batch's length/winner/stats copied to "
                        "pinned host memory, copy of batch i overlapping the kernel of batch i+1",
                 "synchronous_call_value": e2e_sync_value * world,
+                "from_positions": fp,
             },
             "gpu_launches": args.steps,
             "gpu_launches_note": "1 connect_rollout_kernel per step in each timed region (value, kernel-only, e2e)",

@@ -1,1 +1,1 @@
-from .protocol import ConfigLike, StateLike, ActionLike  # noqa: F401
+"""Oracle-backed stand-in for ``simulator.game`` (tests only): the ``connect`` and ``bounce`` submodules."""

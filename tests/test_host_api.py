@@ -36,6 +36,18 @@ def test_surface_matches_reference_stubs():
         connect.Config(height=6, width=7, count=4)
 
 
+def test_protocols_are_satisfied():
+    # reference src/simulator/game/protocol.py:8-29: ConfigLike / StateLike / ActionLike
+    c = connect.Config(6, 7, 4)
+    s = c.sample_initial_state()
+    assert isinstance(c, ConfigLike) and isinstance(connect.Action(s, 0), ActionLike)
+    b = bounce.Config(np.array(DEFAULT_BOUNCE_GRID))
+    assert isinstance(b, ConfigLike) and isinstance(bounce.Action(b.sample_initial_state(), (0, 1), (0, 2)), ActionLike)
+    for cls in (connect.State, bounce.State):
+        for name in ("config", "has_ended", "player", "reward", "actions", "Action"):
+            assert hasattr(cls, name) or name == "config"
+
+
 def test_connect_config_and_json(golden):
     rec = golden["connect"]["test_json"]["json"]
     c = connect.Config(2, 3, 2)

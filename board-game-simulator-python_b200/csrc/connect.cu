@@ -141,7 +141,10 @@ struct RolloutParams {
     uint32_t one;               // always 1: an IMAD multiplier ptxas cannot fold (keeps adds on the FMA pipe)
 };
 
-constexpr int ROLLOUT_THREADS = 256;
+#ifndef BGS_ROLLOUT_THREADS
+#define BGS_ROLLOUT_THREADS 256
+#endif
+constexpr int ROLLOUT_THREADS = BGS_ROLLOUT_THREADS;
 constexpr int CLAIM_CHUNK = 64;
 
 // Block-level statistics: every finished game bumps s_hist[length]; draws (only possible on a full
@@ -656,8 +659,11 @@ __device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base
     dst[1] = make_uint4(e.ht_lo, e.ht_hi, e.idx, e.t_res);
 }
 
+#ifndef BGS_LUT_MIN_BLOCKS
+#define BGS_LUT_MIN_BLOCKS 1
+#endif
 template <int H, int W, int K, bool ACTIONS, bool PACKED>
-__global__ void __launch_bounds__(ROLLOUT_THREADS)
+__global__ void __launch_bounds__(ROLLOUT_THREADS, BGS_LUT_MIN_BLOCKS)
 connect_rollout_lut_kernel(const RolloutParams p) {
     static_assert(H * W <= 64 && W <= 8, "LUT kernel: one 64-bit board word, at most 8 columns");
     constexpr int WARPS = ROLLOUT_THREADS / 32;

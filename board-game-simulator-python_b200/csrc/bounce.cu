@@ -257,6 +257,11 @@ struct RolloutParams {
     float* reward;       // [n, 2]
     unsigned long long* stats;
     unsigned int* counter;
+    // rollouts from caller-supplied positions (all null: every game starts from plane0, player 0)
+    const int8_t* start_grid;     // [n, H*W]
+    const int8_t* start_player;   // [n]
+    const int8_t* start_winner;   // [n] or null
+    const uint8_t* start_ended;   // [n] or null
 };
 
 constexpr int ROLLOUT_THREADS = 128;
@@ -313,6 +318,7 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
     uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = 0;
     int rem = 0, xs = 0, total = 0, row = 0;
 
+    uint32_t idx = 0;  // index of the lane's game in [0, n)
     auto begin_movegen = [&](int pl, bool prb) {
         mg_player = pl;
         probe = prb;
@@ -332,13 +338,30 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
             for (int x = 0; x < g.W; ++x) T[x * ROLLOUT_THREADS] = 0ull;
     };
     auto begin_game = [&]() {
+        t = 0;
+        if (p.start_grid) {  // per-game start position (reference-layout grid)
+            const int8_t* gi = p.start_grid + (size_t)idx * HW;
 #pragma unroll
-        for (int i = 0; i < NP; ++i) P.b[i] = p.plane0[i];
-        player = 0; t = 0; win = BGS_WINNER_DRAW;
-        begin_movegen(0, false);
+            for (int i = 0; i < NP; ++i) P.b[i] = 0;
+            for (int c = 0; c < HW; ++c) {
+                const int v = gi[c];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) P.b[i] |= (uint64_t)((v >> i) & 1) << c;
+            }
+            player = p.start_player[idx] & 1;
+            win = p.start_winner ? (int)p.start_winner[idx] : BGS_WINNER_DRAW;
+            const bool ended = win >= 0 || (p.start_ended && p.start_ended[idx]);
+            begin_movegen(player, false);
+            if (ended) src8 = 0;  // no move generation: the ply transition sees total == 0 at t == 0
+        } else {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) P.b[i] = p.plane0[i];
+            player = 0; win = BGS_WINNER_DRAW;
+            begin_movegen(0, false);
+        }
     };
 
-    uint32_t idx = atomicAdd(p.counter, 1u);
+    idx = atomicAdd(p.counter, 1u);
     bool active = idx < p.n_games;
     bool waiting = false;  // move generation complete, ply transition not yet executed
     if (active) begin_game();
@@ -650,14 +673,14 @@ static int launch_bounce_rollout(const Geo& g, const RolloutParams& p, cudaStrea
     return BGS_OK;
 }
 
-extern "C" int bgs_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n_games,
-                                  uint64_t game_id0, uint64_t seed, uint8_t* moves, uint16_t* length,
-                                  int8_t* winner, int8_t* final_grid, float* reward, int64_t* stats,
-                                  void* stream_) {
-    if (!grid0) return set_error(BGS_EINVAL, "bounce_rollout: null grid0");
+static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, const int8_t* start_player,
+                               const int8_t* start_winner, const uint8_t* start_ended, int H, int W, int rules,
+                               int max_plies, uint64_t n_games, uint64_t game_id0, uint64_t seed, uint8_t* moves,
+                               uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward, int64_t* stats,
+                               void* stream_) {
     if (max_plies < 0 || max_plies > 65535) return set_error(BGS_EINVAL, "bounce_rollout: max_plies out of range");
     int maxv = 0;
-    if (H >= 1 && W >= 1 && H * W <= 64)
+    if (grid0 && H >= 1 && W >= 1 && H * W <= 64)
         for (int c = 0; c < H * W; ++c) {
             if (grid0[c] < 0) return set_error(BGS_EINVAL, "bounce_rollout: negative cell value");
             if (grid0[c] > maxv) maxv = grid0[c];
@@ -675,16 +698,38 @@ extern "C" int bgs_bounce_rollout(const int8_t* grid0, int H, int W, int rules, 
     p.max_plies = max_plies;
     for (int i = 0; i < 4; ++i) {
         p.plane0[i] = 0;
-        for (int c = 0; c < H * W; ++c) p.plane0[i] |= (uint64_t)((grid0[c] >> i) & 1) << c;
+        if (grid0)
+            for (int c = 0; c < H * W; ++c) p.plane0[i] |= (uint64_t)((grid0[c] >> i) & 1) << c;
     }
     p.moves = moves; p.length = length; p.winner = winner; p.final_grid = final_grid; p.reward = reward;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
+    p.start_grid = start_grid; p.start_player = start_player; p.start_winner = start_winner; p.start_ended = start_ended;
     unsigned int* counter = nullptr;
     if (int rc = next_counter(&counter)) return rc;
     p.counter = counter;
     BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     if (moves) BGS_CUDA_TRY(cudaMemsetAsync(moves, 0xFF, n_games * (size_t)max_plies * 2, stream));
-    return maxv <= 3 ? launch_bounce_rollout<2>(g, p, stream) : launch_bounce_rollout<4>(g, p, stream);
+    // per-game start grids may hold any value up to 15: use the 4-plane kernel
+    return (maxv <= 3 && !start_grid) ? launch_bounce_rollout<2>(g, p, stream) : launch_bounce_rollout<4>(g, p, stream);
+}
+
+extern "C" int bgs_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n_games,
+                                  uint64_t game_id0, uint64_t seed, uint8_t* moves, uint16_t* length,
+                                  int8_t* winner, int8_t* final_grid, float* reward, int64_t* stats,
+                                  void* stream_) {
+    if (!grid0) return set_error(BGS_EINVAL, "bounce_rollout: null grid0");
+    return bounce_rollout_impl(grid0, nullptr, nullptr, nullptr, nullptr, H, W, rules, max_plies, n_games, game_id0,
+                               seed, moves, length, winner, final_grid, reward, stats, stream_);
+}
+
+extern "C" int bgs_bounce_rollout_from(int H, int W, int rules, int max_plies, uint64_t n_games, uint64_t game_id0,
+                                       uint64_t seed, const int8_t* grid, const int8_t* player,
+                                       const int8_t* winner_in, const uint8_t* ended_in, uint8_t* moves,
+                                       uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward,
+                                       int64_t* stats, void* stream_) {
+    if (!grid || !player) return set_error(BGS_EINVAL, "bounce_rollout_from: null required pointer");
+    return bounce_rollout_impl(nullptr, grid, player, winner_in, ended_in, H, W, rules, max_plies, n_games, game_id0,
+                               seed, moves, length, winner, final_grid, reward, stats, stream_);
 }
 
 extern "C" int bgs_bounce_rollout_host(int device, const int8_t* grid0, int H, int W, int rules, int max_plies,

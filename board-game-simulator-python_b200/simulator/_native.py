@@ -38,6 +38,7 @@ _SIGNATURES = {
     "bgs_bounce_moves": (C.c_int, [_i32, _i32, _i32, _u64] + [_vp] * 7),
     "bgs_bounce_step": (C.c_int, [_i32, _i32, _i32, _u64] + [_vp] * 12),
     "bgs_bounce_rollout": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 7),
+    "bgs_bounce_rollout_from": (C.c_int, [_i32, _i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 11),
     "bgs_bounce_rollout_host": (C.c_int, [_i32, _vp, _i32, _i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 6),
 }
 

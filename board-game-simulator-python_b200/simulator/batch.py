@@ -351,17 +351,26 @@ def bounce_rollout(
     final_grid: bool = False,
     reward: bool = False,
     stats=None,
+    start: "BounceBatch | None" = None,
 ) -> RolloutResult:
     """Play ``n_games`` uniform-random Bounce games from ``config`` (a ``bounce.Config`` or an int8
-    grid) on the current CUDA device.  Games still running after ``max_plies`` plies are reported
+    grid) on the current CUDA device -- or, with ``start`` (a :class:`BounceBatch` of ``n_games``
+    positions; ``config`` may then be None), from those positions.  Games still running after ``max_plies`` plies are reported
     with ``winner == -2`` and counted in ``stats[5]``.  ``moves`` returns uint8[n, max_plies, 2] =
     (source cell, target cell) with cell = y*W + x."""
     torch = N.require_cuda()
     L = N.lib()
-    g = _bounce_grid(config)
-    _bounce_check(L, g)
-    H, W = g.shape
     n = int(n_games)
+    if start is None:
+        g = _bounce_grid(config)
+        _bounce_check(L, g)
+        H, W = g.shape
+    else:
+        if start.n != n:
+            raise ValueError("start must hold n_games positions")
+        H, W = int(start.grid.shape[1]), int(start.grid.shape[2])
+        if not L.bgs_bounce_supported(H, W, 0):
+            raise RuntimeError(f"Bounce {H}x{W} is not supported by the CUDA kernels (need H*W <= 64, W <= 8)")
     dev = torch.device("cuda", torch.cuda.current_device())
     res = RolloutResult(n_games=n, game_id0=int(game_id0), seed=int(seed), stats=None)
     res.length = torch.empty(n, dtype=torch.int16, device=dev) if per_game else None
@@ -373,13 +382,23 @@ def bounce_rollout(
         stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
     res.stats = stats
     res.extra["max_plies"] = int(max_plies)
-    N.check(
-        L.bgs_bounce_rollout(
-            g.ctypes.data, H, W, int(rules), int(max_plies), n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
-            N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(res.final_grid), N.ptr(res.reward),
-            N.ptr(stats), N.stream_ptr(torch),
+    if start is None:
+        N.check(
+            L.bgs_bounce_rollout(
+                g.ctypes.data, H, W, int(rules), int(max_plies), n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(res.final_grid), N.ptr(res.reward),
+                N.ptr(stats), N.stream_ptr(torch),
+            )
         )
-    )
+    else:
+        N.check(
+            L.bgs_bounce_rollout_from(
+                H, W, int(rules), int(max_plies), n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                N.ptr(start.grid.contiguous()), N.ptr(start.player.contiguous()), N.ptr(start.winner.contiguous()),
+                N.ptr(start.has_ended.contiguous()), N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner),
+                N.ptr(res.final_grid), N.ptr(res.reward), N.ptr(stats), N.stream_ptr(torch),
+            )
+        )
     return res
 
 

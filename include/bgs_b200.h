@@ -166,6 +166,14 @@ int bgs_bounce_rollout(const int8_t* grid0_host, int H, int W, int rules, int ma
                        uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward,
                        int64_t* stats, void* stream);
 
+/* The same loop from per-game positions (BounceBatch tensors): grid int8[n,H,W] (values 0..15), player
+ * int8[n], winner_in optional int8[n] (-1 none), ended_in optional uint8[n]; all DEVICE pointers.  Draws
+ * and `length` count the plies played in this rollout. */
+int bgs_bounce_rollout_from(int H, int W, int rules, int max_plies, uint64_t n_games, uint64_t game_id0,
+                            uint64_t seed, const int8_t* grid, const int8_t* player, const int8_t* winner_in,
+                            const uint8_t* ended_in, uint8_t* moves, uint16_t* length, int8_t* winner,
+                            int8_t* final_grid, float* reward, int64_t* stats, void* stream);
+
 int bgs_bounce_rollout_host(int device, const int8_t* grid0_host, int H, int W, int rules,
                             int max_plies, uint64_t n_games, uint64_t game_id0, uint64_t seed,
                             uint8_t* moves, uint16_t* length, int8_t* winner, int8_t* final_grid,

@@ -372,9 +372,13 @@ int bgso_bounce_next(const int8_t* grid, int H, int W, int player, int ended, in
     return 0;
 }
 
-int bgso_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n,
-                        uint64_t gid0, uint64_t seed, uint8_t* moves, uint16_t* length,
-                        int8_t* winner, int8_t* final_grid, float* reward, int64_t* stats) {
+/* shared body: per_game == 0 -> every game starts from grid0 with player 0; otherwise game i starts
+ * from grid0 + i*H*W with player_in[i], winner_in[i] (optional) and ended_in[i] (optional). */
+static int bounce_rollout_impl(const int8_t* grid0, int per_game, const int8_t* player_in,
+                               const int8_t* winner_in, const uint8_t* ended_in, int H, int W, int rules,
+                               int max_plies, uint64_t n, uint64_t gid0, uint64_t seed, uint8_t* moves,
+                               uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward,
+                               int64_t* stats) {
     const int HW = H * W;
     if (HW > 255 || max_plies < 0 || max_plies > 65535) return -1;
     const int cap = W * HW;
@@ -382,10 +386,13 @@ int bgso_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_pl
     int32_t* acts = (int32_t*)malloc(sizeof(int32_t) * 4 * (size_t)cap);
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t gid = gid0 + i;
-        memcpy(g, grid0, (size_t)HW);
-        int player = 0, win = -1, end = 0, t = 0;
+        memcpy(g, per_game ? grid0 + i * HW : grid0, (size_t)HW);
+        int player = per_game ? player_in[i] : 0;
+        int win = (per_game && winner_in) ? winner_in[i] : -1;
+        int end = win >= 0 || (per_game && ended_in && ended_in[i]);
+        int t = 0;
         if (moves) memset(moves + i * 2 * (size_t)max_plies, 0xFF, 2 * (size_t)max_plies);
-        /* a start position in which the first player is already blocked has no actions: treat as
+        /* a start position in which the side to move is already blocked has no actions: treat as
          * ended-with-no-winner (README.md:60 promises an action whenever has_ended is false) */
         while (!end && t < max_plies) {
             int na = bgso_bounce_actions(g, H, W, player, end, rules, acts, cap);
@@ -409,6 +416,21 @@ int bgso_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_pl
     free(g);
     free(acts);
     return 0;
+}
+
+int bgso_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n,
+                        uint64_t gid0, uint64_t seed, uint8_t* moves, uint16_t* length,
+                        int8_t* winner, int8_t* final_grid, float* reward, int64_t* stats) {
+    return bounce_rollout_impl(grid0, 0, 0, 0, 0, H, W, rules, max_plies, n, gid0, seed, moves, length, winner,
+                               final_grid, reward, stats);
+}
+
+int bgso_bounce_rollout_from(const int8_t* grids, const int8_t* player, const int8_t* winner_in,
+                             const uint8_t* ended_in, int H, int W, int rules, int max_plies, uint64_t n,
+                             uint64_t gid0, uint64_t seed, uint8_t* moves, uint16_t* length, int8_t* winner,
+                             int8_t* final_grid, float* reward, int64_t* stats) {
+    return bounce_rollout_impl(grids, 1, player, winner_in, ended_in, H, W, rules, max_plies, n, gid0, seed, moves,
+                               length, winner, final_grid, reward, stats);
 }
 
 int64_t bgso_bounce_replay(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n,

@@ -104,6 +104,11 @@ int bgso_bounce_next(const int8_t* grid, int H, int W, int player, int ended, in
 int bgso_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n,
                         uint64_t gid0, uint64_t seed, uint8_t* moves, uint16_t* length,
                         int8_t* winner, int8_t* final_grid, float* reward, int64_t* stats);
+/* The same from per-game positions: grids int8[n,H,W], player int8[n], winner_in / ended_in optional. */
+int bgso_bounce_rollout_from(const int8_t* grids, const int8_t* player, const int8_t* winner_in,
+                             const uint8_t* ended_in, int H, int W, int rules, int max_plies, uint64_t n,
+                             uint64_t gid0, uint64_t seed, uint8_t* moves, uint16_t* length, int8_t* winner,
+                             int8_t* final_grid, float* reward, int64_t* stats);
 int64_t bgso_bounce_replay(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n,
                            const uint8_t* moves, const uint16_t* length, const int8_t* winner,
                            const int8_t* final_grid, const float* reward, int64_t* first_bad);

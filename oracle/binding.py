@@ -241,6 +241,31 @@ def bounce_rollout(grid0, n, max_plies=512, gid0=0, seed=0, rules=0, want_moves=
     return res
 
 
+def bounce_rollout_from(grids, player, winner_in, ended_in, max_plies=512, gid0=0, seed=0, rules=0):
+    grids = np.ascontiguousarray(grids, dtype=np.int8)
+    player = np.ascontiguousarray(player, dtype=np.int8)
+    winner_in = np.ascontiguousarray(winner_in, dtype=np.int8)
+    ended_in = np.ascontiguousarray(ended_in, dtype=np.uint8)
+    n, H, W = grids.shape
+    res = {
+        "moves": np.empty((n, max_plies, 2), dtype=np.uint8),
+        "length": np.empty(n, dtype=np.uint16),
+        "winner": np.empty(n, dtype=np.int8),
+        "final_grid": np.empty((n, H, W), dtype=np.int8),
+        "reward": np.empty((n, 2), dtype=np.float32),
+        "stats": np.zeros(STATS_LEN, dtype=np.int64),
+    }
+    rc = lib().bgso_bounce_rollout_from(
+        _p(grids, C.c_int8), _p(player, C.c_int8), _p(winner_in, C.c_int8), _p(ended_in, C.c_uint8),
+        C.c_int(H), C.c_int(W), C.c_int(rules), C.c_int(max_plies), C.c_uint64(n), C.c_uint64(gid0), C.c_uint64(seed),
+        _p(res["moves"], C.c_uint8), _p(res["length"], C.c_uint16), _p(res["winner"], C.c_int8),
+        _p(res["final_grid"], C.c_int8), _p(res["reward"], C.c_float), _p(res["stats"], C.c_int64),
+    )
+    if rc != 0:
+        raise ValueError("oracle: unsupported Bounce configuration")
+    return res
+
+
 def bounce_replay(grid0, moves, length, winner=None, final_grid=None, reward=None, rules=0):
     g = _grid8(grid0)
     H, W = g.shape

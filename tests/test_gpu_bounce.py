@@ -184,6 +184,39 @@ def test_outputs_stay_inside_their_buffers():
     assert int(stats[0]) == n
 
 
+def test_rollouts_from_supplied_positions_equal_oracle(oracle):
+    """Leaf-evaluation mode for Bounce: rollouts continued from positions reached by random play
+    (either side to move, some already ended) equal the oracle's."""
+    from simulator import batch
+
+    n = 1500
+    pre = oracle.bounce_rollout(GRID, n, max_plies=40, seed=4)  # positions after <= 40 random plies
+    rng = np.random.default_rng(0)
+    cut = np.minimum(rng.integers(0, 30, size=n), pre["length"]).astype(np.int64)
+    grids = np.repeat(GRID[None], n, 0)
+    player = np.zeros(n, np.int8)
+    winner = np.full(n, -1, np.int8)
+    ended = np.zeros(n, np.uint8)
+    H, W = GRID.shape
+    for i in range(n):
+        g, pl, w, e = GRID.copy(), 0, -1, False
+        for t in range(cut[i]):
+            s, tc = pre["moves"][i, t]
+            g, pl, w, e = oracle.bounce_next(g, pl, e, s % W, s // W, tc % W, tc // W)
+        grids[i], player[i], winner[i], ended[i] = g, pl, w, e
+    assert ended.sum() > 0 and (player == 1).sum() > 0
+    b = batch.BounceBatch(torch.from_numpy(grids).cuda(), torch.from_numpy(player).cuda(), torch.from_numpy(winner).cuda(),
+                          torch.from_numpy(ended).cuda())
+    res = batch.bounce_rollout(None, n, seed=9, game_id0=70, max_plies=64, moves=True, final_grid=True, reward=True, start=b)
+    ref = oracle.bounce_rollout_from(grids, player, winner, ended, max_plies=64, gid0=70, seed=9)
+    np.testing.assert_array_equal(res.actions.cpu().numpy(), ref["moves"])
+    np.testing.assert_array_equal(res.length.cpu().numpy().astype(np.uint16), ref["length"])
+    np.testing.assert_array_equal(res.winner.cpu().numpy(), ref["winner"])
+    np.testing.assert_array_equal(res.final_grid.cpu().numpy(), ref["final_grid"])
+    np.testing.assert_array_equal(res.reward.cpu().numpy(), ref["reward"])
+    np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"])
+
+
 def test_truncation_and_unsupported_boards():
     from simulator import batch
 

@@ -217,11 +217,6 @@ __device__ __forceinline__ void move_piece(Planes<NP>& P, int scell, int tcell) 
     }
 }
 
-__device__ __forceinline__ int nth_set_bit(uint64_t m, int k) {
-    for (int i = 0; i < k; ++i) m &= m - 1ull;
-    return __ffsll((long long)m) - 1;
-}
-
 __device__ __forceinline__ float2 reward_of(int winner) {
     return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
                        winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));

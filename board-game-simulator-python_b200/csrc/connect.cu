@@ -776,6 +776,178 @@ connect_rollout_lut_kernel(const RolloutParams p) {
     if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
 }
 
+// ---- line kernel: boards of more than 64 cells (8x9x5, 10x12x6) -----------------------------------
+// On a two-word (unsigned __int128) board the shift-and-AND run test costs ~100 ALU instructions per
+// ply.  This kernel keeps no bitboard at all: every line of the board (H rows, W columns, H+W-1
+// diagonals, H+W-1 anti-diagonals) is one 32-bit shared-memory word holding player 0's stones in
+// bits 0..15 and player 1's in bits 16..31.  A move ORs one bit into the 4 lines through the new
+// cell and tests those 4 words for K consecutive bits: the opponent cannot own a run (the game would
+// be over), and bit 15 of each half is never used (lines are at most 15 long), so the whole word is
+// tested without extracting the mover's half.  Lines are stored [group of 4 lines][thread][4] so that
+// a game is reset with 128-bit stores and accesses of different lanes land in different banks.
+constexpr int LINES_THREADS = 128;
+
+template <int H, int W>
+struct LineGeo {
+    static constexpr int D = H + W - 1;
+    static constexpr int NL = H + W + 2 * D;  // rows | columns | diagonals | anti-diagonals
+    static constexpr int NG = (NL + 3) / 4;
+    static constexpr int COL0 = H, DIA0 = H + W, ANT0 = H + W + D;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
+// K consecutive set bits anywhere in x?
+template <int K>
+__device__ __forceinline__ uint32_t run_bits(uint32_t x) {
+    uint32_t m = x;
+    int len = 1;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        if (2 * len <= K) {
+            m &= m >> len;
+            len *= 2;
+        }
+    }
+    if (len < K) m &= m >> (K - len);
+    return m;
+}
+
+// OR `bit` into line `li` of this thread and return the K-run indicator of the updated word.
+template <int K>
+__device__ __forceinline__ uint32_t line_update(uint32_t lines, uint32_t li, uint32_t bit) {
+    const uint32_t addr = lines + (li >> 2) * (LINES_THREADS * 16) + (li & 3u) * 4u;
+    const uint32_t x = lds_u32(addr) | bit;
+    sts_u32(addr, x);
+    return run_bits<K>(x);
+}
+
+template <int H, int W, int K, int J, int ACT>
+__device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint64_t& hts, uint32_t r, uint32_t& t, int& res,
+                                          uint32_t lut8, uint32_t lines, uint8_t* act_row, uint32_t& blk) {
+    typedef LineGeo<H, W> LG;
+    constexpr int P = J & 1;
+    const uint32_t freem = ~toprow & ((1u << W) - 1u);
+    const uint32_t k = __umulhi(r, (uint32_t)__popc(freem));
+    uint32_t c;
+    if (W <= 8) {
+        c = lds_u8(lut8 + freem * 8u + k);
+    } else {  // k-th set bit of a 16-bit mask from the table of its two bytes
+        const uint32_t lo8 = freem & 0xFFu, nlo = (uint32_t)__popc(lo8);
+        const bool hi = k >= nlo;
+        c = lds_u8(lut8 + (hi ? (freem >> 8) : lo8) * 8u + (hi ? k - nlo : k)) + (hi ? 8u : 0u);
+    }
+    const uint32_t sh = 4u * c;
+    const uint32_t h = (uint32_t)(hts >> sh) & 15u;
+    hts += 1ull << sh;
+    if (h == (uint32_t)(H - 1)) toprow |= 1u << c;
+    if (ACT == 1) act_row[t] = (uint8_t)c;
+    if (ACT == 2) blk |= c << (4 * J);
+    t += 1;
+    const uint32_t bc = 1u << (c + 16u * P), bh = 1u << (h + 16u * P);
+    uint32_t w = line_update<K>(lines, h, bc);                                // row h, position c
+    w |= line_update<K>(lines, LG::COL0 + c, bh);                             // column c, position h
+    w |= line_update<K>(lines, LG::DIA0 + c + (uint32_t)(H - 1) - h, bc);      // diagonal (c - h const)
+    w |= line_update<K>(lines, LG::ANT0 + c + h, bc);                         // anti-diagonal (c + h const)
+    const bool won = w != 0;
+    if (won) res = P;
+    return !(won || t == (uint32_t)(H * W));
+}
+
+template <int H, int W, int K, int ACT, bool PACKED>
+__global__ void __launch_bounds__(LINES_THREADS)
+connect_rollout_lines_kernel(const RolloutParams p) {
+    typedef LineGeo<H, W> LG;
+    static_assert(H <= 15 && W <= 15, "bit 15 of each half word must stay free");
+    constexpr int HW = H * W;
+    __shared__ unsigned int s_hist[HIST_BINS];
+    __shared__ unsigned int s_draws;
+    __shared__ uint8_t s_lut8[256 * 8];  // [byte mask][k] -> index of the k-th set bit
+    __shared__ __align__(16) uint32_t s_lines[LG::NG * LINES_THREADS * 4];
+    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_draws = 0;
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+        int mask = i >> 3, k = i & 7, c = 0;
+        for (; c < 8; ++c)
+            if ((mask >> c) & 1) {
+                if (k == 0) break;
+                --k;
+            }
+        s_lut8[i] = (uint8_t)(c < 8 ? c : 0);
+    }
+    __syncthreads();
+    const uint32_t lut8 = (uint32_t)__cvta_generic_to_shared(s_lut8);
+    uint4* my_lines = reinterpret_cast<uint4*>(s_lines) + threadIdx.x;  // group g at my_lines[g * LINES_THREADS]
+    const uint32_t lines = (uint32_t)__cvta_generic_to_shared(my_lines);
+
+    uint32_t toprow = 0, t = 0;
+    uint64_t hts = 0;
+    int res = BGS_WINNER_DRAW;
+    bool alive = false, retired = false;
+    uint32_t idx = 0, pool_next = 0, pool_cnt = 0;
+
+    for (;;) {
+        // ---- warp-convergent: retire finished games, claim new ones -------------------------
+        if (!alive && t != 0) {
+            p.length[idx] = (uint8_t)t;
+            p.winner[idx] = (int8_t)res;
+            if (PACKED) {  // rebuild the two bitboards from the row lines
+                u128 b0 = 0, b1 = 0;
+#pragma unroll
+                for (int r = 0; r < H; ++r) {
+                    const uint32_t x = lds_u32(lines + (r >> 2) * (LINES_THREADS * 16) + (r & 3) * 4);
+                    b0 |= (u128)(x & 0xFFFFu) << ((H - 1 - r) * W);
+                    b1 |= (u128)(x >> 16) << ((H - 1 - r) * W);
+                }
+                store_packed(p.final_packed, idx, HW, b0, b1);
+            }
+            atomicAdd(&s_hist[t], 1u);
+            if (res < 0) atomicAdd(&s_draws, 1u);
+            t = 0;
+        }
+        const bool need = !alive && !retired;
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
+            if (need) {
+                if (id < p.n_games) {
+                    idx = id;
+#pragma unroll
+                    for (int g = 0; g < LG::NG; ++g) my_lines[g * LINES_THREADS] = make_uint4(0u, 0u, 0u, 0u);
+                    toprow = 0; hts = 0; res = BGS_WINNER_DRAW;
+                    alive = true;
+                } else {
+                    retired = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+
+        // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
+        const unsigned long long gid = p.game_id0 + idx;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+        uint8_t* act_row = ACT ? p.actions + (size_t)idx * HW : nullptr;
+        const bool started = alive;
+        const uint32_t tb = t;
+        uint32_t blk = 0;
+        if (alive) alive = lines_ply<H, W, K, 0, ACT>(toprow, hts, r[0], t, res, lut8, lines, act_row, blk);
+        if (alive) alive = lines_ply<H, W, K, 1, ACT>(toprow, hts, r[1], t, res, lut8, lines, act_row, blk);
+        if (alive) alive = lines_ply<H, W, K, 2, ACT>(toprow, hts, r[2], t, res, lut8, lines, act_row, blk);
+        if (alive) alive = lines_ply<H, W, K, 3, ACT>(toprow, hts, r[3], t, res, lut8, lines, act_row, blk);
+        if (ACT == 2 && started) *reinterpret_cast<uint16_t*>(act_row + (tb >> 1)) = (uint16_t)blk;
+    }
+    __syncthreads();
+    if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
+}
+
 // ---------------------------------------------------------------------------------------------
 // export: per-game records -> the reference's row layouts.  HBM-bound.
 //   MODE_GRID    packed boards (16 / 32 B per game)      -> int8[n,H,W] grids (-1 / 0 / 1)
@@ -1116,6 +1288,32 @@ static int launch_rollout_lut(const RolloutParams& p, cudaStream_t stream) {
     return launch_persistent(connect_rollout_lut_kernel<H, W, K, false, false>, p, stream);
 }
 
+template <typename Kern>
+static int launch_persistent_n(Kern kern, int threads, const RolloutParams& p, cudaStream_t stream) {
+    int per_sm = 0;
+    BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long want = ((unsigned long long)p.n_games + threads - 1) / threads;
+    unsigned long long blocks = (unsigned long long)sm_count() * per_sm;
+    if (want < blocks) blocks = want ? want : 1;
+    kern<<<(unsigned)blocks, threads, 0, stream>>>(p);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+template <int H, int W, int K>
+static int launch_rollout_lines(const RolloutParams& p, cudaStream_t stream) {
+    const int act = p.actions ? actions_mode(H, W) : 0;
+    if (p.final_packed) {
+        if (act == 2) return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 2, true>, LINES_THREADS, p, stream);
+        if (act == 1) return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 1, true>, LINES_THREADS, p, stream);
+        return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 0, true>, LINES_THREADS, p, stream);
+    }
+    if (act == 2) return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 2, false>, LINES_THREADS, p, stream);
+    if (act == 1) return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 1, false>, LINES_THREADS, p, stream);
+    return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 0, false>, LINES_THREADS, p, stream);
+}
+
 template <int MODE, int SH = 0, int SW = 0>
 static int launch_export_rows(int H, int W, unsigned long long n, const uint64_t* packed, const uint8_t* length,
                               uint8_t* out, cudaStream_t stream) {
@@ -1196,6 +1394,8 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
         if (e != cudaSuccess) { rc = cuda_error(e, "cudaMemsetAsync"); break; }
         if (H == 6 && W == 7 && K == 4 && !force_generic() && !start) rc = launch_rollout_lut<6, 7, 4>(p, stream);
         else if (H == 6 && W == 7 && K == 4) rc = launch_rollout(StaticGeo<6, 7, 4>(), p, stream);
+        else if (H == 8 && W == 9 && K == 5 && !force_generic() && !start) rc = launch_rollout_lines<8, 9, 5>(p, stream);
+        else if (H == 10 && W == 12 && K == 6 && !force_generic() && !start) rc = launch_rollout_lines<10, 12, 6>(p, stream);
         else if (H == 8 && W == 9 && K == 5) rc = launch_rollout(StaticGeo<8, 9, 5>(), p, stream);
         else if (H == 10 && W == 12 && K == 6) rc = launch_rollout(StaticGeo<10, 12, 6>(), p, stream);
         else rc = launch_rollout(make_dyn_geo(H, W, K), p, stream);

@@ -125,7 +125,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    per_step = max(1.0, min(15.0, 60.0 / max(1, args.steps + args.warmup)))
+    per_step = args.ref_seconds or max(1.0, min(15.0, 60.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_rollout_throughput(min(per_step, 1.0))
     vals, tot_steps, tot_s = [], 0, 0.0
@@ -478,6 +478,8 @@ def main():
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU, help="concurrent games per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-seconds", type=float, default=0.0,
+                    help="--impl reference: seconds of CPU work per step (default: sized so the run takes ~1 min)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     args.out = _claim_stdout()

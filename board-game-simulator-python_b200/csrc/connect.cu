@@ -783,9 +783,13 @@ connect_rollout_lut_kernel(const RolloutParams p) {
 // bits 0..15 and player 1's in bits 16..31.  A move ORs one bit into the 4 lines through the new
 // cell and tests those 4 words for K consecutive bits: the opponent cannot own a run (the game would
 // be over), and bit 15 of each half is never used (lines are at most 15 long), so the whole word is
-// tested without extracting the mover's half.  Lines are stored [group of 4 lines][thread][4] so that
-// a game is reset with 128-bit stores and accesses of different lanes land in different banks.
+// tested without extracting the mover's half.  Lines are stored [line][thread], so every access of a
+// warp is bank-conflict free whatever lines its lanes touch (measured 9 % faster than a
+// [4 lines][thread][4] layout that resets a game with 128-bit stores).
 constexpr int LINES_THREADS = 128;
+#ifndef BGS_LINES_LAYOUT
+#define BGS_LINES_LAYOUT 1  // 1: [line][thread] (every access conflict-free; measured 9 % faster), 0: [4 lines][thread][4] (128-bit reset)
+#endif
 
 template <int H, int W>
 struct LineGeo {
@@ -823,7 +827,11 @@ __device__ __forceinline__ uint32_t run_bits(uint32_t x) {
 // OR `bit` into line `li` of this thread and return the K-run indicator of the updated word.
 template <int K>
 __device__ __forceinline__ uint32_t line_update(uint32_t lines, uint32_t li, uint32_t bit) {
+#if BGS_LINES_LAYOUT == 1
+    const uint32_t addr = lines + li * (LINES_THREADS * 4);
+#else
     const uint32_t addr = lines + (li >> 2) * (LINES_THREADS * 16) + (li & 3u) * 4u;
+#endif
     const uint32_t x = lds_u32(addr) | bit;
     sts_u32(addr, x);
     return run_bits<K>(x);
@@ -884,7 +892,11 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     }
     __syncthreads();
     const uint32_t lut8 = (uint32_t)__cvta_generic_to_shared(s_lut8);
+#if BGS_LINES_LAYOUT == 1
+    uint32_t* my_lines = s_lines + threadIdx.x;  // line li at my_lines[li * LINES_THREADS]
+#else
     uint4* my_lines = reinterpret_cast<uint4*>(s_lines) + threadIdx.x;  // group g at my_lines[g * LINES_THREADS]
+#endif
     const uint32_t lines = (uint32_t)__cvta_generic_to_shared(my_lines);
 
     uint32_t toprow = 0, t = 0;
@@ -902,7 +914,11 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                 u128 b0 = 0, b1 = 0;
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
+#if BGS_LINES_LAYOUT == 1
+                    const uint32_t x = lds_u32(lines + r * (LINES_THREADS * 4));
+#else
                     const uint32_t x = lds_u32(lines + (r >> 2) * (LINES_THREADS * 16) + (r & 3) * 4);
+#endif
                     b0 |= (u128)(x & 0xFFFFu) << ((H - 1 - r) * W);
                     b1 |= (u128)(x >> 16) << ((H - 1 - r) * W);
                 }
@@ -919,8 +935,13 @@ connect_rollout_lines_kernel(const RolloutParams p) {
             if (need) {
                 if (id < p.n_games) {
                     idx = id;
+#if BGS_LINES_LAYOUT == 1
+#pragma unroll
+                    for (int li = 0; li < LG::NL; ++li) my_lines[li * LINES_THREADS] = 0u;
+#else
 #pragma unroll
                     for (int g = 0; g < LG::NG; ++g) my_lines[g * LINES_THREADS] = make_uint4(0u, 0u, 0u, 0u);
+#endif
                     toprow = 0; hts = 0; res = BGS_WINNER_DRAW;
                     alive = true;
                 } else {
@@ -1351,6 +1372,12 @@ static bool force_generic() {
     return v;
 }
 
+// BGS_CONNECT_LINES=1 runs the 6x7x4 board through the line kernel (A/B measurements).
+static bool force_lines() {
+    static const bool v = [] { const char* e = getenv("BGS_CONNECT_LINES"); return e && e[0] == '1'; }();
+    return v;
+}
+
 static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
                         const uint64_t* start, uint8_t* actions, uint8_t* length, int8_t* winner,
                         uint64_t* final_packed, int64_t* stats, void* stream_) {
@@ -1392,7 +1419,8 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
         p.start = start ? start + off * start_words((int)HW) : nullptr;
         e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) { rc = cuda_error(e, "cudaMemsetAsync"); break; }
-        if (H == 6 && W == 7 && K == 4 && !force_generic() && !start) rc = launch_rollout_lut<6, 7, 4>(p, stream);
+        if (H == 6 && W == 7 && K == 4 && force_lines() && !start) rc = launch_rollout_lines<6, 7, 4>(p, stream);
+        else if (H == 6 && W == 7 && K == 4 && !force_generic() && !start) rc = launch_rollout_lut<6, 7, 4>(p, stream);
         else if (H == 6 && W == 7 && K == 4) rc = launch_rollout(StaticGeo<6, 7, 4>(), p, stream);
         else if (H == 8 && W == 9 && K == 5 && !force_generic() && !start) rc = launch_rollout_lines<8, 9, 5>(p, stream);
         else if (H == 10 && W == 12 && K == 6 && !force_generic() && !start) rc = launch_rollout_lines<10, 12, 6>(p, stream);

@@ -659,11 +659,10 @@ __device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base
     dst[1] = make_uint4(e.ht_lo, e.ht_hi, e.idx, e.t_res);
 }
 
-#ifndef BGS_LUT_MIN_BLOCKS
-#define BGS_LUT_MIN_BLOCKS 1
-#endif
+// NOTE: no minBlocksPerSM argument: with `__launch_bounds__(256, 1)` ptxas spends 72 registers (3 CTAs
+// per SM, 1.02 ms), with (256, 8) it squeezes into 32 (1.04 ms); left alone it uses 40 (6 CTAs, 0.97 ms).
 template <int H, int W, int K, bool ACTIONS, bool PACKED>
-__global__ void __launch_bounds__(ROLLOUT_THREADS, BGS_LUT_MIN_BLOCKS)
+__global__ void __launch_bounds__(ROLLOUT_THREADS)
 connect_rollout_lut_kernel(const RolloutParams p) {
     static_assert(H * W <= 64 && W <= 8, "LUT kernel: one 64-bit board word, at most 8 columns");
     constexpr int WARPS = ROLLOUT_THREADS / 32;

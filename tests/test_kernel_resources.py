@@ -1,0 +1,53 @@
+"""Static resource checks on the built sm_100a code (no GPU needed): the hot kernels must not spill,
+must be compiled for sm_100a, and the headline kernel must keep the register budget its occupancy
+(6 CTAs of 256 threads per SM) depends on -- a stray launch bound once cost 7 % by raising it to 72."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import PRODUCT
+
+LIB = os.path.join(PRODUCT, "csrc", "libbgs_b200.so")
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+
+
+@pytest.fixture(scope="module")
+def usage():
+    if not os.path.exists(LIB):
+        subprocess.run(["make", "-C", os.path.dirname(LIB)], check=True)
+    out = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True, check=True).stdout
+    res, name = {}, None
+    for line in out.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.match(r"\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", line)
+        if m and name:
+            res[name] = tuple(int(v) for v in m.groups())
+    assert "sm_100a" in out
+    return res
+
+
+def _find(usage, *parts):
+    hits = [k for k in usage if all(p in k for p in parts)]
+    assert hits, parts
+    return hits
+
+
+def test_headline_kernel_keeps_its_register_budget(usage):
+    for k in _find(usage, "connect_rollout_lut_kernelILi6ELi7ELi4E"):
+        reg, stack, shared, local = usage[k]
+        assert reg <= 42 and stack == 0 and local == 0, (k, usage[k])
+        assert shared <= 37 * 1024  # 6 CTAs per SM
+
+
+def test_rollout_kernels_do_not_spill(usage):
+    for part in ("connect_rollout_kernel", "connect_rollout_lines_kernel", "bounce_rollout_kernel"):
+        for k in _find(usage, part):
+            reg, stack, shared, local = usage[k]
+            assert stack == 0 and local == 0, (k, usage[k])
+            assert shared <= 48 * 1024 and reg <= 128, (k, usage[k])

@@ -342,7 +342,10 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
             const int win = (START && s.res >= 0) ? (int)((uint32_t)s.res ^ first) : s.res;
             p.length[idx] = (uint8_t)s.t;
             p.winner[idx] = (int8_t)win;
-            if (PACKED) store_packed(p.final_packed, idx, HW, s.p[START ? first : 0], s.p[START ? (first ^ 1u) : 1]);
+            if (PACKED) {
+                const bool swapped = START && first != 0;  // selects, not a dynamically indexed array
+                store_packed(p.final_packed, idx, HW, swapped ? s.p[1] : s.p[0], swapped ? s.p[0] : s.p[1]);
+            }
             atomicAdd(&s_hist[s.t], 1u);
             if (START) {
                 acc_w0 += (win == 0); acc_w1 += (win == 1); acc_dr += (win < 0);

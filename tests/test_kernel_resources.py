@@ -41,7 +41,8 @@ def _find(usage, *parts):
 def test_headline_kernel_keeps_its_register_budget(usage):
     for k in _find(usage, "connect_rollout_lut_kernelILi6ELi7ELi4E"):
         reg, stack, shared, local = usage[k]
-        assert reg <= 42 and stack == 0 and local == 0, (k, usage[k])
+        headline = "ELb0ELb0EE" in k  # no trajectory, no packed boards: the kernel bench.py times
+        assert reg <= (42 if headline else 56) and stack == 0 and local == 0, (k, usage[k])
         assert shared <= 37 * 1024  # 6 CTAs per SM
 
 

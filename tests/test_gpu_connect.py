@@ -348,6 +348,33 @@ def test_outputs_stay_inside_their_buffers(cfg):
     assert bool(((acts != 0xFF).sum(dim=1) == length).all())
 
 
+def test_c_abi_argument_validation():
+    """Bad arguments come back as status codes with a message -- never a crash, never an exception
+    across the ABI (SURVEY.md 8b error contract)."""
+    from simulator import _native as N
+
+    L = N.lib()
+    buf = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+    st = N.stream_ptr(torch)
+    # trajectories need the lengths to be expanded
+    assert L.bgs_connect_rollout(6, 7, 4, 8, 0, 0, N.ptr(buf), None, None, None, None, st) == -1
+    assert "length" in N.last_error()
+    # unsupported boards
+    assert L.bgs_connect_rollout(16, 16, 4, 8, 0, 0, None, None, None, None, None, st) == -2
+    assert L.bgs_connect_step(0, 7, 4, 1, *([N.ptr(buf)] * 12), st) == -2
+    # missing required pointers
+    assert L.bgs_connect_step(6, 7, 4, 1, None, None, None, None, None, None, None, None, None, None, None, st) == -1
+    assert L.bgs_connect_query(6, 7, 1, None, None, None, None, None, st) == -1
+    assert L.bgs_connect_export(6, 7, 4, None, None, N.ptr(buf), None, st) == -1
+    assert L.bgs_connect_rollout_from(6, 7, 4, 4, 0, 0, None, None, None, None, None, None, None, None, None, st) == -1
+    assert L.bgs_bounce_rollout(None, 9, 6, 0, 64, 4, 0, 0, None, None, None, None, None, None, st) == -1
+    assert L.bgs_bounce_moves(9, 9, 0, 1, N.ptr(buf), N.ptr(buf), None, None, N.ptr(buf), None, st) == -2
+    # zero games is a no-op
+    assert L.bgs_connect_rollout(6, 7, 4, 0, 0, 0, None, None, None, None, None, st) == 0
+    torch.cuda.synchronize()
+    assert int(buf.sum()) == 0
+
+
 def test_dlpack_export():
     from simulator import batch
 

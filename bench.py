@@ -330,13 +330,13 @@ def run_b200(args):
     # simulator.batch.HostRollout.stream: every batch's per-game results and statistics are copied
     # device->host into pinned memory inside the timed region (the copy of batch i overlaps the kernel
     # of batch i+1); the loop consumes the host statistics of every batch.
-    host = batch.HostRollout(CONFIG, n)
+    host = batch.HostRollout(CONFIG, n, depth=3, packed=True)  # one byte per game: length | (winner + 1) << 6
     for i in range(min(args.warmup, 3)):
         host.run(SEED, (20_000 + i) * total + rank * n)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = 0
-    for st, length_h, winner_h in host.stream(SEED, 30_000 * total + rank * n * args.steps, args.steps):
+    for st, result_h in host.stream(SEED, 30_000 * total + rank * n * args.steps, args.steps):
         e2e_steps += int(st[N.STAT_STEPS])
     torch.cuda.synchronize()
     e2e_t = torch.tensor(time.perf_counter() - t0, dtype=torch.float64, device=dev)
@@ -345,11 +345,18 @@ def run_b200(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
     e2e_value = int(e2e_n) / float(e2e_t)
-    # the same path, one synchronous call per batch (no overlap), for reference
+    # the same path with separate length / winner arrays (2 bytes per game), pipelined and synchronous
+    host2 = batch.HostRollout(CONFIG, n, depth=3)
+    host2.run(SEED, 39_000 * total + rank * n)
+    t0 = time.perf_counter()
+    un_steps = 0
+    for st, _, _ in host2.stream(SEED, 40_000 * total + rank * n * args.steps, args.steps):
+        un_steps += int(st[N.STAT_STEPS])
+    e2e_unpacked_value = un_steps / (time.perf_counter() - t0)
     t0 = time.perf_counter()
     sync_steps = 0
     for i in range(args.steps):
-        st, _, _ = host.run(SEED, (40_000 + i) * total + rank * n)
+        st, _, _ = host2.run(SEED, (45_000 + i) * total + rank * n)
         sync_steps += int(st[N.STAT_STEPS])
     e2e_sync_value = sync_steps / (time.perf_counter() - t0)
 
@@ -425,13 +432,16 @@ def run_b200(args):
             "e2e": {
                 "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes * world,
                 "d2h_bytes_per_step": host.d2h_bytes * world,
-                "api": "simulator.batch.HostRollout.stream -> bgs_connect_rollout; every batch's length/winner/stats copied to "
-                       "pinned host memory, copy of batch i overlapping the kernel of batch i+1",
+                "api": "simulator.batch.HostRollout(packed=True).stream -> bgs_connect_rollout + bgs_connect_pack_results; "
+                       "every batch's per-game results (1 byte: length | (winner+1)<<6) and statistics copied to pinned "
+                       "host memory, copy of batch i overlapping the kernels of the next batches",
+                "two_arrays_value": e2e_unpacked_value * world,
                 "synchronous_call_value": e2e_sync_value * world,
                 "from_positions": fp,
             },
             "gpu_launches": args.steps,
-            "gpu_launches_note": "1 connect_rollout_kernel per step in each timed region (value, kernel-only, e2e)",
+            "gpu_launches_note": "1 connect_rollout_lut_kernel per step in each timed region (value, kernel-only, e2e; "
+                             "the e2e region adds 1 pack_results_kernel per step)",
             "roofline": {
                 "bound": "int_issue", "achieved": achieved, "peak": peak, "unit": "G thread-instr/s",
                 "frac": achieved / peak, "traffic": traffic,

@@ -1105,6 +1105,25 @@ __device__ __forceinline__ float2 reward_of(int winner) {
                        winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
 }
 
+// length (<= 63) and winner of every game in one byte: bits 0..5 length, bits 6..7 winner + 1.
+// Halves the device->host traffic of the per-game results (16 bytes per thread in, 16 out).
+__global__ void __launch_bounds__(256)
+pack_results_kernel(unsigned long long n, const uint8_t* __restrict__ length, const int8_t* __restrict__ winner,
+                    uint8_t* __restrict__ packed) {
+    const unsigned long long nvec = n / 16ull;
+    for (unsigned long long v = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v < nvec;
+         v += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 l = reinterpret_cast<const uint4*>(length)[v];
+        const uint4 w = reinterpret_cast<const uint4*>(winner)[v];
+        // per byte: (winner + 1) << 6 | length; winner + 1 is 0..2 and length < 64, so no carries between bytes
+        auto f = [](uint32_t lw, uint32_t ww) { return (((ww + 0x01010101u) & 0x03030303u) << 6) | (lw & 0x3F3F3F3Fu); };
+        reinterpret_cast<uint4*>(packed)[v] = make_uint4(f(l.x, w.x), f(l.y, w.y), f(l.z, w.z), f(l.w, w.w));
+    }
+    if (blockIdx.x == 0)
+        for (unsigned long long i = nvec * 16ull + threadIdx.x; i < n; i += blockDim.x)
+            packed[i] = (uint8_t)((((uint32_t)(winner[i] + 1) & 3u) << 6) | (length[i] & 63u));
+}
+
 __global__ void __launch_bounds__(256)
 reward_kernel(unsigned long long n, const int8_t* __restrict__ winner, float2* __restrict__ reward) {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
@@ -1484,6 +1503,22 @@ extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* pack
         reward_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, winner, reinterpret_cast<float2*>(reward));
         BGS_CUDA_TRY(cudaGetLastError());
     }
+    return BGS_OK;
+}
+
+extern "C" int bgs_connect_pack_results(uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed,
+                                        void* stream_) {
+    if (!length || !winner || !packed) return set_error(BGS_EINVAL, "connect_pack_results: null pointer");
+    if ((((uintptr_t)length | (uintptr_t)winner | (uintptr_t)packed) & 15u) != 0)
+        return set_error(BGS_EINVAL, "connect_pack_results: pointers must be 16-byte aligned");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    unsigned long long blocks = (n / 16ull + 255ull) / 256ull;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    pack_results_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(n, length, winner, packed);
+    BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }
 

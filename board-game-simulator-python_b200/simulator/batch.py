@@ -178,17 +178,26 @@ class HostRollout:
     compute stream (two buffer sets), which hides the PCIe time behind the kernel.
     """
 
-    def __init__(self, config, n_games: int, depth: int = 2):
+    def __init__(self, config, n_games: int, depth: int = 2, packed: bool = False):
         torch = N.require_cuda()
         self.torch = torch
         self.config = config
         self.n = int(n_games)
         self.depth = int(depth)
+        H, W, _ = _hwk(config)
+        if packed and H * W > 63:
+            raise ValueError("packed per-game results need a board of at most 63 cells")
+        #: packed=True: ONE byte per game crosses PCIe (length | (winner + 1) << 6, packed on the device by
+        #: bgs_connect_pack_results); run() / stream() then yield (stats, result) and HostRollout.unpack
+        #: recovers (length, winner) on the host
+        self.packed = bool(packed)
         self.sets = []
         for _ in range(self.depth):
             self.sets.append({
-                "length_host": torch.empty(self.n, dtype=torch.uint8).pin_memory(),
-                "winner_host": torch.empty(self.n, dtype=torch.int8).pin_memory(),
+                "length_host": None if packed else torch.empty(self.n, dtype=torch.uint8).pin_memory(),
+                "winner_host": None if packed else torch.empty(self.n, dtype=torch.int8).pin_memory(),
+                "result_host": torch.empty(self.n, dtype=torch.uint8).pin_memory() if packed else None,
+                "result_dev": torch.empty(self.n, dtype=torch.uint8, device="cuda") if packed else None,
                 "stats_host": torch.zeros(N.STATS_LEN, dtype=torch.int64).pin_memory(),
                 "stats_dev": torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda"),
                 "res": None,
@@ -197,26 +206,44 @@ class HostRollout:
             })
         self.copy_stream = torch.cuda.Stream()
         self.h2d_bytes = 0
-        self.d2h_bytes = self.n * 2 + N.STATS_LEN * 8
+        self.d2h_bytes = self.n * (1 if packed else 2) + N.STATS_LEN * 8
+
+    @staticmethod
+    def unpack(result):
+        """(length uint8, winner int8) from packed per-game results (host or device tensor)."""
+        import torch
+
+        return result & 63, (result >> 6).to(torch.int8) - 1
 
     def _launch(self, s, seed, game_id0):
         torch = self.torch
         s["stats_dev"].zero_()
         s["res"] = connect_rollout(self.config, self.n, seed, game_id0, per_game=True, stats=s["stats_dev"], out=s["res"])
+        if self.packed:
+            N.check(N.lib().bgs_connect_pack_results(self.n, N.ptr(s["res"].length), N.ptr(s["res"].winner),
+                                                      N.ptr(s["result_dev"]), N.stream_ptr(torch)))
         s["computed"].record()
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(s["computed"])
-            s["length_host"].copy_(s["res"].length, non_blocking=True)
-            s["winner_host"].copy_(s["res"].winner, non_blocking=True)
+            if self.packed:
+                s["result_host"].copy_(s["result_dev"], non_blocking=True)
+            else:
+                s["length_host"].copy_(s["res"].length, non_blocking=True)
+                s["winner_host"].copy_(s["res"].winner, non_blocking=True)
             s["stats_host"].copy_(s["stats_dev"], non_blocking=True)
             s["copied"].record()
+
+    def _out(self, s):
+        if self.packed:
+            return s["stats_host"], s["result_host"]
+        return s["stats_host"], s["length_host"], s["winner_host"]
 
     def run(self, seed: int, game_id0: int = 0):
         """One end-to-end rollout; returns (stats, length, winner) as pinned host tensors (synchronised)."""
         s = self.sets[0]
         self._launch(s, seed, game_id0)
         s["copied"].synchronize()
-        return s["stats_host"], s["length_host"], s["winner_host"]
+        return self._out(s)
 
     def stream(self, seed: int, game_id0: int, n_batches: int):
         """Yields ``(stats, length, winner)`` host tensors for ``n_batches`` consecutive batches of
@@ -233,10 +260,10 @@ class HostRollout:
             if len(pending) == self.depth:
                 done = pending.pop(0)
                 done["copied"].synchronize()
-                yield done["stats_host"], done["length_host"], done["winner_host"]
+                yield self._out(done)
         for done in pending:
             done["copied"].synchronize()
-            yield done["stats_host"], done["length_host"], done["winner_host"]
+            yield self._out(done)
 
 
 class ConnectBatch:

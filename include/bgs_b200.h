@@ -108,6 +108,12 @@ int bgs_connect_rollout_from(int H, int W, int K, uint64_t n_games, uint64_t gam
 int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,
                        int8_t* grid, float* reward, void* stream);
 
+/* Per-game results in one byte each, to halve the device->host traffic of State::get_reward
+ * (connect.cpp:41) for a whole batch: packed[i] = length[i] | (winner[i] + 1) << 6.  Valid for boards of
+ * at most 63 cells (length < 64); winner + 1 is 0 (draw), 1 (player 0), 2 (player 1).  All pointers 16-byte
+ * aligned device pointers. */
+int bgs_connect_pack_results(uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed, void* stream);
+
 /* Batched single transition on reference-layout states.  Replaces, for n states at once,
  *   State::get_action_at (connect.cpp:44)  -> status[i] = 0 ok / 1 illegal (state left unchanged)
  *   Action::sample_next_state (connect.cpp:52) -> grid_out, player_out, winner_out

@@ -375,6 +375,22 @@ def test_c_abi_argument_validation():
     assert int(buf.sum()) == 0
 
 
+def test_packed_host_results_equal_oracle(oracle):
+    """HostRollout(packed=True): one byte per game over PCIe, unpacked on the host = the oracle's results."""
+    from simulator import batch
+
+    n, k = 20011, 3
+    host = batch.HostRollout((6, 7, 4), n, packed=True)
+    for i, (st, result) in enumerate(host.stream(13, 500, k)):
+        ref = oracle.connect_rollout(6, 7, 4, n, gid0=500 + i * n, seed=13, want_actions=False, want_grid=False)
+        length, winner = batch.HostRollout.unpack(result)
+        np.testing.assert_array_equal(length.numpy(), ref["length"])
+        np.testing.assert_array_equal(winner.numpy(), ref["winner"])
+        np.testing.assert_array_equal(st.numpy(), ref["stats"])
+    with pytest.raises(ValueError):
+        batch.HostRollout((8, 9, 5), 10, packed=True)
+
+
 def test_dlpack_export():
     from simulator import batch
 

@@ -1115,8 +1115,11 @@ pack_results_kernel(unsigned long long n, const uint8_t* __restrict__ length, co
          v += (unsigned long long)gridDim.x * blockDim.x) {
         const uint4 l = reinterpret_cast<const uint4*>(length)[v];
         const uint4 w = reinterpret_cast<const uint4*>(winner)[v];
-        // per byte: (winner + 1) << 6 | length; winner + 1 is 0..2 and length < 64, so no carries between bytes
-        auto f = [](uint32_t lw, uint32_t ww) { return (((ww + 0x01010101u) & 0x03030303u) << 6) | (lw & 0x3F3F3F3Fu); };
+        // per byte: (winner + 1) << 6 | length
+        // (a winner byte of -1 is 0xFF: reduce it to 2 bits BEFORE adding 1, or the carry crosses into the next byte)
+        auto f = [](uint32_t lw, uint32_t ww) {
+            return ((((ww & 0x03030303u) + 0x01010101u) & 0x03030303u) << 6) | (lw & 0x3F3F3F3Fu);
+        };
         reinterpret_cast<uint4*>(packed)[v] = make_uint4(f(l.x, w.x), f(l.y, w.y), f(l.z, w.z), f(l.w, w.w));
     }
     if (blockIdx.x == 0)

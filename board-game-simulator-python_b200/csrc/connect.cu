@@ -983,7 +983,7 @@ connect_rollout_lines_kernel(const RolloutParams p) {
 // writes anything.
 // ---------------------------------------------------------------------------------------------
 constexpr int EXPORT_THREADS = 256;
-enum { MODE_GRID = 0, MODE_ACTIONS = 1 };
+enum { MODE_GRID = 0, MODE_ACTIONS = 1, MODE_TRAJ = 2 };
 
 // Warp-cooperative copy of `span` contiguous bytes; 128-bit accesses when both sides are 16-byte
 // aligned (`vec`), which they are for torch allocations because 32 rows of any board are a multiple
@@ -1031,21 +1031,55 @@ __device__ __forceinline__ void expand_grid_static(u128 v0, u128 v1, uint8_t* mi
     }
 }
 
+// Two bitboards (two words each) -> H*W grid bytes at `mine`: compile-time board if SH != 0.
+template <int SH, int SW>
+__device__ __forceinline__ void expand_grid(int H, int W, const uint64_t (&b0)[2], const uint64_t (&b1)[2], uint8_t* mine) {
+    if constexpr (SH != 0) {
+        expand_grid_static<SH, SW>(((u128)b0[1] << 64) | b0[0], ((u128)b1[1] << 64) | b1[0], mine);
+    } else {
+        // bit row br (bits br*W .. br*W+W-1) is board row H-1-br
+        for (int br = 0; br < H; ++br) {
+            const int bit = br * W, wd = bit >> 6, sh = bit & 63;
+            uint64_t r0 = b0[wd] >> sh, r1 = b1[wd] >> sh;
+            if (sh + W > 64) {
+                r0 |= b0[1] << (64 - sh);
+                r1 |= b1[1] << (64 - sh);
+            }
+            uint8_t* dst = mine + (H - 1 - br) * W;
+            for (int c = 0; c < W; c += 4) {
+                const uint32_t a = spread4((uint32_t)(r0 >> c)), b = spread4((uint32_t)(r1 >> c));
+                const uint32_t v = (0x01010101u - a - b) * 0xFFu + b;  // 0 / 1 / 0xFF per byte
+                for (int j = 0; j < 4 && c + j < W; ++j) dst[c + j] = (uint8_t)(v >> (8 * j));
+            }
+        }
+    }
+}
+
+//   MODE_TRAJ    trajectories uint8[n_games, H*W] + lengths -> the board after every ply,
+//                int8[n_games, H*W+1, H, W] (entry t = position after t plies; entries past the end
+//                repeat the final position): observation tensors for a learner.  A "row" is one
+//                (game, ply) pair; its lane replays the first t moves on bitboards (t <= H*W cheap
+//                register operations) and expands the result -- output-stationary, so the stores are
+//                the same coalesced 128-bit stores as for the final grids.
 template <int MODE, int SH = 0, int SW = 0>
 __global__ void __launch_bounds__(EXPORT_THREADS)
 connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* __restrict__ packed,
-                           const uint8_t* __restrict__ length, uint8_t* out, bool vec) {
+                           const uint8_t* __restrict__ length, uint8_t* out, bool vec,
+                           const uint8_t* __restrict__ actions, int rpl) {
     extern __shared__ __align__(16) uint8_t s_stage[];
     if (SH) { H = SH; W = SW; }
     const int HW = H * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* st = s_stage + (size_t)warp * 32 * HW;  // multiple of 32 bytes: 16-byte aligned
-    uint8_t* mine = st + lane * HW;
-    const unsigned long long ngroups = (n + 31ull) / 32ull;
+    // every lane produces `rpl` consecutive rows (1 except for MODE_TRAJ, where consecutive rows of a
+    // game share the replayed prefix): a warp covers 32*rpl rows
+    const unsigned rows_per_warp = 32u * (unsigned)rpl;
+    uint8_t* st = s_stage + (size_t)warp * rows_per_warp * HW;  // multiple of 32 bytes: 16-byte aligned
+    uint8_t* mine = st + (size_t)lane * rpl * HW;
+    const unsigned long long ngroups = (n + rows_per_warp - 1ull) / rows_per_warp;
     constexpr int WARPS = EXPORT_THREADS / 32;
     for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
          group += (unsigned long long)gridDim.x * WARPS) {
-        const unsigned long long g = group * 32ull + lane;
+        const unsigned long long g = group * rows_per_warp + (unsigned long long)lane * rpl;
         if (g < n) {
             if (MODE == MODE_GRID) {
                 uint64_t b0[2] = {0, 0}, b1[2] = {0, 0};
@@ -1057,23 +1091,38 @@ connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* _
                     const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(packed + g * 4 + 2);
                     b0[0] = v0.x; b0[1] = v0.y; b1[0] = v1.x; b1[1] = v1.y;
                 }
-                if (SH) {
-                    expand_grid_static<SH ? SH : 2, SW ? SW : 2>(((u128)b0[1] << 64) | b0[0], ((u128)b1[1] << 64) | b1[0], mine);
-                } else
-                // bit row br (bits br*W .. br*W+W-1) is board row H-1-br
-                for (int br = 0; br < H; ++br) {
-                    const int bit = br * W, wd = bit >> 6, sh = bit & 63;
-                    uint64_t r0 = b0[wd] >> sh, r1 = b1[wd] >> sh;
-                    if (sh + W > 64) {
-                        r0 |= b0[1] << (64 - sh);
-                        r1 |= b1[1] << (64 - sh);
+                expand_grid<SH, SW>(H, W, b0, b1, mine);
+            } else if (MODE == MODE_TRAJ) {
+                const unsigned T = (unsigned)HW + 1u;
+                unsigned long long game = g / T;
+                unsigned t = (unsigned)(g - game * T);
+                unsigned len = length[game];
+                const uint8_t* act = actions + game * (unsigned)HW;
+                u128 q[2] = {0, 0};
+                uint64_t hts = 0;
+                auto apply = [&](unsigned j) {  // move j of the current game
+                    const unsigned c = act[j];
+                    const unsigned h = (unsigned)(hts >> (4u * c)) & 15u;
+                    hts += 1ull << (4u * c);
+                    const u128 bit = (u128)1 << ((H - 1 - h) * W + c);
+                    if (j & 1) q[1] |= bit; else q[0] |= bit;
+                };
+                const unsigned plies = t < len ? t : len;
+                for (unsigned j = 0; j < plies; ++j) apply(j);
+                for (int i = 0; i < rpl && g + i < n; ++i) {
+                    if (i > 0) {  // the next row: one more ply of the same game, or the next game's empty board
+                        if (++t == T) {
+                            ++game; t = 0;
+                            len = length[game];
+                            act += HW;
+                            q[0] = 0; q[1] = 0; hts = 0;
+                        } else if (t <= len) {
+                            apply(t - 1);
+                        }
                     }
-                    uint8_t* dst = mine + (H - 1 - br) * W;
-                    for (int c = 0; c < W; c += 4) {
-                        const uint32_t a = spread4((uint32_t)(r0 >> c)), b = spread4((uint32_t)(r1 >> c));
-                        const uint32_t v = (0x01010101u - a - b) * 0xFFu + b;  // 0 / 1 / 0xFF per byte
-                        for (int j = 0; j < 4 && c + j < W; ++j) dst[c + j] = (uint8_t)(v >> (8 * j));
-                    }
+                    const uint64_t b0[2] = {(uint64_t)q[0], (uint64_t)(q[0] >> 64)};
+                    const uint64_t b1[2] = {(uint64_t)q[1], (uint64_t)(q[1] >> 64)};
+                    expand_grid<SH, SW>(H, W, b0, b1, mine + (size_t)i * HW);
                 }
             } else {
                 const uint8_t* row = out + g * (unsigned)HW;
@@ -1092,8 +1141,8 @@ connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* _
             }
         }
         __syncwarp();
-        const unsigned long long g0 = group * 32ull;
-        const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
+        const unsigned long long g0 = group * rows_per_warp;
+        const unsigned rows = (unsigned)((n - g0) < rows_per_warp ? (n - g0) : rows_per_warp);
         const unsigned span = rows * (unsigned)HW;
         warp_copy(out + g0 * (unsigned)HW, st, span, lane, vec);
         __syncwarp();
@@ -1361,21 +1410,27 @@ static int launch_rollout_lines(const RolloutParams& p, cudaStream_t stream) {
 
 template <int MODE, int SH = 0, int SW = 0>
 static int launch_export_rows(int H, int W, unsigned long long n, const uint64_t* packed, const uint8_t* length,
-                              uint8_t* out, cudaStream_t stream) {
-    if (MODE == MODE_GRID && SH == 0) {  // compile-time boards of the BASELINE configurations
-        if (H == 6 && W == 7) return launch_export_rows<MODE, 6, 7>(H, W, n, packed, length, out, stream);
-        if (H == 8 && W == 9) return launch_export_rows<MODE, 8, 9>(H, W, n, packed, length, out, stream);
-        if (H == 10 && W == 12) return launch_export_rows<MODE, 10, 12>(H, W, n, packed, length, out, stream);
+                              uint8_t* out, cudaStream_t stream, const uint8_t* actions = nullptr) {
+    if (MODE != MODE_ACTIONS && SH == 0) {  // compile-time boards of the BASELINE configurations
+        if (H == 6 && W == 7) return launch_export_rows<MODE, 6, 7>(H, W, n, packed, length, out, stream, actions);
+        if (H == 8 && W == 9) return launch_export_rows<MODE, 8, 9>(H, W, n, packed, length, out, stream, actions);
+        if (H == 10 && W == 12) return launch_export_rows<MODE, 10, 12>(H, W, n, packed, length, out, stream, actions);
     }
-    const size_t smem = (size_t)(EXPORT_THREADS / 32) * 32 * H * W;
+    // MODE_TRAJ: as many rows per lane (4 / 2 / 1) as fit the 48 KB of static-limit shared memory
+    int rpl = 1;
+    if (MODE == MODE_TRAJ)
+        for (int r = 4; r >= 1; r >>= 1)
+            if ((size_t)(EXPORT_THREADS / 32) * 32 * r * H * W <= 48 * 1024) { rpl = r; break; }
+    const size_t smem = (size_t)(EXPORT_THREADS / 32) * 32 * rpl * H * W;
     auto kern = connect_export_rows_kernel<MODE, SH, SW>;
     int per_sm = 0;
     BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EXPORT_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    unsigned long long blocks = (n + 255ull) / 256ull;
+    unsigned long long blocks = (n + 256ull * rpl - 1ull) / (256ull * rpl);
     const unsigned long long cap = (unsigned long long)sm_count() * per_sm;  // one resident wave, grid-stride
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, EXPORT_THREADS, smem, stream>>>(H, W, n, packed, length, out, ((uintptr_t)out & 15u) == 0);
+    kern<<<(unsigned)blocks, EXPORT_THREADS, smem, stream>>>(H, W, n, packed, length, out, ((uintptr_t)out & 15u) == 0,
+                                                            actions, rpl);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }
@@ -1507,6 +1562,16 @@ extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* pack
         BGS_CUDA_TRY(cudaGetLastError());
     }
     return BGS_OK;
+}
+
+extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, const uint8_t* actions,
+                                           const uint8_t* length, int8_t* grids, void* stream_) {
+    if (!supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
+    if (!actions || !length || !grids) return set_error(BGS_EINVAL, "connect_trajectory_grids: null pointer");
+    if (int rc = require_device()) return rc;
+    if (n_games == 0) return BGS_OK;
+    return launch_export_rows<MODE_TRAJ>(H, W, n_games * (unsigned long long)(H * W + 1), nullptr, length,
+                                         reinterpret_cast<uint8_t*>(grids), (cudaStream_t)stream_, actions);
 }
 
 extern "C" int bgs_connect_pack_results(uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed,

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "bgs_connect_start_words": (C.c_int, [_i32, _i32]),
     "bgs_connect_rollout_from": (C.c_int, [_i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 10),
     "bgs_connect_export": (C.c_int, [_i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "bgs_connect_trajectory_grids": (C.c_int, [_i32, _i32, _u64, _vp, _vp, _vp, _vp]),
     "bgs_connect_pack_results": (C.c_int, [_u64, _vp, _vp, _vp, _vp]),
     "bgs_connect_step": (C.c_int, [_i32, _i32, _i32, _u64] + [_vp] * 12),
     "bgs_connect_query": (C.c_int, [_i32, _i32, _u64] + [_vp] * 6),

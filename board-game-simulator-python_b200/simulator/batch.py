@@ -165,6 +165,25 @@ def connect_rollout(
     return res
 
 
+def connect_trajectory_grids(config, actions, length, out=None):
+    """Observation tensors for a learner: ``int8[n, H*W+1, H, W]`` with entry ``t`` = the position
+    after ``t`` plies of each recorded game (``actions`` uint8[n, H*W], ``length`` uint8[n] from
+    :func:`connect_rollout`); entries past the end of a game repeat its final position."""
+    torch = N.require_cuda()
+    H, W, _ = _hwk(config)
+    n = int(actions.shape[0])
+    if tuple(actions.shape) != (n, H * W) or tuple(length.shape) != (n,):
+        raise ValueError("actions must be uint8[n, H*W] and length uint8[n]")
+    if out is None:
+        out = torch.empty((n, H * W + 1, H, W), dtype=torch.int8, device=actions.device)
+    N.check(
+        N.lib().bgs_connect_trajectory_grids(
+            H, W, n, N.ptr(actions.contiguous()), N.ptr(length.contiguous()), N.ptr(out), N.stream_ptr(torch)
+        )
+    )
+    return out
+
+
 class HostRollout:
     """End-to-end rollouts with results in pinned host memory (what bench.py's ``e2e`` times).
 

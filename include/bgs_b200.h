@@ -108,6 +108,13 @@ int bgs_connect_rollout_from(int H, int W, int K, uint64_t n_games, uint64_t gam
 int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,
                        int8_t* grid, float* reward, void* stream);
 
+/* State::get_grid (connect.cpp:42) at EVERY ply of n recorded games: actions uint8[n, H*W] and length
+ * uint8[n] as written by bgs_connect_rollout -> grids int8[n, H*W+1, H, W]; entry t is the position
+ * after t plies (entry 0 = empty board), entries past the end of a game repeat its final position.
+ * HBM-write bound: (H*W+1) * H*W bytes per game. */
+int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, const uint8_t* actions, const uint8_t* length,
+                                 int8_t* grids, void* stream);
+
 /* Per-game results in one byte each, to halve the device->host traffic of State::get_reward
  * (connect.cpp:41) for a whole batch: packed[i] = length[i] | (winner[i] + 1) << 6.  Valid for boards of
  * at most 63 cells (length < 64); winner + 1 is 0 (draw), 1 (player 0), 2 (player 1).  All pointers 16-byte

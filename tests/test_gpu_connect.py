@@ -375,6 +375,31 @@ def test_c_abi_argument_validation():
     assert int(buf.sum()) == 0
 
 
+@pytest.mark.parametrize("cfg", [(6, 7, 4), (8, 9, 5), (10, 12, 6), (4, 5, 3), (5, 5, 4)])
+def test_per_ply_grids_equal_oracle_replay(oracle, cfg):
+    """connect_trajectory_grids: the position after every ply of every game equals the oracle's
+    transition applied move by move."""
+    from simulator import batch
+
+    H, W, K = cfg
+    n = 300
+    res = batch.connect_rollout(cfg, n, 8, 40, per_game=True, actions=True, final_grid=True)
+    grids = batch.connect_trajectory_grids(cfg, res.actions, res.length)
+    torch.cuda.synchronize()
+    assert tuple(grids.shape) == (n, H * W + 1, H, W) and grids.dtype == torch.int8
+    got = grids.cpu().numpy()
+    acts, lens = res.actions.cpu().numpy(), res.length.cpu().numpy()
+    for i in range(n):
+        g, pl, w = np.full((H, W), -1, np.int8), 0, -1
+        np.testing.assert_array_equal(got[i, 0], g)
+        for t in range(int(lens[i])):
+            g, pl, w = oracle.connect_next(g, K, pl, w, int(acts[i, t]))
+            np.testing.assert_array_equal(got[i, t + 1], g, err_msg=f"game {i} ply {t + 1}")
+        for t in range(int(lens[i]) + 1, H * W + 1):
+            np.testing.assert_array_equal(got[i, t], g)
+    np.testing.assert_array_equal(got[np.arange(n), lens.astype(np.int64)], res.final_grid.cpu().numpy())
+
+
 def test_packed_host_results_equal_oracle(oracle):
     """HostRollout(packed=True): one byte per game over PCIe, unpacked on the host = the oracle's results."""
     from simulator import batch

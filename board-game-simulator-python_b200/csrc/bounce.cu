@@ -15,6 +15,9 @@
 // The per-source target masks of the mover (<= W sources, all in one row) are staged in shared
 // memory so that the uniform draw can be mapped to the k-th (source, target) pair in ascending order.
 #include "bgs_common.cuh"
+#include "bounce_lane.cuh"
+
+#include <cstdlib>
 
 namespace bgs {
 namespace bounce {
@@ -257,6 +260,7 @@ struct RolloutParams {
     const int8_t* start_player;   // [n]
     const int8_t* start_winner;   // [n] or null
     const uint8_t* start_ended;   // [n] or null
+    int ply_batch;                // lanes that must be ready before the ply transition runs
 };
 
 constexpr int ROLLOUT_THREADS = 128;
@@ -523,6 +527,82 @@ bounce_rollout_kernel(const Geo g, const RolloutParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// rollout kernel, second formulation: the lane state machine of bounce_lane.cuh (mover-relative
+// orientation, compile-time shift directions, the first segment of a piece handled as a bounce off
+// itself so that every iteration is [short piece boundary] + [segment setup] + [u steps]).  The warp
+// shell is the same: lanes whose move generation is complete wait until PLY_BATCH of them can run the
+// ply transition together.
+// ---------------------------------------------------------------------------------------------
+template <int NP, class G, int RULES>
+__global__ void __launch_bounds__(ROLLOUT_THREADS)
+bounce_rollout_lane_kernel(const GeoRT grt, const RolloutParams p) {
+    __shared__ unsigned int s_hist[HIST_BINS];
+    __shared__ uint64_t s_T[8 * ROLLOUT_THREADS];
+    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    uint64_t* T = s_T + threadIdx.x;  // T[j * ROLLOUT_THREADS] = targets of the j-th movable piece
+    const G g(grt);
+    const LaneOut out{p.moves, p.length, p.winner, p.final_grid, p.reward};
+    Lane<NP, G, RULES> L;
+    L.waiting = false;
+    uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
+    unsigned long long acc_steps = 0;
+
+    uint32_t idx = atomicAdd(p.counter, 1u);
+    bool active = idx < p.n_games;
+    auto begin_game = [&]() {
+        if (p.start_grid)
+            L.begin_game_grid(g, p.start_grid + (size_t)idx * g.hw(), p.start_player[idx],
+                              p.start_winner ? (int)p.start_winner[idx] : BGS_WINNER_DRAW,
+                              p.start_ended && p.start_ended[idx]);
+        else
+            L.begin_game_planes(g, p.plane0);
+    };
+    if (active) begin_game();
+
+    for (;;) {
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        if (!am) break;
+        const unsigned wm = __ballot_sync(0xffffffffu, active && L.waiting);
+        if (__popc(wm) >= p.ply_batch || wm == am) {
+            if (active && L.waiting) {
+                uint8_t* row = p.moves ? p.moves + (size_t)idx * p.max_plies * 2ull : nullptr;
+                if (L.transition(g, T, ROLLOUT_THREADS, p.game_id0 + idx, p.seed_lo, p.seed_hi, p.max_plies, row)) {
+                    L.write_result(g, out, idx);
+                    acc_w0 += (L.win == 0);
+                    acc_w1 += (L.win == 1);
+                    acc_dr += (L.win == BGS_WINNER_DRAW);
+                    acc_tr += (L.win == BGS_WINNER_TRUNCATED);
+                    acc_steps += (unsigned)L.t;
+                    atomicAdd(&s_hist[hist_bin(L.t)], 1u);
+                    idx = atomicAdd(p.counter, 1u);
+                    if (idx < p.n_games) begin_game();
+                    else active = false;
+                }
+            }
+        }
+        if (active && !L.waiting) L.movegen_iter(g, T, ROLLOUT_THREADS);
+    }
+    __syncwarp();
+
+    if (p.stats) {
+        const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
+        const unsigned long long tr = warp_sum(acc_tr), st = warp_sum(acc_steps);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr + tr);
+            atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
+            atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
+            atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
+            atomicAdd(&p.stats[BGS_STAT_TRUNCATED], tr);
+            atomicAdd(&p.stats[BGS_STAT_STEPS], st);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&p.stats[BGS_STAT_HIST0 + i], (unsigned long long)s_hist[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // batched move generation / single step on reference-layout states (int8 grids)
 // ---------------------------------------------------------------------------------------------
 constexpr int STEP_THREADS = 64;
@@ -654,16 +734,34 @@ extern "C" int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t
     return BGS_OK;
 }
 
-template <int NP>
-static int launch_bounce_rollout(const Geo& g, const RolloutParams& p, cudaStream_t stream) {
-    auto kern = bounce_rollout_kernel<NP>;
+template <class K>
+static int persistent_blocks(K kern, uint32_t n_games, int* blocks_out) {
     int per_sm = 0;
     BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ROLLOUT_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
-    unsigned long long want = ((unsigned long long)p.n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+    const unsigned long long want = ((unsigned long long)n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
     unsigned long long blocks = (unsigned long long)sm_count() * per_sm;
     if (want < blocks) blocks = want ? want : 1;
+    *blocks_out = (int)blocks;
+    return BGS_OK;
+}
+
+template <int NP>
+static int launch_bounce_rollout(const Geo& g, const RolloutParams& p, cudaStream_t stream) {
+    auto kern = bounce_rollout_kernel<NP>;
+    int blocks = 0;
+    if (int rc = persistent_blocks(kern, p.n_games, &blocks)) return rc;
     kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(g, p);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+template <int NP, class G, int RULES>
+static int launch_bounce_lane(const GeoRT& grt, const RolloutParams& p, cudaStream_t stream) {
+    auto kern = bounce_rollout_lane_kernel<NP, G, RULES>;
+    int blocks = 0;
+    if (int rc = persistent_blocks(kern, p.n_games, &blocks)) return rc;
+    kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(grt, p);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }
@@ -705,7 +803,17 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     if (moves) BGS_CUDA_TRY(cudaMemsetAsync(moves, 0xFF, n_games * (size_t)max_plies * 2, stream));
     // per-game start grids may hold any value up to 15: use the 4-plane kernel
-    return (maxv <= 3 && !start_grid) ? launch_bounce_rollout<2>(g, p, stream) : launch_bounce_rollout<4>(g, p, stream);
+    static const bool use_old = getenv("BGS_BOUNCE_OLD") != nullptr;  // TEMPORARY: A/B timing
+    static const int ply_batch = getenv("BGS_BOUNCE_PLY_BATCH") ? atoi(getenv("BGS_BOUNCE_PLY_BATCH")) : PLY_BATCH;
+    p.ply_batch = ply_batch;
+    if (use_old)
+        return (maxv <= 3 && !start_grid) ? launch_bounce_rollout<2>(g, p, stream) : launch_bounce_rollout<4>(g, p, stream);
+    const GeoRT grt = make_geo_rt(H, W, rules);
+    if (maxv <= 3 && !start_grid) {
+        if (H == 9 && W == 6 && rules == 0) return launch_bounce_lane<2, GeoCT<9, 6>, 0>(grt, p, stream);
+        return launch_bounce_lane<2, GeoRT, -1>(grt, p, stream);
+    }
+    return launch_bounce_lane<4, GeoRT, -1>(grt, p, stream);
 }
 
 extern "C" int bgs_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n_games,

@@ -1,0 +1,75 @@
+// Host build of the Bounce lane state machine (csrc/bounce_lane.cuh) -- TEST HARNESS ONLY.
+//
+// Plays games one lane at a time on the CPU with exactly the code the CUDA kernel inlines, so that the
+// move generation, the mover-relative orientation and the action-selection map can be compared with the
+// oracle in the CPU test suite (tests/test_bounce_lane_host.py).  The product never loads this.
+#include <cstring>
+#include <vector>
+
+#include "../../board-game-simulator-python_b200/csrc/bounce_lane.cuh"
+
+using namespace bgs::bounce;
+
+template <int NP, class G, int RULES>
+static void play(const G& g, const uint64_t* plane0, const int8_t* start_grid, const int8_t* start_player,
+                 const int8_t* start_winner, const uint8_t* start_ended, int max_plies, uint64_t n, uint64_t gid0,
+                 uint64_t seed, const LaneOut& out, int64_t* stats) {
+    std::vector<uint64_t> T(8);
+    for (uint64_t idx = 0; idx < n; ++idx) {
+        Lane<NP, G, RULES> L;
+        if (start_grid)
+            L.begin_game_grid(g, start_grid + idx * (size_t)g.hw(), start_player[idx],
+                              start_winner ? (int)start_winner[idx] : BGS_WINNER_DRAW,
+                              start_ended && start_ended[idx]);
+        else
+            L.begin_game_planes(g, plane0);
+        for (;;) {
+            if (!L.waiting) {
+                L.movegen_iter(g, T.data(), 1);
+                continue;
+            }
+            uint8_t* row = out.moves ? out.moves + idx * (size_t)max_plies * 2 : nullptr;
+            if (L.transition(g, T.data(), 1, gid0 + idx, (uint32_t)seed, (uint32_t)(seed >> 32), max_plies, row)) break;
+        }
+        L.write_result(g, out, idx);
+        if (stats) {
+            stats[BGS_STAT_GAMES] += 1;
+            stats[BGS_STAT_WIN0] += L.win == 0;
+            stats[BGS_STAT_WIN1] += L.win == 1;
+            stats[BGS_STAT_DRAWS] += L.win == BGS_WINNER_DRAW;
+            stats[BGS_STAT_TRUNCATED] += L.win == BGS_WINNER_TRUNCATED;
+            stats[BGS_STAT_STEPS] += L.t;
+            const int cap = BGS_STATS_LEN - BGS_STAT_HIST0 - 1;
+            stats[BGS_STAT_HIST0 + (L.t < cap ? L.t : cap)] += 1;
+        }
+    }
+}
+
+// mode 0: run-time geometry and rules; mode 1: compile-time 9x6 board with compile-time rules 0
+extern "C" int bgs_lane_host_bounce_rollout(int mode, const int8_t* grid0, const int8_t* start_grid,
+                                            const int8_t* start_player, const int8_t* start_winner,
+                                            const uint8_t* start_ended, int H, int W, int rules, int max_plies,
+                                            uint64_t n, uint64_t gid0, uint64_t seed, uint8_t* moves,
+                                            uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward,
+                                            int64_t* stats) {
+    if (H < 1 || W < 1 || W > 8 || H * W > 64) return -1;
+    const GeoRT g = make_geo_rt(H, W, rules);
+    uint64_t plane0[4] = {0, 0, 0, 0};
+    int maxv = 0;
+    if (grid0)
+        for (int c = 0; c < H * W; ++c) {
+            if (grid0[c] > maxv) maxv = grid0[c];
+            for (int i = 0; i < 4; ++i) plane0[i] |= (uint64_t)((grid0[c] >> i) & 1) << c;
+        }
+    if (moves) memset(moves, 0xFF, n * (size_t)max_plies * 2);
+    const LaneOut out{moves, length, winner, final_grid, reward};
+    if (mode == 1) {
+        if (H != 9 || W != 6 || rules != 0 || maxv > 3 || start_grid) return -2;
+        play<2, GeoCT<9, 6>, 0>(GeoCT<9, 6>(g), plane0, nullptr, nullptr, nullptr, nullptr, max_plies, n, gid0, seed, out, stats);
+    } else if (maxv <= 3 && !start_grid) {
+        play<2, GeoRT, -1>(g, plane0, start_grid, start_player, start_winner, start_ended, max_plies, n, gid0, seed, out, stats);
+    } else {
+        play<4, GeoRT, -1>(g, plane0, start_grid, start_player, start_winner, start_ended, max_plies, n, gid0, seed, out, stats);
+    }
+    return 0;
+}

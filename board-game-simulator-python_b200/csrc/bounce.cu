@@ -14,10 +14,12 @@
 //     of the piece hit, until no unexpanded bounce cell is left (at most #pieces expansions).
 // The per-source target masks of the mover (<= W sources, all in one row) are staged in shared
 // memory so that the uniform draw can be mapped to the k-th (source, target) pair in ascending order.
+//
+// The rollout kernel uses the lane state machine of bounce_lane.cuh (mover-relative orientation, a
+// guard column between rows, compile-time geometry for the default 9x6 board); the batched
+// moves / step kernels below keep the plain y*W + x layout of this file.
 #include "bgs_common.cuh"
 #include "bounce_lane.cuh"
-
-#include <cstdlib>
 
 namespace bgs {
 namespace bounce {
@@ -231,16 +233,7 @@ __device__ __forceinline__ void store_grid(const Planes<NP>& P, int HW, int8_t* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// rollout kernel: one game per lane, ONE flat loop.
-//
-// Every loop iteration performs one frontier step of the lane's current move generation; the
-// bookkeeping between segments / pieces is a short branch.  A lane whose move generation is complete
-// waits until PLY_BATCH lanes of its warp are in the same state; then the (long) ply transition --
-// draw, k-th action, move, goal test, blocked test, game end + next game -- runs once for all of
-// them.  Lanes never wait for the slowest move generation of the warp (a formulation with one move
-// generation per outer iteration ran at 5 of 32 active lanes), and the transition does not execute
-// on nearly every iteration with a handful of lanes either.  Game indices are claimed with one atomic per game (games last ~28 plies of ~1.4k
-// instructions, so the counter is not contended).
+// rollout kernel
 // ---------------------------------------------------------------------------------------------
 struct RolloutParams {
     uint32_t n_games;  // <= 2^31 per launch
@@ -260,277 +253,14 @@ struct RolloutParams {
     const int8_t* start_player;   // [n]
     const int8_t* start_winner;   // [n] or null
     const uint8_t* start_ended;   // [n] or null
-    int ply_batch;                // lanes that must be ready before the ply transition runs
 };
 
 constexpr int ROLLOUT_THREADS = 128;
-#ifndef BGS_BOUNCE_PLY_BATCH
-#define BGS_BOUNCE_PLY_BATCH 12
-#endif
-constexpr int PLY_BATCH = BGS_BOUNCE_PLY_BATCH;  // lanes that must be ready before the ply transition runs
-
-// index of the k-th (0-based) set bit of m, by binary search on population counts
-__device__ __forceinline__ int kth_set_bit(uint64_t m, int k) {
-    int pos = 0;
-#pragma unroll
-    for (int w = 32; w >= 1; w >>= 1) {
-        const uint64_t low = m & ((1ull << w) - 1ull);
-        const int c = __popcll(low);
-        if (k >= c) {
-            k -= c;
-            m >>= w;
-            pos += w;
-        } else {
-            m = low;
-        }
-    }
-    return pos;
-}
-
-template <int NP>
-__global__ void __launch_bounds__(ROLLOUT_THREADS)
-bounce_rollout_kernel(const Geo g, const RolloutParams p) {
-    __shared__ unsigned int s_hist[HIST_BINS];
-    __shared__ uint64_t s_T[8 * ROLLOUT_THREADS];
-    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    uint64_t* T = s_T + threadIdx.x;  // T[x * ROLLOUT_THREADS] = target mask of the piece in column x
-    const int HW = g.H * g.W;
-    const int variant = g.rules & 3;
-    const bool allow_null = (g.rules & BGS_BOUNCE_ALLOW_NULL_MOVE) != 0;
-
-    // ---- game state ---------------------------------------------------------------------------
-    Planes<NP> P;
-    int player = 0, t = 0, win = BGS_WINNER_DRAW;
-    uint32_t r[4] = {0, 0, 0, 0};
-    uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
-    unsigned long long acc_steps = 0;
-    // ---- move-generation state ------------------------------------------------------------------
-    int mg_player = 0;      // whose moves are being generated (differs from `player` while probing)
-    bool probe = false;     // true: only "does mg_player have any action?" (blocked test)
-    bool found = false, have = false;
-    uint64_t occ = 0, sbit = 0, occS = 0, open = 0, inter = 0, expanded = 0, pending = 0, targets = 0;
-    uint32_t src8 = 0;      // movable pieces not yet expanded: bit x = column x of the source row
-    uint32_t rb[NP];        // the source row of every value plane (bit x = column x)
-#pragma unroll
-    for (int i = 0; i < NP; ++i) rb[i] = 0;
-    uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = 0;
-    int rem = 0, xs = 0, total = 0, row = 0;
-
-    uint32_t idx = 0;  // index of the lane's game in [0, n)
-    auto begin_movegen = [&](int pl, bool prb) {
-        mg_player = pl;
-        probe = prb;
-        occ = P.occ();
-        src8 = 0;
-        if (source_row_mask(g, occ, pl, &row)) {
-            const int base = row * g.W;
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                rb[i] = (uint32_t)(P.b[i] >> base) & (uint32_t)g.row0;
-                src8 |= rb[i];
-            }
-        }
-        have = false; found = false;
-        pending = 0; rem = 0; total = 0;
-        if (!prb)
-            for (int x = 0; x < g.W; ++x) T[x * ROLLOUT_THREADS] = 0ull;
-    };
-    auto begin_game = [&]() {
-        t = 0;
-        if (p.start_grid) {  // per-game start position (reference-layout grid)
-            const int8_t* gi = p.start_grid + (size_t)idx * HW;
-#pragma unroll
-            for (int i = 0; i < NP; ++i) P.b[i] = 0;
-            for (int c = 0; c < HW; ++c) {
-                const int v = gi[c];
-#pragma unroll
-                for (int i = 0; i < NP; ++i) P.b[i] |= (uint64_t)((v >> i) & 1) << c;
-            }
-            player = p.start_player[idx] & 1;
-            win = p.start_winner ? (int)p.start_winner[idx] : BGS_WINNER_DRAW;
-            const bool ended = win >= 0 || (p.start_ended && p.start_ended[idx]);
-            begin_movegen(player, false);
-            if (ended) src8 = 0;  // no move generation: the ply transition sees total == 0 at t == 0
-        } else {
-#pragma unroll
-            for (int i = 0; i < NP; ++i) P.b[i] = p.plane0[i];
-            player = 0; win = BGS_WINNER_DRAW;
-            begin_movegen(0, false);
-        }
-    };
-
-    idx = atomicAdd(p.counter, 1u);
-    bool active = idx < p.n_games;
-    bool waiting = false;  // move generation complete, ply transition not yet executed
-    if (active) begin_game();
-
-    for (;;) {
-        // ---- warp-convergent: run the (long) ply transition only when enough lanes are ready for it,
-        // so that it executes with many lanes at once instead of on nearly every iteration with a few
-        const unsigned am = __ballot_sync(0xffffffffu, active);
-        if (!am) break;
-        const unsigned wm = __ballot_sync(0xffffffffu, waiting);
-        if (__popc(wm) >= PLY_BATCH || wm == am) {
-            if (waiting) {
-                waiting = false;
-                bool over = false;
-                if (probe) {
-                    // `player` is blocked; the previous mover wins unless blocked too (draw)
-                    win = found ? 1 - player : BGS_WINNER_DRAW;
-                    over = true;
-                } else if (total == 0) {
-                    if (t == 0) over = true;  // a blocked start position: ended, no winner
-                    else begin_movegen(1 - player, true);
-                } else if (t >= p.max_plies) {
-                    win = BGS_WINNER_TRUNCATED;
-                    over = true;
-                } else {
-                    if ((t & 3) == 0) {
-                        const unsigned long long gid = p.game_id0 + idx;
-                        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2, DOMAIN_BOUNCE,
-                                      p.seed_lo, p.seed_hi, r);
-                    }
-                    const uint32_t rr = (t & 3) == 0 ? r[0] : ((t & 3) == 1 ? r[1] : ((t & 3) == 2 ? r[2] : r[3]));
-                    int k = (int)__umulhi(rr, (uint32_t)total);
-                    // k-th action in ascending (source column, target cell) order
-                    int sx = 0;
-                    uint64_t tm = T[0];
-                    for (;;) {
-                        const int c = __popcll(tm);
-                        if (k < c) break;
-                        k -= c;
-                        ++sx;
-                        tm = T[sx * ROLLOUT_THREADS];
-                    }
-                    const int scell = row * g.W + sx;
-                    const int tcell = kth_set_bit(tm, k);
-                    if (p.moves) {
-                        uint8_t* m = p.moves + ((size_t)idx * p.max_plies + (unsigned)t) * 2ull;
-                        *reinterpret_cast<uchar2*>(m) = make_uchar2((unsigned char)scell, (unsigned char)tcell);
-                    }
-                    move_piece<NP>(P, scell, tcell);
-                    ++t;
-                    if ((1ull << tcell) & g.far(player)) {
-                        win = player;
-                        over = true;
-                    }
-                    player ^= 1;
-                    if (!over) begin_movegen(player, false);
-                }
-                if (over) {
-                    if (p.length) p.length[idx] = (uint16_t)t;
-                    if (p.winner) p.winner[idx] = (int8_t)win;
-                    if (p.final_grid) store_grid<NP>(P, HW, p.final_grid + (size_t)idx * HW);
-                    if (p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(win);
-                    acc_w0 += (win == 0);
-                    acc_w1 += (win == 1);
-                    acc_dr += (win == BGS_WINNER_DRAW);
-                    acc_tr += (win == BGS_WINNER_TRUNCATED);
-                    acc_steps += (unsigned)t;
-                    atomicAdd(&s_hist[hist_bin(t)], 1u);
-                    idx = atomicAdd(p.counter, 1u);
-                    if (idx < p.n_games) begin_game();
-                    else active = false;
-                }
-            }
-        }
-        if (active && !waiting) {
-            if (rem == 0) {
-                if (pending != 0) {
-                    // bounce: all unexpanded landing cells that hold a piece of the same value as the
-                    // lowest one (membership of that cell in each value plane selects the plane or
-                    // its complement)
-                    const uint64_t low = pending & (~pending + 1ull);
-                    uint64_t S = pending;
-                    int u = 0;
-#pragma unroll
-                    for (int i = 0; i < NP; ++i) {
-                        const bool in = (P.b[i] & low) != 0;
-                        S &= in ? P.b[i] : ~P.b[i];
-                        u |= in ? (1 << i) : 0;
-                    }
-                    pending &= ~S;
-                    expanded |= S;
-                    Ff = 0; Fl = 0; Fr = 0; Nn = S;
-                    rem = u;
-                } else {
-                    if (have) {  // the piece on sbit is done
-                        if (!allow_null) targets &= ~sbit;
-                        if (probe) {
-                            found = targets != 0;
-                        } else {
-                            T[xs * ROLLOUT_THREADS] = targets;
-                            total += __popcll(targets);
-                        }
-                        have = false;
-                    }
-                    if (src8 != 0 && !found) {  // next movable piece (ascending column)
-                        xs = __ffs((int)src8) - 1;
-                        src8 &= src8 - 1u;
-                        have = true;
-                        sbit = 1ull << (row * g.W + xs);
-                        occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
-                        open = variant == BGS_BOUNCE_SOURCE_BLOCKED ? (g.board & ~sbit) : g.board;
-                        inter = open & ~occS & ~g.far(mg_player);
-                        expanded = sbit;
-                        targets = 0;
-                        Ff = 0; Fl = 0; Fr = 0; Nn = sbit;
-                        int u = 0;
-#pragma unroll
-                        for (int i = 0; i < NP; ++i) u |= (int)((rb[i] >> xs) & 1u) << i;
-                        rem = u;
-                    } else {
-                        waiting = true;  // move generation complete
-                    }
-                }
-            }
-            // ---- the steps of the current segment (1..value of the piece), all frontier cells at once.
-            // The whole segment runs inside one iteration: a frontier step is ~50 instructions, the
-            // bookkeeping above ~130, so lanes with a short segment idling here costs far less than
-            // running the bookkeeping branches once per step.
-            while (rem != 0) {
-                const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn;  // may go left / right (no reversal)
-                const uint64_t all = fl | Fr;
-                const uint64_t nf = mg_player == 0 ? (all << g.W) : (all >> g.W);  // never backwards
-                const uint64_t nl = (fl & g.not_left) >> 1;
-                const uint64_t nr = (fr & g.not_right) << 1;
-                if (rem > 1) {  // intermediate cells: empty, not the far goal row
-                    Ff = nf & inter; Fl = nl & inter; Fr = nr & inter; Nn = 0;
-                    rem = (Ff | Fl | Fr) ? rem - 1 : 0;
-                } else {        // last step: rest on an empty cell, or bounce off a piece
-                    const uint64_t land = (nf | nl | nr) & open;
-                    targets |= land & ~occS;
-                    pending |= land & occS & ~expanded;
-                    rem = 0;
-                }
-            }
-        }
-    }
-    __syncwarp();
-
-    if (p.stats) {
-        const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
-        const unsigned long long tr = warp_sum(acc_tr), st = warp_sum(acc_steps);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr + tr);
-            atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
-            atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
-            atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
-            atomicAdd(&p.stats[BGS_STAT_TRUNCATED], tr);
-            atomicAdd(&p.stats[BGS_STAT_STEPS], st);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
-            if (s_hist[i]) atomicAdd(&p.stats[BGS_STAT_HIST0 + i], (unsigned long long)s_hist[i]);
-    }
-}
+constexpr int PLY_BATCH = 12;  // lanes that must be ready before the ply transition runs (8: 13.0 ms, 12: 12.45, 16: 12.6, 24: 13.3)
 
 // ---------------------------------------------------------------------------------------------
-// rollout kernel, second formulation: the lane state machine of bounce_lane.cuh (mover-relative
-// orientation, compile-time shift directions, the first segment of a piece handled as a bounce off
-// itself so that every iteration is [short piece boundary] + [segment setup] + [u steps]).  The warp
-// shell is the same: lanes whose move generation is complete wait until PLY_BATCH of them can run the
+// rollout kernel, lane formulation: one game per lane (Game + MoveGen of bounce_lane.cuh in
+// registers).  Lanes whose move generation is complete wait until PLY_BATCH of them can run the
 // ply transition together.
 // ---------------------------------------------------------------------------------------------
 template <int NP, class G, int RULES>
@@ -543,45 +273,68 @@ bounce_rollout_lane_kernel(const GeoRT grt, const RolloutParams p) {
     uint64_t* T = s_T + threadIdx.x;  // T[j * ROLLOUT_THREADS] = targets of the j-th movable piece
     const G g(grt);
     const LaneOut out{p.moves, p.length, p.winner, p.final_grid, p.reward};
-    Lane<NP, G, RULES> L;
-    L.waiting = false;
+    Game<NP, G> gm;
+    MoveGen<NP, G, RULES> mg;
+    mg.done = false;
+    uint32_t r[4] = {0, 0, 0, 0};
     uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
     unsigned long long acc_steps = 0;
 
     uint32_t idx = atomicAdd(p.counter, 1u);
     bool active = idx < p.n_games;
+    auto start_movegen = [&](bool probe, bool no_moves) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) mg.b[i] = gm.b[i];
+        mg.begin(g, probe, no_moves);
+    };
     auto begin_game = [&]() {
+        bool no_moves = false;
         if (p.start_grid)
-            L.begin_game_grid(g, p.start_grid + (size_t)idx * g.hw(), p.start_player[idx],
-                              p.start_winner ? (int)p.start_winner[idx] : BGS_WINNER_DRAW,
-                              p.start_ended && p.start_ended[idx]);
+            no_moves = gm.begin_grid(g, p.start_grid + (size_t)idx * (g.h() * g.w()), p.start_player[idx],
+                                     p.start_winner ? (int)p.start_winner[idx] : BGS_WINNER_DRAW,
+                                     p.start_ended && p.start_ended[idx]);
         else
-            L.begin_game_planes(g, p.plane0);
+            gm.begin_planes(g, p.plane0);
+        start_movegen(false, no_moves);
     };
     if (active) begin_game();
 
     for (;;) {
         const unsigned am = __ballot_sync(0xffffffffu, active);
         if (!am) break;
-        const unsigned wm = __ballot_sync(0xffffffffu, active && L.waiting);
-        if (__popc(wm) >= p.ply_batch || wm == am) {
-            if (active && L.waiting) {
+        const unsigned wm = __ballot_sync(0xffffffffu, active && mg.done);
+        if (__popc(wm) >= PLY_BATCH || wm == am) {
+            if (active && mg.done) {
                 uint8_t* row = p.moves ? p.moves + (size_t)idx * p.max_plies * 2ull : nullptr;
-                if (L.transition(g, T, ROLLOUT_THREADS, p.game_id0 + idx, p.seed_lo, p.seed_hi, p.max_plies, row)) {
-                    L.write_result(g, out, idx);
-                    acc_w0 += (L.win == 0);
-                    acc_w1 += (L.win == 1);
-                    acc_dr += (L.win == BGS_WINNER_DRAW);
-                    acc_tr += (L.win == BGS_WINNER_TRUNCATED);
-                    acc_steps += (unsigned)L.t;
-                    atomicAdd(&s_hist[hist_bin(L.t)], 1u);
+                const Next nx = gm.transition(g, T, ROLLOUT_THREADS, mg.total, mg.probe, mg.found, p.max_plies, row,
+                                              [&](int t) -> uint32_t {
+                                                  if ((t & 3) == 0) {
+                                                      const unsigned long long gid = p.game_id0 + idx;
+                                                      philox_hd((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2,
+                                                                DOMAIN_BOUNCE, p.seed_lo, p.seed_hi, r);
+                                                  }
+                                                  return (t & 3) == 0 ? r[0] : ((t & 3) == 1 ? r[1] : ((t & 3) == 2 ? r[2] : r[3]));
+                                              });
+                if (nx == NEXT_OVER) {
+                    gm.write_result(g, out, idx);
+                    acc_w0 += (gm.win == 0);
+                    acc_w1 += (gm.win == 1);
+                    acc_dr += (gm.win == BGS_WINNER_DRAW);
+                    acc_tr += (gm.win == BGS_WINNER_TRUNCATED);
+                    acc_steps += (unsigned)gm.t;
+                    atomicAdd(&s_hist[hist_bin(gm.t)], 1u);
                     idx = atomicAdd(p.counter, 1u);
                     if (idx < p.n_games) begin_game();
                     else active = false;
+                } else {
+                    start_movegen(nx == NEXT_PROBE, false);
                 }
             }
         }
-        if (active && !L.waiting) L.movegen_iter(g, T, ROLLOUT_THREADS);
+        if (active && !mg.done) {
+            mg.iter(g, T, ROLLOUT_THREADS);
+            if (!mg.done) mg.iter(g, T, ROLLOUT_THREADS);  // two segments per readiness check: 12.8 -> 11.9 ms
+        }
     }
     __syncwarp();
 
@@ -746,16 +499,6 @@ static int persistent_blocks(K kern, uint32_t n_games, int* blocks_out) {
     return BGS_OK;
 }
 
-template <int NP>
-static int launch_bounce_rollout(const Geo& g, const RolloutParams& p, cudaStream_t stream) {
-    auto kern = bounce_rollout_kernel<NP>;
-    int blocks = 0;
-    if (int rc = persistent_blocks(kern, p.n_games, &blocks)) return rc;
-    kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(g, p);
-    BGS_CUDA_TRY(cudaGetLastError());
-    return BGS_OK;
-}
-
 template <int NP, class G, int RULES>
 static int launch_bounce_lane(const GeoRT& grt, const RolloutParams& p, cudaStream_t stream) {
     auto kern = bounce_rollout_lane_kernel<NP, G, RULES>;
@@ -784,16 +527,13 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const Geo g = make_geo(H, W, rules);
+    const GeoRT grt = make_geo_rt(H, W, rules);
     RolloutParams p;
     p.n_games = (uint32_t)n_games; p.game_id0 = game_id0;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.max_plies = max_plies;
-    for (int i = 0; i < 4; ++i) {
-        p.plane0[i] = 0;
-        if (grid0)
-            for (int c = 0; c < H * W; ++c) p.plane0[i] |= (uint64_t)((grid0[c] >> i) & 1) << c;
-    }
+    for (int i = 0; i < 4; ++i) p.plane0[i] = 0;
+    if (grid0) planes_from_grid(grt, grid0, p.plane0);
     p.moves = moves; p.length = length; p.winner = winner; p.final_grid = final_grid; p.reward = reward;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
     p.start_grid = start_grid; p.start_player = start_player; p.start_winner = start_winner; p.start_ended = start_ended;
@@ -803,12 +543,6 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     if (moves) BGS_CUDA_TRY(cudaMemsetAsync(moves, 0xFF, n_games * (size_t)max_plies * 2, stream));
     // per-game start grids may hold any value up to 15: use the 4-plane kernel
-    static const bool use_old = getenv("BGS_BOUNCE_OLD") != nullptr;  // TEMPORARY: A/B timing
-    static const int ply_batch = getenv("BGS_BOUNCE_PLY_BATCH") ? atoi(getenv("BGS_BOUNCE_PLY_BATCH")) : PLY_BATCH;
-    p.ply_batch = ply_batch;
-    if (use_old)
-        return (maxv <= 3 && !start_grid) ? launch_bounce_rollout<2>(g, p, stream) : launch_bounce_rollout<4>(g, p, stream);
-    const GeoRT grt = make_geo_rt(H, W, rules);
     if (maxv <= 3 && !start_grid) {
         if (H == 9 && W == 6 && rules == 0) return launch_bounce_lane<2, GeoCT<9, 6>, 0>(grt, p, stream);
         return launch_bounce_lane<2, GeoRT, -1>(grt, p, stream);

@@ -3,8 +3,8 @@
 // Everything a lane does between claiming a game and writing its result lives here, as
 // __host__ __device__ code with no warp intrinsics, so the same source is (a) inlined into
 // bounce_rollout_kernel (bounce.cu) and (b) compiled by g++ into a host harness
-// (tests/native/bounce_lane_host.cpp) that plays games lane by lane on the CPU and is compared with
-// the oracle without a GPU.  The product never runs the host build.
+// (tests/native/bounce_lane_host.cpp) that plays games lane by lane on the CPU and is checked by
+// the CPU test suite without a GPU.  The product never runs the host build.
 //
 // Replaces, inside the rollout loop, the reference's State::get_actions + the caller's uniform choice
 // + Action::sample_next_state + has_ended / reward (src/simulator/game/bounce.cpp:36-51,
@@ -103,67 +103,89 @@ BGS_HD void philox_hd(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32
 }
 
 // ---- geometry: run-time (any board) or compile-time (the BASELINE default 9x6) -------------------
+// Cell (x, y) is bit y*S + x.  S = W + 1 whenever H*(W+1) <= 64: the spare GUARD column (never part
+// of `board`) absorbs horizontal steps off the left / right edge, so that the frontier steps need no
+// edge masks (not_left / not_right are all-ones then); S = W otherwise.
 struct GeoRT {
-    int H, W, HW, rules;
-    uint64_t board;      // low H*W bits
-    uint64_t not_left;   // cells with x > 0
-    uint64_t not_right;  // cells with x < W-1
+    int H, W, S, rules;
+    int rot_shift;       // 63 - (index of the last cell): rot180(x) = brev64(x) >> rot_shift
+    uint64_t board;      // the H*W valid cells
+    uint64_t not_left;   // cells with x > 0      (all-ones with a guard column)
+    uint64_t not_right;  // cells with x < W-1    (all-ones with a guard column)
     uint64_t far;        // the mover's far goal row in mover-relative orientation = row H-1
     uint32_t row0;       // (1 << W) - 1
-    uint32_t inv_w;      // ceil(2^16 / W): cell / W == (cell * inv_w) >> 16 for cell < 64, W <= 8
+    uint32_t inv_s;      // ceil(2^16 / S): cell / S == (cell * inv_s) >> 16 for cell < 64, S <= 9
     BGS_HD int h() const { return H; }
     BGS_HD int w() const { return W; }
-    BGS_HD int hw() const { return HW; }
+    BGS_HD int s() const { return S; }
+    BGS_HD int rot_sh() const { return rot_shift; }
     BGS_HD uint64_t m_board() const { return board; }
     BGS_HD uint64_t m_not_left() const { return not_left; }
     BGS_HD uint64_t m_not_right() const { return not_right; }
     BGS_HD uint64_t m_far() const { return far; }
     BGS_HD uint32_t m_row0() const { return row0; }
-    BGS_HD int row_of(int cell) const { return (int)(((uint32_t)cell * inv_w) >> 16); }
+    BGS_HD int row_of(int cell) const { return (int)(((uint32_t)cell * inv_s) >> 16); }
 };
 
 inline GeoRT make_geo_rt(int H, int W, int rules) {
     GeoRT g;
-    g.H = H; g.W = W; g.HW = H * W; g.rules = rules;
-    g.board = (H * W == 64) ? ~0ull : ((1ull << (H * W)) - 1ull);
-    g.not_left = 0; g.not_right = 0;
+    g.H = H; g.W = W; g.rules = rules;
+    g.S = (H * (W + 1) <= 64) ? W + 1 : W;
+    g.rot_shift = 63 - ((H - 1) * g.S + W - 1);
+    g.board = 0; g.not_left = 0; g.not_right = 0;
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
-            if (x > 0) g.not_left |= 1ull << (y * W + x);
-            if (x < W - 1) g.not_right |= 1ull << (y * W + x);
+            g.board |= 1ull << (y * g.S + x);
+            if (x > 0) g.not_left |= 1ull << (y * g.S + x);
+            if (x < W - 1) g.not_right |= 1ull << (y * g.S + x);
         }
+    if (g.S > W) g.not_left = g.not_right = ~0ull;
     g.row0 = (uint32_t)((1ull << W) - 1ull);
-    g.far = (uint64_t)g.row0 << ((H - 1) * W);
-    g.inv_w = (65536u + (uint32_t)W - 1u) / (uint32_t)W;
+    g.far = (uint64_t)g.row0 << ((H - 1) * g.S);
+    g.inv_s = (65536u + (uint32_t)g.S - 1u) / (uint32_t)g.S;
     return g;
+}
+
+// Bit-planes of a reference-layout grid (int8[H*W], row 0 = bottom) in the layout of g.
+inline void planes_from_grid(const GeoRT& g, const int8_t* grid, uint64_t plane[4]) {
+    for (int i = 0; i < 4; ++i) plane[i] = 0;
+    for (int y = 0; y < g.H; ++y)
+        for (int x = 0; x < g.W; ++x)
+            for (int i = 0; i < 4; ++i) plane[i] |= (uint64_t)((grid[y * g.W + x] >> i) & 1) << (y * g.S + x);
 }
 
 template <int H_, int W_>
 struct GeoCT {
     static_assert(H_ * W_ <= 64 && W_ <= 8 && W_ >= 1 && H_ >= 1, "board must fit one 64-bit word");
-    static constexpr uint64_t kBoard = (H_ * W_ == 64) ? ~0ull : ((1ull << (H_ * W_ % 64)) - 1ull);
+    static constexpr int S_ = (H_ * (W_ + 1) <= 64) ? W_ + 1 : W_;
     static constexpr uint64_t col_mask(int x0, int x1) {
         uint64_t m = 0;
         for (int y = 0; y < H_; ++y)
-            for (int x = x0; x < x1; ++x) m |= 1ull << (y * W_ + x);
+            for (int x = x0; x < x1; ++x) m |= 1ull << (y * S_ + x);
         return m;
     }
-    static constexpr uint64_t kNotLeft = col_mask(1, W_);
-    static constexpr uint64_t kNotRight = col_mask(0, W_ - 1);
+    static constexpr uint64_t kBoard = col_mask(0, W_);
+    static constexpr uint64_t kNotLeft = S_ > W_ ? ~0ull : col_mask(1, W_);
+    static constexpr uint64_t kNotRight = S_ > W_ ? ~0ull : col_mask(0, W_ - 1);
     static constexpr uint32_t kRow0 = (uint32_t)((1ull << W_) - 1ull);
-    static constexpr uint64_t kFar = (uint64_t)kRow0 << ((H_ - 1) * W_);
+    static constexpr uint64_t kFar = (uint64_t)kRow0 << ((H_ - 1) * S_);
     int rules;
     BGS_HD explicit GeoCT(const GeoRT& g) : rules(g.rules) {}
     BGS_HD int h() const { return H_; }
     BGS_HD int w() const { return W_; }
-    BGS_HD int hw() const { return H_ * W_; }
+    BGS_HD int s() const { return S_; }
+    BGS_HD int rot_sh() const { return 63 - ((H_ - 1) * S_ + W_ - 1); }
     BGS_HD uint64_t m_board() const { return kBoard; }
     BGS_HD uint64_t m_not_left() const { return kNotLeft; }
     BGS_HD uint64_t m_not_right() const { return kNotRight; }
     BGS_HD uint64_t m_far() const { return kFar; }
     BGS_HD uint32_t m_row0() const { return kRow0; }
-    BGS_HD int row_of(int cell) const { return cell / W_; }
+    BGS_HD int row_of(int cell) const { return cell / S_; }
 };
+
+// public cell index y*W + x of internal cell y*S + x
+template <class G>
+BGS_HD int pub_cell(const G& g, int cell) { return cell - g.row_of(cell) * (g.s() - g.w()); }
 
 // index of the k-th (0-based) set bit of m (k < popcount(m))
 BGS_HD int kth_set_bit64(uint64_t m, int k) {
@@ -201,78 +223,53 @@ struct LaneOut {
     float* reward;       // [n, 2]
 };
 
+#if defined(__CUDA_ARCH__)
+#define BGS_UNROLL _Pragma("unroll")
+#else
+#define BGS_UNROLL
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// MoveGen: the move generation of ONE position for its mover -- SURVEY.md 4.4 rules 2-4.
 // RULES_ >= 0: compile-time rule set; -1: read g.rules.
+// ---------------------------------------------------------------------------------------------
 template <int NP, class G, int RULES_>
-struct Lane {
-    // ---- game --------------------------------------------------------------------------------
-    uint64_t b[NP];  // value bit-planes, oriented for `orient`
-    int t;           // plies played in this rollout
-    int player;      // side to move
-    int orient;      // whose orientation b[] is in
-    int win;
-    uint32_t r[4];   // the Philox block of plies 4*(t>>2) .. +3
-    // ---- move generation ---------------------------------------------------------------------
+struct MoveGen {
+    uint64_t b[NP];  // value bit-planes in the mover's orientation (read-only here)
     uint64_t occ, src_left, sbit, occS, inter, open, expanded, pending, targets;
     int total, nsrc;
-    bool probe, found, have, waiting;
+    bool probe;  // only "does the mover have any action?" (the blocked test): no target masks
+    bool found, have, done;
 
     BGS_HD int rules(const G& g) const { return RULES_ >= 0 ? RULES_ : g.rules; }
-    BGS_HD uint64_t rot(const G& g, uint64_t x) const { return brev64(x) >> (64 - g.hw()); }
 
-    // Start (or restart, for the blocked test) a move generation for `pl`.
-    BGS_HD void begin_movegen(const G& g, int pl, bool prb) {
-        if (orient != pl) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int i = 0; i < NP; ++i) b[i] = rot(g, b[i]);
-            orient = pl;
-        }
+    // The movable pieces of the mover: the occupied row nearest to it (tests/test_bounce.py:43-48,60).
+    // no_moves: an ended start position (no generation at all).
+    BGS_HD static uint64_t sources(const G& g, const uint64_t* planes, bool no_moves) {
+        uint64_t o = planes[0];
+        BGS_UNROLL
+        for (int i = 1; i < NP; ++i) o |= planes[i];
+        if (!o || no_moves) return 0ull;
+        const int row = g.row_of(ctz64(o));
+        return o & ((uint64_t)g.m_row0() << (row * g.s()));
+    }
+
+    // planes b[] already set; src = sources(g, b, no_moves), possibly computed earlier.
+    BGS_HD void begin_with(const G& g, uint64_t src, bool prb) {
         uint64_t o = b[0];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+        BGS_UNROLL
         for (int i = 1; i < NP; ++i) o |= b[i];
         occ = o;
-        src_left = 0;
-        if (o) {  // movable pieces: the occupied row nearest to the mover (tests/test_bounce.py:43-48,60)
-            const int row = g.row_of(ctz64(o));
-            src_left = o & ((uint64_t)g.m_row0() << (row * g.w()));
-        }
-        probe = prb; found = false; have = false; waiting = false;
+        src_left = src;
+        probe = prb; found = false; have = false; done = false;
         pending = 0; total = 0; nsrc = 0;
     }
 
-    BGS_HD void begin_game_planes(const G& g, const uint64_t* plane0) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int i = 0; i < NP; ++i) b[i] = plane0[i];
-        t = 0; player = 0; orient = 0; win = BGS_WINNER_DRAW;
-        begin_movegen(g, 0, false);
-    }
+    BGS_HD void begin(const G& g, bool prb, bool no_moves) { begin_with(g, sources(g, b, no_moves), prb); }
 
-    // Per-game start position in the reference's layout (int8 grid, row 0 = bottom).
-    BGS_HD void begin_game_grid(const G& g, const int8_t* grid, int pl, int winner_in, bool ended) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int i = 0; i < NP; ++i) b[i] = 0;
-        for (int c = 0; c < g.hw(); ++c) {
-            const int v = grid[c];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (int i = 0; i < NP; ++i) b[i] |= (uint64_t)((v >> i) & 1) << c;
-        }
-        t = 0; player = pl & 1; orient = 0; win = winner_in;
-        begin_movegen(g, player, false);
-        if (ended || winner_in >= 0) src_left = 0;  // no move generation: ends at t == 0 with total == 0
-    }
-
-    // One iteration of the move generation: at most one piece boundary, then one whole segment.
-    // T[j * stride] receives the target mask (mover-relative) of the j-th movable piece.
-    BGS_HD void movegen_iter(const G& g, uint64_t* T, int stride) {
+    // One iteration: at most one piece boundary, then one whole segment.  T[j * stride] receives the
+    // target mask (mover-relative) of the j-th movable piece.  Sets done when nothing is left.
+    BGS_HD void iter(const G& g, uint64_t* T, int stride) {
         const int rl = rules(g);
         if (pending == 0) {  // piece boundary
             if (have) {
@@ -287,7 +284,7 @@ struct Lane {
                 have = false;
             }
             if (src_left == 0 || found) {
-                waiting = true;
+                done = true;
                 return;
             }
             sbit = src_left & (~src_left + 1ull);  // next movable piece, ascending relative column
@@ -306,9 +303,7 @@ struct Lane {
         const uint64_t low = pending & (~pending + 1ull);
         uint64_t S = pending;
         int u = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+        BGS_UNROLL
         for (int i = 0; i < NP; ++i) {
             const bool in = (b[i] & low) != 0;
             S &= in ? b[i] : ~b[i];
@@ -318,7 +313,7 @@ struct Lane {
         expanded |= S;
         // ---- u steps, every frontier cell at once; x* = cells entered by a forward / left / right
         // step (a left step may not follow a right step and vice versa; never backwards)
-        const int W = g.w();
+        const int W = g.s();  // one row up
         uint64_t xf = S << W;
         uint64_t xl = (S & g.m_not_left()) >> 1;
         uint64_t xr = (S & g.m_not_right()) << 1;
@@ -347,31 +342,80 @@ struct Lane {
         targets |= land & ~occS;
         pending |= land & occS & ~expanded;
     }
+};
 
-    // The ply transition of a lane whose move generation is complete (waiting == true).
-    // Returns true when the game is over (win / t final; the caller writes the result).
-    BGS_HD bool transition(const G& g, const uint64_t* T, int stride, uint64_t gid, uint32_t seed_lo,
-                           uint32_t seed_hi, int max_plies, uint8_t* moves_row) {
-        waiting = false;
+// What the game needs next after a transition.
+enum Next { NEXT_OVER = 0, NEXT_MOVEGEN = 1, NEXT_PROBE = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// Game: one rollout between two move generations -- the caller's uniform choice (README.md:61-62)
+// + Action::sample_next_state + has_ended / reward (SURVEY.md 4.4 rules 5-6).
+// ---------------------------------------------------------------------------------------------
+template <int NP, class G>
+struct Game {
+    uint64_t b[NP];  // value bit-planes, oriented for `orient`
+    int t;           // plies played in this rollout
+    int player;      // side to move
+    int orient;      // whose orientation b[] is in
+    int win;
+
+    BGS_HD uint64_t rot(const G& g, uint64_t x) const { return brev64(x) >> g.rot_sh(); }
+    BGS_HD void orient_for(const G& g, int pl) {
+        if (orient != pl) {
+            BGS_UNROLL
+            for (int i = 0; i < NP; ++i) b[i] = rot(g, b[i]);
+            orient = pl;
+        }
+    }
+
+    BGS_HD void begin_planes(const G& g, const uint64_t* plane0) {
+        BGS_UNROLL
+        for (int i = 0; i < NP; ++i) b[i] = plane0[i];
+        t = 0; player = 0; orient = 0; win = BGS_WINNER_DRAW;
+    }
+
+    // Per-game start position in the reference's layout (int8 grid, row 0 = bottom).  Returns true if
+    // the position has already ended (the first move generation must then be started with no_moves).
+    BGS_HD bool begin_grid(const G& g, const int8_t* grid, int pl, int winner_in, bool ended) {
+        BGS_UNROLL
+        for (int i = 0; i < NP; ++i) b[i] = 0;
+        for (int y = 0; y < g.h(); ++y)
+            for (int x = 0; x < g.w(); ++x) {
+                const int v = grid[y * g.w() + x];
+                BGS_UNROLL
+                for (int i = 0; i < NP; ++i) b[i] |= (uint64_t)((v >> i) & 1) << (y * g.s() + x);
+            }
+        t = 0; player = pl & 1; orient = 0; win = winner_in;
+        orient_for(g, player);
+        return ended || winner_in >= 0;
+    }
+
+    // The ply transition after a complete move generation (total / found / probe are its results, T
+    // its target masks, rr the draw of ply t -- read only when a move is played).  On NEXT_MOVEGEN /
+    // NEXT_PROBE the planes are oriented for the player whose moves must be generated next.
+    template <class Draw>
+    BGS_HD Next transition(const G& g, const uint64_t* T, int stride, int total, bool probe, bool found,
+                           int max_plies, uint8_t* moves_row, Draw draw) {
         if (probe) {  // `player` is blocked; the previous mover wins unless blocked too (draw)
             win = found ? 1 - player : BGS_WINNER_DRAW;
-            return true;
+            return NEXT_OVER;
         }
         if (total == 0) {
-            if (t == 0) return true;  // a blocked / ended start position: no winner
-            begin_movegen(g, 1 - player, true);
-            return false;
+            if (t == 0) return NEXT_OVER;  // a blocked / ended start position: no winner
+            orient_for(g, 1 - player);
+            return NEXT_PROBE;
         }
         if (t >= max_plies) {
             win = BGS_WINNER_TRUNCATED;
-            return true;
+            return NEXT_OVER;
         }
-        if ((t & 3) == 0) philox_hd((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2, 1u, seed_lo, seed_hi, r);
-        const uint32_t rr = (t & 3) == 0 ? r[0] : ((t & 3) == 1 ? r[1] : ((t & 3) == 2 ? r[2] : r[3]));
-        int k = (int)mulhi32(rr, (uint32_t)total);
+        int k = (int)mulhi32(draw(t), (uint32_t)total);
         if (player) k = total - 1 - k;  // canonical (absolute) order is the reverse of the rotated one
         // k-th action in ascending relative (source, target) order
-        const int base = g.row_of(ctz64(occ)) * g.w();
+        uint64_t occ = b[0];
+        BGS_UNROLL
+        for (int i = 1; i < NP; ++i) occ |= b[i];
+        const int base = g.row_of(ctz64(occ)) * g.s();
         uint32_t sm = (uint32_t)(occ >> base) & g.m_row0();
         uint64_t tm = T[0];
         int j = 0;
@@ -386,15 +430,12 @@ struct Lane {
         const int scell = base + ctz32(sm);
         const int tcell = kth_set_bit64(tm, k);
         if (moves_row) {
-            const int HW1 = g.hw() - 1;
-            const int sa = player ? HW1 - scell : scell, ta = player ? HW1 - tcell : tcell;
-            moves_row[2 * t] = (uint8_t)sa;
-            moves_row[2 * t + 1] = (uint8_t)ta;
+            const int HW1 = g.h() * g.w() - 1, sp = pub_cell(g, scell), tp = pub_cell(g, tcell);
+            moves_row[2 * t] = (uint8_t)(player ? HW1 - sp : sp);
+            moves_row[2 * t + 1] = (uint8_t)(player ? HW1 - tp : tp);
         }
         const uint64_t smask = 1ull << scell, tmask = 1ull << tcell;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+        BGS_UNROLL
         for (int i = 0; i < NP; ++i) {
             const bool has = (b[i] & smask) != 0;
             b[i] = (b[i] & ~smask) | (has ? tmask : 0ull);
@@ -403,17 +444,15 @@ struct Lane {
         const bool goal = (tmask & g.m_far()) != 0;
         if (goal) win = player;
         player ^= 1;
-        if (goal) return true;
-        begin_movegen(g, player, false);
-        return false;
+        if (goal) return NEXT_OVER;
+        orient_for(g, player);
+        return NEXT_MOVEGEN;
     }
 
-    BGS_HD int value_abs(const G& g, int cell) const {
-        const int c = orient ? g.hw() - 1 - cell : cell;
+    BGS_HD int value_abs(const G& g, int x, int y) const {  // absolute (x, y)
+        const int c = orient ? (g.h() - 1 - y) * g.s() + (g.w() - 1 - x) : y * g.s() + x;
         int v = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+        BGS_UNROLL
         for (int i = 0; i < NP; ++i) v |= (int)((b[i] >> c) & 1ull) << i;
         return v;
     }
@@ -423,8 +462,9 @@ struct Lane {
         if (o.length) o.length[idx] = (uint16_t)t;
         if (o.winner) o.winner[idx] = (int8_t)win;
         if (o.final_grid) {
-            int8_t* out = o.final_grid + idx * (size_t)g.hw();
-            for (int c = 0; c < g.hw(); ++c) out[c] = (int8_t)value_abs(g, c);
+            int8_t* out = o.final_grid + idx * (size_t)(g.h() * g.w());
+            for (int y = 0; y < g.h(); ++y)
+                for (int x = 0; x < g.w(); ++x) out[y * g.w() + x] = (int8_t)value_abs(g, x, y);
         }
         if (o.reward) {
             o.reward[2 * idx] = win == 0 ? 1.f : (win == 1 ? -1.f : 0.f);
@@ -432,6 +472,13 @@ struct Lane {
         }
     }
 };
+
+// The t-th draw of game gid: word t & 3 of Philox(key = seed, ctr = (gid, t >> 2, 1)).
+BGS_HD uint32_t bounce_draw(uint64_t gid, uint32_t seed_lo, uint32_t seed_hi, int t) {
+    uint32_t r[4];
+    philox_hd((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2, 1u, seed_lo, seed_hi, r);
+    return (t & 3) == 0 ? r[0] : ((t & 3) == 1 ? r[1] : ((t & 3) == 2 ? r[2] : r[3]));
+}
 
 }  // namespace bounce
 }  // namespace bgs

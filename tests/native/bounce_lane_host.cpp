@@ -16,31 +16,37 @@ static void play(const G& g, const uint64_t* plane0, const int8_t* start_grid, c
                  uint64_t seed, const LaneOut& out, int64_t* stats) {
     std::vector<uint64_t> T(8);
     for (uint64_t idx = 0; idx < n; ++idx) {
-        Lane<NP, G, RULES> L;
+        Game<NP, G> game;
+        MoveGen<NP, G, RULES> mg;
+        bool no_moves = false;
         if (start_grid)
-            L.begin_game_grid(g, start_grid + idx * (size_t)g.hw(), start_player[idx],
-                              start_winner ? (int)start_winner[idx] : BGS_WINNER_DRAW,
-                              start_ended && start_ended[idx]);
+            no_moves = game.begin_grid(g, start_grid + idx * (size_t)(g.h() * g.w()), start_player[idx],
+                                       start_winner ? (int)start_winner[idx] : BGS_WINNER_DRAW,
+                                       start_ended && start_ended[idx]);
         else
-            L.begin_game_planes(g, plane0);
-        for (;;) {
-            if (!L.waiting) {
-                L.movegen_iter(g, T.data(), 1);
-                continue;
-            }
+            game.begin_planes(g, plane0);
+        Next next = NEXT_MOVEGEN;
+        while (next != NEXT_OVER) {
+            for (int i = 0; i < NP; ++i) mg.b[i] = game.b[i];
+            mg.begin(g, next == NEXT_PROBE, no_moves);
+            no_moves = false;
+            while (!mg.done) mg.iter(g, T.data(), 1);
             uint8_t* row = out.moves ? out.moves + idx * (size_t)max_plies * 2 : nullptr;
-            if (L.transition(g, T.data(), 1, gid0 + idx, (uint32_t)seed, (uint32_t)(seed >> 32), max_plies, row)) break;
+            const uint64_t gid = gid0 + idx;
+            next = game.transition(g, T.data(), 1, mg.total, mg.probe, mg.found, max_plies, row, [&](int t) {
+                return bounce_draw(gid, (uint32_t)seed, (uint32_t)(seed >> 32), t);
+            });
         }
-        L.write_result(g, out, idx);
+        game.write_result(g, out, idx);
         if (stats) {
             stats[BGS_STAT_GAMES] += 1;
-            stats[BGS_STAT_WIN0] += L.win == 0;
-            stats[BGS_STAT_WIN1] += L.win == 1;
-            stats[BGS_STAT_DRAWS] += L.win == BGS_WINNER_DRAW;
-            stats[BGS_STAT_TRUNCATED] += L.win == BGS_WINNER_TRUNCATED;
-            stats[BGS_STAT_STEPS] += L.t;
+            stats[BGS_STAT_WIN0] += game.win == 0;
+            stats[BGS_STAT_WIN1] += game.win == 1;
+            stats[BGS_STAT_DRAWS] += game.win == BGS_WINNER_DRAW;
+            stats[BGS_STAT_TRUNCATED] += game.win == BGS_WINNER_TRUNCATED;
+            stats[BGS_STAT_STEPS] += game.t;
             const int cap = BGS_STATS_LEN - BGS_STAT_HIST0 - 1;
-            stats[BGS_STAT_HIST0 + (L.t < cap ? L.t : cap)] += 1;
+            stats[BGS_STAT_HIST0 + (game.t < cap ? game.t : cap)] += 1;
         }
     }
 }
@@ -56,11 +62,11 @@ extern "C" int bgs_lane_host_bounce_rollout(int mode, const int8_t* grid0, const
     const GeoRT g = make_geo_rt(H, W, rules);
     uint64_t plane0[4] = {0, 0, 0, 0};
     int maxv = 0;
-    if (grid0)
-        for (int c = 0; c < H * W; ++c) {
+    if (grid0) {
+        for (int c = 0; c < H * W; ++c)
             if (grid0[c] > maxv) maxv = grid0[c];
-            for (int i = 0; i < 4; ++i) plane0[i] |= (uint64_t)((grid0[c] >> i) & 1) << c;
-        }
+        planes_from_grid(g, grid0, plane0);
+    }
     if (moves) memset(moves, 0xFF, n * (size_t)max_plies * 2);
     const LaneOut out{moves, length, winner, final_grid, reward};
     if (mode == 1) {

@@ -1149,6 +1149,88 @@ connect_export_rows_kernel(int H, int W, unsigned long long n, const uint64_t* _
     }
 }
 
+// MODE_ACTIONS for the BASELINE boards (compile-time row length HW, 16-byte aligned `out`): the
+// generic kernel above reads every row's 16-bit blocks straight from global memory -- 32 lanes, 32
+// different lines per load instruction -- and is LSU-bound (10x12: 0.49 ms for 0.76 GB).  Here the
+// warp first stages the 32 rows' blocks in shared memory with coalesced 8 / 16-byte loads, every lane
+// then expands its own row in registers (8 plies per 32-bit word: two masks, two byte permutes) and
+// the warp writes the 32*HW contiguous bytes back with 128-bit stores.
+template <int HW>
+__global__ void __launch_bounds__(EXPORT_THREADS)
+connect_expand_actions_kernel(unsigned long long n, const uint8_t* __restrict__ length, uint8_t* out) {
+    static_assert(HW % 2 == 0, "4-bit blocks come in pairs");
+    constexpr int WARPS = EXPORT_THREADS / 32;
+    constexpr int SPAN = 32 * HW;         // bytes of one warp group
+    constexpr int NB = HW / 2;            // block bytes at the start of every row
+    constexpr int NIW = (HW + 7) / 8;     // 32-bit block words per row (8 plies each)
+    constexpr int NOW = (HW + 3) / 4;     // 32-bit output words per row
+    constexpr bool A8 = HW % 8 == 0;      // rows 8-byte aligned: row-wise staging, 32 / 64-bit shared accesses
+    constexpr int N8 = (NB + 7) / 8;      // 8-byte pieces holding a row's blocks
+    __shared__ __align__(16) uint8_t s_stage[WARPS * SPAN];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* st = s_stage + warp * SPAN;
+    uint8_t* mine = st + lane * HW;
+    const unsigned long long ngroups = (n + 31ull) / 32ull;
+    for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
+         group += (unsigned long long)gridDim.x * WARPS) {
+        const unsigned long long g0 = group * 32ull;
+        const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
+        uint8_t* base = out + g0 * (unsigned)HW;
+        const unsigned span = rows * (unsigned)HW;
+        // ---- (a) blocks -> stage, coalesced
+        if (A8) {
+            for (unsigned q = lane; q < rows * N8; q += 32) {
+                const unsigned r = q / N8, k = q - r * N8;
+                *reinterpret_cast<uint2*>(st + r * HW + 8 * k) = *reinterpret_cast<const uint2*>(base + r * HW + 8 * k);
+            }
+        } else {
+            for (unsigned q = lane; q < (span >> 4); q += 32)
+                reinterpret_cast<uint4*>(st)[q] = reinterpret_cast<const uint4*>(base)[q];
+            for (unsigned i = (span & ~15u) + lane; i < span; i += 32) st[i] = base[i];
+        }
+        __syncwarp();
+        // ---- (b) every lane expands its own row in registers
+        if (lane < rows) {
+            const unsigned len = length[g0 + lane];
+            uint32_t w[NIW];
+#pragma unroll
+            for (int i = 0; i < NIW; ++i) {
+                if (A8) {
+                    w[i] = *reinterpret_cast<const uint32_t*>(mine + 4 * i);
+                } else {
+                    w[i] = *reinterpret_cast<const uint16_t*>(mine + 4 * i);
+                    if (4 * i + 2 < NB) w[i] |= (uint32_t)*reinterpret_cast<const uint16_t*>(mine + 4 * i + 2) << 16;
+                }
+            }
+            const unsigned fw = len >> 2;                              // output words that are all moves
+            const uint32_t pm = 0xFFFFFFFFu << (8u * (len & 3u));      // 0xFF padding of word fw
+            uint32_t o[NOW];
+#pragma unroll
+            for (int ow = 0; ow < NOW; ++ow) {
+                const uint32_t even = w[ow >> 1] & 0x0F0F0F0Fu, odd = (w[ow >> 1] >> 4) & 0x0F0F0F0Fu;
+                const uint32_t v = __byte_perm(even, odd, (ow & 1) ? 0x7362 : 0x5140);
+                const uint32_t mask = (unsigned)ow < fw ? 0u : ((unsigned)ow > fw ? 0xFFFFFFFFu : pm);
+                o[ow] = v | mask;
+            }
+#pragma unroll
+            for (int ow = 0; ow < NOW; ++ow) {
+                if (A8) {
+                    if ((ow & 1) == 0) *reinterpret_cast<uint2*>(mine + 4 * ow) = make_uint2(o[ow], o[ow + 1]);
+                } else {
+                    *reinterpret_cast<uint16_t*>(mine + 4 * ow) = (uint16_t)o[ow];
+                    if (4 * ow + 2 < HW) *reinterpret_cast<uint16_t*>(mine + 4 * ow + 2) = (uint16_t)(o[ow] >> 16);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- (c) stage -> out
+        for (unsigned q = lane; q < (span >> 4); q += 32)
+            reinterpret_cast<uint4*>(base)[q] = reinterpret_cast<const uint4*>(st)[q];
+        for (unsigned i = (span & ~15u) + lane; i < span; i += 32) base[i] = st[i];
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ float2 reward_of(int winner) {
     return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
                        winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
@@ -1237,26 +1319,42 @@ connect_step_kernel(const DynGeo g, unsigned long long n, const int8_t* __restri
         __syncwarp();
         const unsigned long long i = g0 + lane;
         if (i < n) {
-            BoardBits b = load_grid(mine, H, W);
+            // Work on the staged bytes directly (empty = 0xFF): the transition only needs the height
+            // of one column, the top row and the <= 8*(K-1) cells around the new stone -- converting
+            // the whole grid to bitboards cost ~15 instructions per cell and made the kernel
+            // instruction-bound (4 Mi 6x7 states: 0.41 ms against 0.07 ms of HBM time).
             int pl = player[i];
             int win = winner[i];
             const int col = action[i];
-            const bool ended = win >= 0 || b.full;
-            const bool legal = !ended && col >= 0 && col < W && ((b.legal >> col) & 1u) && (pl == 0 || pl == 1);
+            uint32_t legal_mask = 0;
+            for (int c = 0; c < W; ++c)
+                if (mine[(H - 1) * W + c] == 0xFFu) legal_mask |= 1u << c;
+            const bool ended = win >= 0 || legal_mask == 0;
+            const bool legal = !ended && col >= 0 && col < W && ((legal_mask >> col) & 1u) && (pl == 0 || pl == 1);
             if (legal) {
-                const int row = (int)((b.hts >> (4 * col)) & 15ull);  // lowest empty cell of the column
-                const u128 me = (pl == 0 ? b.p[0] : b.p[1]) | ((u128)1 << ((H - 1 - row) * W + col));
-                if (row == H - 1) b.legal &= ~(1u << col);
-                if (has_run(g, me)) win = pl;
-                b.full = b.legal == 0;
+                int row = 0;  // lowest empty cell of the column
+                while (mine[row * W + col] != 0xFFu) ++row;
                 mine[row * W + col] = (uint8_t)pl;
+                if (row == H - 1) legal_mask &= ~(1u << col);
+                const int K = g.K();
+                // a run of >= K stones of `pl` through (row, col): horizontal, vertical, two diagonals
+                auto run = [&](int dr, int dc) {
+                    int cnt = 0, r = row + dr, c = col + dc;
+                    while (cnt < K - 1 && r >= 0 && r < H && c >= 0 && c < W && mine[r * W + c] == (uint8_t)pl) {
+                        ++cnt; r += dr; c += dc;
+                    }
+                    return cnt;
+                };
+                if (1 + run(0, 1) + run(0, -1) >= K || 1 + run(-1, 0) >= K || 1 + run(1, 1) + run(-1, -1) >= K ||
+                    1 + run(1, -1) + run(-1, 1) >= K)
+                    win = pl;
                 pl = 1 - pl;
             }
             player_out[i] = (int8_t)pl;
             winner_out[i] = (int8_t)win;
-            const bool ended_new = win >= 0 || b.full;
+            const bool ended_new = win >= 0 || legal_mask == 0;
             if (ended_out) ended_out[i] = ended_new;
-            if (legal_out) legal_out[i] = ended_new ? 0u : b.legal;
+            if (legal_out) legal_out[i] = ended_new ? 0u : legal_mask;
             if (reward_out) reinterpret_cast<float2*>(reward_out)[i] = reward_of(win);
             if (status) status[i] = legal ? 0 : 1;
         }
@@ -1415,6 +1513,22 @@ static int launch_export_rows(int H, int W, unsigned long long n, const uint64_t
         if (H == 6 && W == 7) return launch_export_rows<MODE, 6, 7>(H, W, n, packed, length, out, stream, actions);
         if (H == 8 && W == 9) return launch_export_rows<MODE, 8, 9>(H, W, n, packed, length, out, stream, actions);
         if (H == 10 && W == 12) return launch_export_rows<MODE, 10, 12>(H, W, n, packed, length, out, stream, actions);
+    }
+    if (MODE == MODE_ACTIONS && ((uintptr_t)out & 15u) == 0 && (H * W == 42 || H * W == 72 || H * W == 120)) {
+        auto launch = [&](auto kern) {
+            int per_sm = 0;
+            BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EXPORT_THREADS, 0));
+            if (per_sm < 1) per_sm = 1;
+            unsigned long long blocks = (n + 255ull) / 256ull;
+            const unsigned long long cap = (unsigned long long)sm_count() * per_sm;
+            if (blocks > cap) blocks = cap;
+            kern<<<(unsigned)blocks, EXPORT_THREADS, 0, stream>>>(n, length, out);
+            BGS_CUDA_TRY(cudaGetLastError());
+            return (int)BGS_OK;
+        };
+        if (H * W == 42) return launch(connect_expand_actions_kernel<42>);
+        if (H * W == 72) return launch(connect_expand_actions_kernel<72>);
+        return launch(connect_expand_actions_kernel<120>);
     }
     // MODE_TRAJ: as many rows per lane (4 / 2 / 1) as fit the 48 KB of static-limit shared memory
     int rpl = 1;

@@ -1231,6 +1231,83 @@ connect_expand_actions_kernel(unsigned long long n, const uint8_t* __restrict__ 
     }
 }
 
+// MODE_TRAJ for boards whose rows are a multiple of 8 bytes (8x9, 10x12): cell-stationary.
+// Consecutive positions of a game differ in ONE byte, so expanding every position from bitboards
+// (~5 instructions per output byte, above) is wasted work.  Here a lane owns 8 fixed cells of one game
+// and holds, in registers, the ply at which each of them is filled (tm, 0x7F = never) and by whom
+// (ow); position t is then  byte = tm <= t ? ow : 0xFF  for all 8 cells at once (per 32-bit word: one
+// subtract whose byte-wise sign bits are the comparison, one sign-replicating PRMT, one LOP3) and goes
+// straight to global memory as one 64-bit store -- the H*W/8 lanes of a game write H*W contiguous bytes,
+// and 32 / (H*W/8) games share a warp.  tm / ow are built per game by a ply-parallel scatter: lane
+// q handles ply q, its row is the number of earlier plies in the same column (__match_any_sync rank
+// + a per-column counter in shared memory).
+// every byte of x replaced by 0xFF if its sign bit is set, else 0x00: PRMT with the sign-replicate bit
+// of each selector nibble (the __byte_perm intrinsic masks that bit off, hence the PTX)
+__device__ __forceinline__ uint32_t sign_bytes(uint32_t x) {
+    uint32_t m;
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(m) : "r"(x));
+    return m;
+}
+
+template <int H, int W>
+__global__ void __launch_bounds__(EXPORT_THREADS)
+connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict__ actions,
+                          const uint8_t* __restrict__ length, uint8_t* out) {
+    constexpr int HW = H * W, T = HW + 1, CH = HW / 8, GPW = 32 / CH, WARPS = EXPORT_THREADS / 32;
+    static_assert(HW % 8 == 0 && HW <= 126 && W <= 16 && GPW >= 1, "8-byte cell chunks, ply numbers below 0x7F");
+    __shared__ __align__(8) uint8_t s_tm[WARPS][GPW * HW];
+    __shared__ __align__(8) uint8_t s_ow[WARPS][GPW * HW];
+    __shared__ uint8_t s_cnt[WARPS][GPW * 16];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const unsigned sg = lane / CH, ci = lane - sg * CH;  // game of the warp's group, 8-cell chunk
+    uint8_t* tm = s_tm[warp];
+    uint8_t* ow = s_ow[warp];
+    uint8_t* cnt = s_cnt[warp];
+    const unsigned long long ngroups = (n_games + GPW - 1ull) / GPW;
+    for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
+         group += (unsigned long long)gridDim.x * WARPS) {
+        const unsigned long long g0 = group * GPW;
+        for (unsigned i = lane; i < GPW * HW / 8; i += 32) {
+            reinterpret_cast<uint64_t*>(tm)[i] = 0x7F7F7F7F7F7F7F7Full;
+            reinterpret_cast<uint64_t*>(ow)[i] = ~0ull;
+        }
+        for (unsigned i = lane; i < GPW * 16; i += 32) cnt[i] = 0;
+        __syncwarp();
+        // ---- scatter: ply p of game j fills the lowest empty cell of its column
+        for (unsigned q0 = 0; q0 < GPW * HW; q0 += 32) {
+            const unsigned q = q0 + lane;
+            const unsigned j = q / HW, pl = q - j * HW;
+            const unsigned long long g = g0 + j;
+            const bool valid = q < GPW * HW && g < n_games && pl < length[g];
+            const unsigned col = valid ? actions[g * HW + pl] : 0u;
+            const unsigned mm = __match_any_sync(0xffffffffu, valid ? (j * 16u + col) : (0x100u + lane));
+            const unsigned below = valid ? cnt[j * 16 + col] : 0u;  // stones already in the column
+            __syncwarp();
+            if (valid) {
+                if ((mm >> lane) == 1u) cnt[j * 16 + col] = (uint8_t)(below + __popc(mm));  // last ply of the column
+                const unsigned cell = (below + __popc(mm & lt)) * W + col;
+                tm[j * HW + cell] = (uint8_t)(pl + 1);
+                ow[j * HW + cell] = (uint8_t)(pl & 1);
+            }
+            __syncwarp();
+        }
+        // ---- every position of the game, 8 cells per lane
+        if (sg < GPW && g0 + sg < n_games) {
+            const uint2 tm8 = *reinterpret_cast<const uint2*>(tm + sg * HW + 8 * ci);
+            const uint2 ow8 = *reinterpret_cast<const uint2*>(ow + sg * HW + 8 * ci);
+            uint8_t* dst = out + (g0 + sg) * (unsigned long long)(T * HW) + 8 * ci;
+            uint32_t tb = 0x80808080u;  // 0x80 | t in every byte
+#pragma unroll 4
+            for (int t = 0; t < T; ++t) {
+                const uint32_t m0 = sign_bytes(tb - tm8.x), m1 = sign_bytes(tb - tm8.y);
+                *reinterpret_cast<uint2*>(dst + (size_t)t * HW) = make_uint2((ow8.x & m0) | ~m0, (ow8.y & m1) | ~m1);
+                tb += 0x01010101u;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ float2 reward_of(int winner) {
     return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
                        winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
@@ -1684,6 +1761,22 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
     if (!actions || !length || !grids) return set_error(BGS_EINVAL, "connect_trajectory_grids: null pointer");
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
+    if (((uintptr_t)grids & 7u) == 0 && ((H == 8 && W == 9) || (H == 10 && W == 12))) {
+        cudaStream_t stream = (cudaStream_t)stream_;
+        auto launch = [&](auto kern, int gpw) {
+            int per_sm = 0;
+            BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EXPORT_THREADS, 0));
+            if (per_sm < 1) per_sm = 1;
+            unsigned long long blocks = (n_games + 8ull * gpw - 1ull) / (8ull * gpw);
+            const unsigned long long cap = (unsigned long long)sm_count() * per_sm;
+            if (blocks > cap) blocks = cap;
+            kern<<<(unsigned)blocks, EXPORT_THREADS, 0, stream>>>(n_games, actions, length, reinterpret_cast<uint8_t*>(grids));
+            BGS_CUDA_TRY(cudaGetLastError());
+            return (int)BGS_OK;
+        };
+        if (H == 8) return launch(connect_traj_cells_kernel<8, 9>, 3);
+        return launch(connect_traj_cells_kernel<10, 12>, 2);
+    }
     return launch_export_rows<MODE_TRAJ>(H, W, n_games * (unsigned long long)(H * W + 1), nullptr, length,
                                          reinterpret_cast<uint8_t*>(grids), (cudaStream_t)stream_, actions);
 }

@@ -400,6 +400,35 @@ def test_per_ply_grids_equal_oracle_replay(oracle, cfg):
     np.testing.assert_array_equal(got[np.arange(n), lens.astype(np.int64)], res.final_grid.cpu().numpy())
 
 
+@pytest.mark.parametrize("cfg", [(8, 9, 5), (10, 12, 6)])
+@pytest.mark.parametrize("n", [1, 7, 1031])
+def test_per_ply_grids_ragged_batches(cfg, n):
+    """The cell-stationary per-ply kernel packs 3 (8x9) / 2 (10x12) games into a warp: batch sizes that
+    are not a multiple of that, checked against a host replay of the recorded trajectories."""
+    from simulator import batch
+
+    H, W, K = cfg
+    res = batch.connect_rollout(cfg, n, 5, 77, per_game=True, actions=True, final_grid=True)
+    canary = torch.full((n + 1, H * W + 1, H, W), 7, dtype=torch.int8, device="cuda")
+    grids = batch.connect_trajectory_grids(cfg, res.actions, res.length, out=canary[:n])
+    torch.cuda.synchronize()
+    assert int((canary[n] != 7).sum()) == 0  # nothing written past the last game
+    got = grids.cpu().numpy()
+    acts, lens = res.actions.cpu().numpy(), res.length.cpu().numpy()
+    for i in range(n):
+        g = np.full((H, W), -1, np.int8)
+        heights = [0] * W
+        np.testing.assert_array_equal(got[i, 0], g)
+        for t in range(int(lens[i])):
+            c = int(acts[i, t])
+            g[heights[c], c] = t & 1
+            heights[c] += 1
+            np.testing.assert_array_equal(got[i, t + 1], g, err_msg=f"game {i} ply {t + 1}")
+        for t in range(int(lens[i]) + 1, H * W + 1):
+            np.testing.assert_array_equal(got[i, t], g)
+    np.testing.assert_array_equal(got[np.arange(n), lens.astype(np.int64)], res.final_grid.cpu().numpy())
+
+
 def test_packed_host_results_equal_oracle(oracle):
     """HostRollout(packed=True): one byte per game over PCIe, unpacked on the host = the oracle's results."""
     from simulator import batch

@@ -1236,9 +1236,9 @@ connect_expand_actions_kernel(unsigned long long n, const uint8_t* __restrict__ 
 // (~5 instructions per output byte, above) is wasted work.  Here a lane owns 8 fixed cells of one game
 // and holds, in registers, the ply at which each of them is filled (tm, 0x7F = never) and by whom
 // (ow); position t is then  byte = tm <= t ? ow : 0xFF  for all 8 cells at once (per 32-bit word: one
-// subtract whose byte-wise sign bits are the comparison, one sign-replicating PRMT, one LOP3) and goes
-// straight to global memory as one 64-bit store -- the H*W/8 lanes of a game write H*W contiguous bytes,
-// and 32 / (H*W/8) games share a warp.  tm / ow are built per game by a ply-parallel scatter: lane
+// subtract whose byte-wise sign bits are the comparison, one sign-replicating PRMT, one LOP3); the
+// H*W/8 lanes of a game produce H*W contiguous bytes, 32 / (H*W/8) games share a warp, and 8 rows at a
+// time leave through a shared-memory stage as 128-bit stores.  tm / ow are built per game by a ply-parallel scatter: lane
 // q handles ply q, its row is the number of earlier plies in the same column (__match_any_sync rank
 // + a per-column counter in shared memory).
 // every byte of x replaced by 0xFF if its sign bit is set, else 0x00: PRMT with the sign-replicate bit
@@ -1258,6 +1258,9 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
     __shared__ __align__(8) uint8_t s_tm[WARPS][GPW * HW];
     __shared__ __align__(8) uint8_t s_ow[WARPS][GPW * HW];
     __shared__ uint8_t s_cnt[WARPS][GPW * 16];
+    constexpr int RB = 8;                        // rows per pass through the stage (7 for 8x9 and more resident CTAs: no gain)
+    constexpr int SPAN_STAGE = (RB * HW + 16 + 15) & ~15;  // one game's rows + room for the 8-byte alignment pad
+    __shared__ __align__(16) uint8_t s_stage[WARPS][GPW * SPAN_STAGE];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     const unsigned sg = lane / CH, ci = lane - sg * CH;  // game of the warp's group, 8-cell chunk
     uint8_t* tm = s_tm[warp];
@@ -1273,13 +1276,24 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
         }
         for (unsigned i = lane; i < GPW * 16; i += 32) cnt[i] = 0;
         __syncwarp();
+        // ---- the group's trajectories and lengths: ONE round trip to global memory (the scatter below
+        // would otherwise pay two dependent load latencies per 32 plies), parked in the stage
+        uint8_t* stg = s_stage[warp];
+        {
+            uint2 a8 = make_uint2(0u, 0u);
+            if (lane < GPW * CH && g0 + lane / CH < n_games)
+                a8 = *reinterpret_cast<const uint2*>(actions + g0 * HW + 8 * lane);
+            *reinterpret_cast<uint2*>(stg + 8 * lane) = a8;
+        }
+        const unsigned len_mine = (lane < GPW && g0 + lane < n_games) ? length[g0 + lane] : 0u;
+        __syncwarp();
         // ---- scatter: ply p of game j fills the lowest empty cell of its column
         for (unsigned q0 = 0; q0 < GPW * HW; q0 += 32) {
             const unsigned q = q0 + lane;
             const unsigned j = q / HW, pl = q - j * HW;
-            const unsigned long long g = g0 + j;
-            const bool valid = q < GPW * HW && g < n_games && pl < length[g];
-            const unsigned col = valid ? actions[g * HW + pl] : 0u;
+            const unsigned lenj = __shfl_sync(0xffffffffu, len_mine, j < GPW ? j : 0);
+            const bool valid = q < GPW * HW && pl < lenj;
+            const unsigned col = valid ? stg[q] : 0u;
             const unsigned mm = __match_any_sync(0xffffffffu, valid ? (j * 16u + col) : (0x100u + lane));
             const unsigned below = valid ? cnt[j * 16 + col] : 0u;  // stones already in the column
             __syncwarp();
@@ -1291,18 +1305,50 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
             }
             __syncwarp();
         }
-        // ---- every position of the game, 8 cells per lane
-        if (sg < GPW && g0 + sg < n_games) {
-            const uint2 tm8 = *reinterpret_cast<const uint2*>(tm + sg * HW + 8 * ci);
-            const uint2 ow8 = *reinterpret_cast<const uint2*>(ow + sg * HW + 8 * ci);
-            uint8_t* dst = out + (g0 + sg) * (unsigned long long)(T * HW) + 8 * ci;
-            uint32_t tb = 0x80808080u;  // 0x80 | t in every byte
-#pragma unroll 4
-            for (int t = 0; t < T; ++t) {
-                const uint32_t m0 = sign_bytes(tb - tm8.x), m1 = sign_bytes(tb - tm8.y);
-                *reinterpret_cast<uint2*>(dst + (size_t)t * HW) = make_uint2((ow8.x & m0) | ~m0, (ow8.y & m1) | ~m1);
-                tb += 0x01010101u;
+        // ---- every position of the game, 8 cells per lane, RB rows at a time through the stage: the
+        // lanes' 64-bit pieces of a row would reach L2 as partial sectors (72 / 120-byte rows: 0.6 of the
+        // copy peak); from the stage every game's RB*HW contiguous bytes leave as 128-bit stores.
+        uint2 tm8 = make_uint2(0x7F7F7F7Fu, 0x7F7F7F7Fu), ow8 = make_uint2(0u, 0u);
+        const bool mine = sg < GPW && g0 + sg < n_games;
+        if (mine) {
+            tm8 = *reinterpret_cast<const uint2*>(tm + sg * HW + 8 * ci);
+            ow8 = *reinterpret_cast<const uint2*>(ow + sg * HW + 8 * ci);
+        }
+        uint32_t tb = 0x80808080u;  // 0x80 | t in every byte
+        for (int t0 = 0; t0 < T; t0 += RB) {
+            const int rows = (T - t0) < RB ? (T - t0) : RB;
+            if (mine) {
+                // game sg's rows start 8 bytes into its stage area when its global address is 8 mod 16
+                uint8_t* mystage = stg + sg * SPAN_STAGE + (((g0 + sg) * (unsigned long long)(T * HW) + (unsigned)t0 * HW) & 8u) + 8 * ci;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    if (r < rows) {
+                        const uint32_t m0 = sign_bytes(tb - tm8.x), m1 = sign_bytes(tb - tm8.y);
+                        *reinterpret_cast<uint2*>(mystage + r * HW) = make_uint2((ow8.x & m0) | ~m0, (ow8.y & m1) | ~m1);
+                        tb += 0x01010101u;
+                    }
+                }
             }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < GPW; ++j) {
+                if (g0 + j < n_games) {
+                    const unsigned long long off = (g0 + j) * (unsigned long long)(T * HW) + (unsigned)t0 * HW;
+                    uint8_t* dst = out + off;
+                    const unsigned pad = (unsigned)(off & 8u);
+                    const uint8_t* src = stg + j * SPAN_STAGE + pad;
+                    const unsigned span = (unsigned)rows * HW;  // multiple of 8
+                    // head (8 bytes, if dst is 8 mod 16), 16-byte body, tail (8 bytes)
+                    const unsigned head = pad ? 8u : 0u;
+                    const unsigned body = (span - head) & ~15u;
+                    if (head && lane == 0) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+                    for (unsigned q = lane; q < (body >> 4); q += 32)
+                        *reinterpret_cast<uint4*>(dst + head + 16 * q) = *reinterpret_cast<const uint4*>(src + head + 16 * q);
+                    if (head + body < span && lane == 31)
+                        *reinterpret_cast<uint2*>(dst + head + body) = *reinterpret_cast<const uint2*>(src + head + body);
+                }
+            }
+            __syncwarp();
         }
         __syncwarp();
     }
@@ -1761,7 +1807,7 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
     if (!actions || !length || !grids) return set_error(BGS_EINVAL, "connect_trajectory_grids: null pointer");
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
-    if (((uintptr_t)grids & 7u) == 0 && ((H == 8 && W == 9) || (H == 10 && W == 12))) {
+    if (((uintptr_t)grids & 15u) == 0 && ((H == 8 && W == 9) || (H == 10 && W == 12))) {
         cudaStream_t stream = (cudaStream_t)stream_;
         auto launch = [&](auto kern, int gpw) {
             int per_sm = 0;

@@ -88,6 +88,19 @@ __device__ __forceinline__ uint32_t claim_index(unsigned m, unsigned int* counte
     return id;
 }
 
+// Warp-cooperative copy of `span` contiguous bytes; 128-bit accesses when both sides are 16-byte
+// aligned (`vec`).
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src, unsigned span, unsigned lane, bool vec) {
+    unsigned done = 0;
+    if (vec) {
+        const unsigned nvec = span >> 4;
+        for (unsigned q = lane; q < nvec; q += 32)
+            reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(src)[q];
+        done = nvec << 4;
+    }
+    for (unsigned i = done + lane; i < span; i += 32) dst[i] = src[i];
+}
+
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

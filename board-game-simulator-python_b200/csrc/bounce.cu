@@ -5,9 +5,9 @@
 // Action::sample_next_state, State::has_ended / get_reward / get_grid).  The rules are restated in
 // SURVEY.md 4.4 from tests/test_bounce.py (the engine source is not part of the reference tree).
 //
-// Data layout: a board of H*W <= 64 cells (cell = y*W + x, row 0 = bottom) is held in registers as
-// NP bit-planes of the piece values (plane b, bit cell = bit b of the value; NP = 2 for values <= 3,
-// 4 for values <= 15).  Move generation is bit-parallel reachability, not a recursive search:
+// Data layout: a board of H*W <= 64 cells is held in registers as NP bit-planes of the piece values
+// (plane b, bit cell = bit b of the value; NP = 2 for values <= 3, 4 for values <= 15).  Move
+// generation is bit-parallel reachability, not a recursive search:
 //   * one "segment" of u steps keeps three frontier masks keyed by the last direction
 //     (forward / left / right) and advances all cells at once with a shift + mask per direction;
 //   * a segment whose last step lands on pieces seeds new segments ("bounces"), grouped by the value
@@ -15,222 +15,14 @@
 // The per-source target masks of the mover (<= W sources, all in one row) are staged in shared
 // memory so that the uniform draw can be mapped to the k-th (source, target) pair in ascending order.
 //
-// The rollout kernel uses the lane state machine of bounce_lane.cuh (mover-relative orientation, a
-// guard column between rows, compile-time geometry for the default 9x6 board); the batched
-// moves / step kernels below keep the plain y*W + x layout of this file.
+// The rules live in ONE place, the lane state machine of bounce_lane.cuh (mover-relative orientation;
+// compile-time geometry and a guard column between rows for the rollout of the default 9x6 board,
+// the plain y*W + x layout for the batched moves / step kernels).
 #include "bgs_common.cuh"
 #include "bounce_lane.cuh"
 
 namespace bgs {
 namespace bounce {
-
-struct Geo {
-    int H, W, rules;
-    uint64_t board;      // low H*W bits
-    uint64_t not_left;   // cells with x > 0
-    uint64_t not_right;  // cells with x < W-1
-    uint64_t far0, far1;  // far goal row of player 0 (row H-1) / player 1 (row 0)
-    uint64_t row0;        // (1 << W) - 1
-    __host__ __device__ uint64_t far(int player) const { return player == 0 ? far0 : far1; }
-};
-
-static Geo make_geo(int H, int W, int rules) {
-    Geo g;
-    g.H = H; g.W = W; g.rules = rules;
-    g.board = (H * W == 64) ? ~0ull : ((1ull << (H * W)) - 1ull);
-    g.not_left = 0; g.not_right = 0;
-    for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) {
-            if (x > 0) g.not_left |= 1ull << (y * W + x);
-            if (x < W - 1) g.not_right |= 1ull << (y * W + x);
-        }
-    g.row0 = (1ull << W) - 1ull;
-    g.far0 = g.row0 << ((H - 1) * W);
-    g.far1 = g.row0;
-    return g;
-}
-
-template <int NP>
-struct Planes {
-    uint64_t b[NP];
-    __device__ __forceinline__ uint64_t occ() const {
-        uint64_t o = b[0];
-#pragma unroll
-        for (int i = 1; i < NP; ++i) o |= b[i];
-        return o;
-    }
-    __device__ __forceinline__ int value_at(int cell) const {
-        int v = 0;
-#pragma unroll
-        for (int i = 0; i < NP; ++i) v |= (int)((b[i] >> cell) & 1ull) << i;
-        return v;
-    }
-    __device__ __forceinline__ uint64_t cells_with_value(int u) const {
-        uint64_t m = ~0ull;
-#pragma unroll
-        for (int i = 0; i < NP; ++i) m &= ((u >> i) & 1) ? b[i] : ~b[i];
-        return m;
-    }
-};
-
-// Mask of the row holding the movable pieces of `player`: the occupied row nearest to its own side
-// (tests/test_bounce.py:43-48,60).  0 if the board is empty.  *row receives the row index.
-__device__ __forceinline__ uint64_t source_row_mask(const Geo& g, uint64_t occ, int player, int* row) {
-    if (!occ) {
-        *row = -1;
-        return 0;
-    }
-    const int cell = player == 0 ? (__ffsll((long long)occ) - 1) : (63 - __clzll((long long)occ));
-    const int y = cell / g.W;
-    *row = y;
-    return g.row0 << (y * g.W);
-}
-
-// Move generation for `player` -- SURVEY.md 4.4 rules 2-4 -- as ONE flat loop per lane.
-//
-// A lane walks its own work list: for every movable piece (ascending column) a sequence of segments,
-// for every segment `u` frontier steps.  Each loop iteration performs exactly one frontier step of
-// whatever (piece, segment) the lane is at; the bookkeeping between segments / pieces is a short
-// branch at the top.  Lanes of a warp therefore stay busy until the lane with the most steps is
-// done, instead of serialising over columns and bounce rounds (the nested formulation ran at 5 of 32
-// active lanes).
-//
-// ANY = false: writes the target mask of the piece in column x to T[x*stride] (0 where there is no
-//              movable piece) and returns the number of (source, target) pairs; *row = source row.
-// ANY = true : returns 1 as soon as one piece has a target, else 0 (T is not touched).
-template <int NP, bool ANY>
-__device__ __forceinline__ int movegen(const Geo& g, const Planes<NP>& P, int player, uint64_t* T, int stride,
-                                       int* row) {
-    const uint64_t occ = P.occ();
-    const uint64_t rowm = source_row_mask(g, occ, player, row);
-    if (!ANY)
-        for (int x = 0; x < g.W; ++x) T[x * stride] = 0ull;
-    const int base = *row * g.W;
-    const int variant = g.rules & 3;
-    const bool allow_null = (g.rules & BGS_BOUNCE_ALLOW_NULL_MOVE) != 0;
-    const uint64_t farm = g.far(player);
-    uint64_t src_left = rowm & occ;
-    uint64_t sbit = 0, occS = 0, open = 0, inter = 0, expanded = 0, pending = 0, targets = 0;
-    uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = 0;  // frontier by last direction: forward / left / right / none
-    int rem = 0, xs = 0, total = 0;
-    bool have = false;
-    for (;;) {
-        if (rem == 0) {  // between segments
-            int u;
-            uint64_t S;
-            if (pending == 0) {  // between pieces
-                if (have) {
-                    if (!allow_null) targets &= ~sbit;
-                    if (ANY) {
-                        if (targets) return 1;
-                    } else {
-                        T[xs * stride] = targets;
-                        total += __popcll(targets);
-                    }
-                }
-                if (src_left == 0) break;
-                sbit = src_left & (~src_left + 1ull);
-                src_left ^= sbit;
-                have = true;
-                const int cell = __ffsll((long long)sbit) - 1;
-                xs = cell - base;
-                occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
-                open = variant == BGS_BOUNCE_SOURCE_BLOCKED ? (g.board & ~sbit) : g.board;
-                inter = open & ~occS & ~farm;  // cells a path may pass through
-                expanded = sbit;
-                targets = 0;
-                S = sbit;
-                u = P.value_at(cell);
-            } else {  // bounce: all unexpanded landing cells that hold a piece of the same value
-                const int c = __ffsll((long long)pending) - 1;
-                u = P.value_at(c);
-                S = pending & P.cells_with_value(u);
-                pending &= ~S;
-                expanded |= S;
-            }
-            Ff = 0; Fl = 0; Fr = 0; Nn = S;  // no direction memory at the start of a segment
-            rem = u;
-        }
-        // one step of the current segment, all frontier cells at once
-        const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn;  // may go left / right (no reversal)
-        const uint64_t all = fl | Fr;
-        const uint64_t nf = player == 0 ? (all << g.W) : (all >> g.W);  // never backwards
-        const uint64_t nl = (fl & g.not_left) >> 1;
-        const uint64_t nr = (fr & g.not_right) << 1;
-        if (rem > 1) {  // intermediate cells: empty, not the far goal row
-            Ff = nf & inter; Fl = nl & inter; Fr = nr & inter; Nn = 0;
-            rem = (Ff | Fl | Fr) ? rem - 1 : 0;
-        } else {        // last step: rest on an empty cell, or bounce off a piece
-            const uint64_t land = (nf | nl | nr) & open;
-            targets |= land & ~occS;
-            pending |= land & occS & ~expanded;
-            rem = 0;
-        }
-    }
-    return ANY ? 0 : total;
-}
-
-// All targets of the single piece on (cell) -- used by the batched step kernel to validate a move.
-template <int NP>
-__device__ __forceinline__ uint64_t targets_of(const Geo& g, const Planes<NP>& P, uint64_t occ, int player,
-                                               uint64_t sbit, int v) {
-    const int variant = g.rules & 3;
-    const uint64_t occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
-    const uint64_t open = variant == BGS_BOUNCE_SOURCE_BLOCKED ? (g.board & ~sbit) : g.board;
-    const uint64_t inter = open & ~occS & ~g.far(player);
-    uint64_t expanded = sbit, pending = 0, targets = 0, S = sbit;
-    int u = v;
-    for (;;) {
-        uint64_t Ff = 0, Fl = 0, Fr = 0, Nn = S, land = 0;
-        for (int step = u; step >= 1; --step) {
-            const uint64_t fl = Ff | Fl | Nn, fr = Ff | Fr | Nn, all = fl | Fr;
-            const uint64_t nf = player == 0 ? (all << g.W) : (all >> g.W);
-            const uint64_t nl = (fl & g.not_left) >> 1, nr = (fr & g.not_right) << 1;
-            if (step > 1) {
-                Ff = nf & inter; Fl = nl & inter; Fr = nr & inter; Nn = 0;
-                if (!(Ff | Fl | Fr)) break;
-            } else {
-                land = (nf | nl | nr) & open;
-            }
-        }
-        targets |= land & ~occS;
-        pending |= land & occS & ~expanded;
-        if (!pending) break;
-        const int c = __ffsll((long long)pending) - 1;
-        u = P.value_at(c);
-        S = pending & P.cells_with_value(u);
-        pending &= ~S;
-        expanded |= S;
-    }
-    if (!(g.rules & BGS_BOUNCE_ALLOW_NULL_MOVE)) targets &= ~sbit;
-    return targets;
-}
-
-template <int NP>
-__device__ __forceinline__ bool has_any(const Geo& g, const Planes<NP>& P, int player) {
-    int row;
-    return movegen<NP, true>(g, P, player, nullptr, 0, &row) != 0;
-}
-
-template <int NP>
-__device__ __forceinline__ void move_piece(Planes<NP>& P, int scell, int tcell) {
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const uint64_t bit = (P.b[i] >> scell) & 1ull;
-        P.b[i] &= ~(1ull << scell);
-        P.b[i] |= bit << tcell;
-    }
-}
-
-__device__ __forceinline__ float2 reward_of(int winner) {
-    return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
-                       winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
-}
-
-template <int NP>
-__device__ __forceinline__ void store_grid(const Planes<NP>& P, int HW, int8_t* out) {
-    for (int c = 0; c < HW; ++c) out[c] = (int8_t)P.value_at(c);
-}
 
 // ---------------------------------------------------------------------------------------------
 // rollout kernel
@@ -356,91 +148,174 @@ bounce_rollout_lane_kernel(const GeoRT grt, const RolloutParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// batched move generation / single step on reference-layout states (int8 grids)
+// batched move generation / single step on reference-layout states (int8 grids).  Same MoveGen as
+// the rollout kernel (bounce_lane.cuh), here on the plain y*W + x layout (no guard column), so that
+// the relative target masks of player 0 ARE the public masks and those of player 1 are one 180-degree
+// rotation away.
 // ---------------------------------------------------------------------------------------------
 constexpr int STEP_THREADS = 64;
+typedef MoveGen<4, GeoRT, -1> StepGen;
 
-// Returns false if a cell holds a value outside 0..15.
-__device__ __forceinline__ bool load_planes(const int8_t* __restrict__ grid, int HW, Planes<4>& P) {
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) P.b[i] = 0;
-    for (int c = 0; c < HW; ++c) {
-        const int v = grid[c];
-        if (v < 0 || v > 15) ok = false;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) P.b[i] |= (uint64_t)((v >> i) & 1) << c;
-    }
-    return ok;
+__device__ __forceinline__ float2 reward_of(int winner) {
+    return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
+                       winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
 }
 
+__device__ __forceinline__ uint64_t rot180(const GeoRT& g, uint64_t x) { return brev64(x) >> g.rot_sh(); }
+
+// Value planes (ABSOLUTE orientation, cell = y*W + x; g has no guard column) of a state whose grid
+// bytes are staged in shared memory.  Returns false if a cell holds a value outside 0..15.
+__device__ __forceinline__ bool planes_from_stage(const uint8_t* mine, int HW, uint64_t (&b)[4]) {
+    uint32_t lo[4] = {0u, 0u, 0u, 0u}, hi[4] = {0u, 0u, 0u, 0u};
+    uint32_t bad = 0;
+    const int n_lo = HW < 32 ? HW : 32;
+    for (int c = 0; c < n_lo; ++c) {
+        const uint32_t v = mine[c], m = 1u << c;
+        bad |= v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lo[k] |= ((v >> k) & 1u) ? m : 0u;
+    }
+    for (int c = 32; c < HW; ++c) {
+        const uint32_t v = mine[c], m = 1u << (c - 32);
+        bad |= v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hi[k] |= ((v >> k) & 1u) ? m : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b[k] = ((uint64_t)hi[k] << 32) | lo[k];
+    return bad <= 15u;  // a negative int8 has bit 7 set
+}
+
+// Runs a started move generation to completion.
+__device__ __forceinline__ void run_movegen(const GeoRT& g, StepGen& mg, uint64_t* T) {
+    while (!mg.done) mg.iter(g, T, STEP_THREADS);
+}
+
+// One warp per 32 consecutive states: their grids (32*H*W contiguous bytes) are staged in shared
+// memory with coalesced 128-bit loads; lane l works on state g0 + l out of the stage.
 __global__ void __launch_bounds__(STEP_THREADS)
-bounce_moves_kernel(const Geo g, unsigned long long n, const int8_t* __restrict__ grid,
+bounce_moves_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict__ grid,
                     const int8_t* __restrict__ player, const uint8_t* __restrict__ ended,
-                    int8_t* source_row, uint64_t* targets, int32_t* count) {
+                    int8_t* source_row, uint64_t* targets, int32_t* count, bool vec) {
     __shared__ uint64_t s_T[8 * STEP_THREADS];
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    __shared__ __align__(16) uint8_t s_stage[STEP_THREADS / 32][32 * 64];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long g0 = ((unsigned long long)blockIdx.x * (STEP_THREADS / 32) + warp) * 32ull;
+    if (g0 >= n) return;  // warp-uniform
+    const int HW = g.H * g.W;
+    const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
+    warp_copy_bytes(s_stage[warp], reinterpret_cast<const uint8_t*>(grid) + g0 * (unsigned)HW, rows * (unsigned)HW, lane, vec);
+    __syncwarp();
+    const unsigned long long i = g0 + lane;
     if (i >= n) return;
     uint64_t* T = s_T + threadIdx.x;
-    const int HW = g.H * g.W;
-    Planes<4> P;
-    const bool ok = load_planes(grid + i * HW, HW, P);
-    int row = -1, total = 0;
+    StepGen mg;
+    const bool ok = planes_from_stage(s_stage[warp] + lane * HW, HW, mg.b);
     const bool over = (ended && ended[i]) || !ok;
     const int pl = player[i] & 1;
-    if (!over) total = movegen<4, false>(g, P, pl, T, STEP_THREADS, &row);
-    for (int x = 0; x < g.W; ++x) targets[i * g.W + x] = over ? 0ull : T[x * STEP_THREADS];
-    if (source_row) source_row[i] = (int8_t)(total > 0 ? row : -1);
-    if (count) count[i] = ok ? total : -1;
+    if (pl) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mg.b[k] = rot180(g, mg.b[k]);
+    }
+    uint64_t src = StepGen::sources(g, mg.b, over);  // movable pieces, mover-relative
+    mg.begin_with(g, src, false);
+    run_movegen(g, mg, T);
+    for (int x = 0; x < g.W; ++x) targets[i * g.W + x] = 0ull;
+    int row_rel = -1;
+    if (src) row_rel = g.row_of(ctz64(src));
+    for (int j = 0; src; ++j) {  // the j-th movable piece in ascending relative column
+        const int cell = ctz64(src);
+        src &= src - 1ull;
+        const int x_rel = cell - row_rel * g.S;
+        const uint64_t t = T[j * STEP_THREADS];
+        targets[i * g.W + (pl ? g.W - 1 - x_rel : x_rel)] = pl ? rot180(g, t) : t;
+    }
+    if (source_row) source_row[i] = (int8_t)(mg.total > 0 ? (pl ? g.H - 1 - row_rel : row_rel) : -1);
+    if (count) count[i] = ok ? mg.total : -1;
 }
 
 __global__ void __launch_bounds__(STEP_THREADS)
-bounce_step_kernel(const Geo g, unsigned long long n, const int8_t* __restrict__ grid,
+bounce_step_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict__ grid,
                    const int8_t* __restrict__ player, const int8_t* __restrict__ winner,
                    const uint8_t* __restrict__ ended,
                    const int32_t* __restrict__ move, int8_t* grid_out, int8_t* player_out,
-                   int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status) {
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                   int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status, bool vec) {
+    __shared__ uint64_t s_T[8 * STEP_THREADS];
+    __shared__ __align__(16) uint8_t s_stage[STEP_THREADS / 32][32 * 64];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long g0 = ((unsigned long long)blockIdx.x * (STEP_THREADS / 32) + warp) * 32ull;
+    if (g0 >= n) return;  // warp-uniform
     const int HW = g.H * g.W;
-    const int8_t* gi = grid + i * HW;
-    int8_t* go = grid_out + i * HW;
-    Planes<4> P;
-    const bool ok = load_planes(gi, HW, P);
-    int pl = player[i] & 1;
-    const bool over = ended && ended[i];
-    const int sx = move[4 * i + 0], sy = move[4 * i + 1], tx = move[4 * i + 2], ty = move[4 * i + 3];
-    bool legal = ok && !over && sx >= 0 && sx < g.W && sy >= 0 && sy < g.H && tx >= 0 && tx < g.W && ty >= 0 && ty < g.H;
-    int win = winner ? (int)winner[i] : -1;
-    bool end_new = over;
-    if (legal) {
-        const uint64_t occ = P.occ();
-        int row;
-        const uint64_t rowm = source_row_mask(g, occ, pl, &row);
-        const int scell = sy * g.W + sx, tcell = ty * g.W + tx;
-        const uint64_t sbit = 1ull << scell;
-        legal = (rowm & occ & sbit) != 0;
-        if (legal) legal = (targets_of<4>(g, P, occ, pl, sbit, P.value_at(scell)) >> tcell) & 1ull;
+    const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
+    const unsigned span = rows * (unsigned)HW;
+    warp_copy_bytes(s_stage[warp], reinterpret_cast<const uint8_t*>(grid) + g0 * (unsigned)HW, span, lane, vec);
+    __syncwarp();
+    const unsigned long long i = g0 + lane;
+    if (i < n) {
+        uint64_t* T = s_T + threadIdx.x;
+        uint8_t* mine = s_stage[warp] + lane * HW;  // the new grid = the old one with two cells changed
+        StepGen mg;
+        const bool ok = planes_from_stage(mine, HW, mg.b);
+        int pl = player[i] & 1;
+        const bool over = ended && ended[i];
+        const int sx = move[4 * i + 0], sy = move[4 * i + 1], tx = move[4 * i + 2], ty = move[4 * i + 3];
+        bool legal = ok && !over && sx >= 0 && sx < g.W && sy >= 0 && sy < g.H && tx >= 0 && tx < g.W && ty >= 0 && ty < g.H;
+        int win = winner ? (int)winner[i] : -1;
+        bool end_new = over;
         if (legal) {
-            move_piece<4>(P, scell, tcell);
-            if ((1ull << tcell) & g.far(pl)) {
-                win = pl;
-                end_new = true;
-            } else if (!has_any<4>(g, P, 1 - pl)) {
-                end_new = true;
-                if (has_any<4>(g, P, pl)) win = pl;
+            if (pl) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mg.b[k] = rot180(g, mg.b[k]);
             }
-            pl = 1 - pl;
+            const int scell_abs = sy * g.W + sx, tcell_abs = ty * g.W + tx;
+            const int scell = pl ? HW - 1 - scell_abs : scell_abs, tcell = pl ? HW - 1 - tcell_abs : tcell_abs;
+            const uint64_t smask = 1ull << scell, tmask = 1ull << tcell;
+            legal = (StepGen::sources(g, mg.b, false) & smask) != 0;  // a movable piece of the mover
+            if (legal) {
+                mg.begin_with(g, smask, false);  // the targets of that piece only
+                run_movegen(g, mg, T);
+                legal = mg.total > 0 && (T[0] & tmask) != 0;
+            }
+            if (legal) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool has = (mg.b[k] & smask) != 0;
+                    mg.b[k] = (mg.b[k] & ~smask) | (has ? tmask : 0ull);
+                }
+                mine[tcell_abs] = mine[scell_abs];
+                mine[scell_abs] = 0;
+                if (tmask & g.m_far()) {  // reached the far goal row
+                    win = pl;
+                    end_new = true;
+                } else {
+                    uint64_t own[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        own[k] = mg.b[k];
+                        mg.b[k] = rot180(g, mg.b[k]);  // the opponent's orientation
+                    }
+                    mg.begin(g, true, false);  // does the opponent have any action?
+                    run_movegen(g, mg, T);
+                    if (!mg.found) {  // blocked: the mover wins unless blocked too (draw)
+                        end_new = true;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mg.b[k] = own[k];
+                        mg.begin(g, true, false);
+                        run_movegen(g, mg, T);
+                        if (mg.found) win = pl;
+                    }
+                }
+                pl = 1 - pl;
+            }
         }
+        player_out[i] = (int8_t)pl;
+        winner_out[i] = (int8_t)win;
+        if (ended_out) ended_out[i] = end_new;
+        if (reward_out) reinterpret_cast<float2*>(reward_out)[i] = reward_of(win);
+        if (status) status[i] = legal ? 0 : 1;
     }
-    if (legal) store_grid<4>(P, HW, go);
-    else if (go != gi)
-        for (int c = 0; c < HW; ++c) go[c] = gi[c];
-    player_out[i] = (int8_t)pl;
-    winner_out[i] = (int8_t)win;
-    if (ended_out) ended_out[i] = end_new;
-    if (reward_out) reinterpret_cast<float2*>(reward_out)[i] = reward_of(win);
-    if (status) status[i] = legal ? 0 : 1;
+    __syncwarp();
+    warp_copy_bytes(reinterpret_cast<uint8_t*>(grid_out) + g0 * (unsigned)HW, s_stage[warp], span, lane, vec);
 }
 
 static bool supported(int H, int W, int max_value) {
@@ -462,10 +337,10 @@ extern "C" int bgs_bounce_moves(int H, int W, int rules, uint64_t n, const int8_
     if (!grid || !player || !targets) return set_error(BGS_EINVAL, "bounce_moves: null required pointer");
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
-    const Geo g = make_geo(H, W, rules);
+    const GeoRT g = make_geo_rt(H, W, rules, /*guard=*/false);
     const unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
-    bounce_moves_kernel<<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(g, n, grid, player, ended,
-                                                                                     source_row, targets, count);
+    bounce_moves_kernel<<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
+        g, n, grid, player, ended, source_row, targets, count, ((uintptr_t)grid & 15u) == 0);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }
@@ -479,10 +354,11 @@ extern "C" int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t
         return set_error(BGS_EINVAL, "bounce_step: null required pointer");
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
-    const Geo g = make_geo(H, W, rules);
+    const GeoRT g = make_geo_rt(H, W, rules, /*guard=*/false);
     const unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
     bounce_step_kernel<<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
-        g, n, grid, player, winner, ended, move, grid_out, player_out, winner_out, ended_out, reward_out, status);
+        g, n, grid, player, winner, ended, move, grid_out, player_out, winner_out, ended_out, reward_out, status,
+        (((uintptr_t)grid | (uintptr_t)grid_out) & 15u) == 0);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }

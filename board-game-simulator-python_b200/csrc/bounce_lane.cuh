@@ -127,10 +127,10 @@ struct GeoRT {
     BGS_HD int row_of(int cell) const { return (int)(((uint32_t)cell * inv_s) >> 16); }
 };
 
-inline GeoRT make_geo_rt(int H, int W, int rules) {
+inline GeoRT make_geo_rt(int H, int W, int rules, bool guard = true) {
     GeoRT g;
     g.H = H; g.W = W; g.rules = rules;
-    g.S = (H * (W + 1) <= 64) ? W + 1 : W;
+    g.S = (guard && H * (W + 1) <= 64) ? W + 1 : W;
     g.rot_shift = 63 - ((H - 1) * g.S + W - 1);
     g.board = 0; g.not_left = 0; g.not_right = 0;
     for (int y = 0; y < H; ++y)

@@ -400,11 +400,12 @@ def test_per_ply_grids_equal_oracle_replay(oracle, cfg):
     np.testing.assert_array_equal(got[np.arange(n), lens.astype(np.int64)], res.final_grid.cpu().numpy())
 
 
-@pytest.mark.parametrize("cfg", [(8, 9, 5), (10, 12, 6)])
+@pytest.mark.parametrize("cfg", [(6, 7, 4), (8, 9, 5), (10, 12, 6)])
 @pytest.mark.parametrize("n", [1, 7, 1031])
 def test_per_ply_grids_ragged_batches(cfg, n):
-    """The cell-stationary per-ply kernel packs 3 (8x9) / 2 (10x12) games into a warp: batch sizes that
-    are not a multiple of that, checked against a host replay of the recorded trajectories."""
+    """The cell-stationary per-ply kernel packs 3 (8x9) / 2 (10x12) games into a warp, the row kernel (6x7)
+    32 positions: batch sizes that are not a multiple of that, checked against a host replay of the
+    recorded trajectories."""
     from simulator import batch
 
     H, W, K = cfg

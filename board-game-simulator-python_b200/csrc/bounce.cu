@@ -32,7 +32,8 @@ struct RolloutParams {
     unsigned long long game_id0;
     uint32_t seed_lo, seed_hi;
     int max_plies;
-    uint64_t plane0[4];  // bit-planes of the start position (the Config grid)
+    uint64_t plane0[4];     // bit-planes of the start position (the Config grid), low 64 bits
+    uint64_t plane0_hi[4];  // ... bits 64..127 (boards on 128-bit words)
     uint8_t* moves;      // [n, max_plies, 2] pre-filled 0xFF, or null
     uint16_t* length;
     int8_t* winner;
@@ -57,13 +58,18 @@ constexpr int PLY_BATCH = 12;  // lanes that must be ready before the ply transi
 // ---------------------------------------------------------------------------------------------
 template <int NP, class G, int RULES>
 __global__ void __launch_bounds__(ROLLOUT_THREADS)
-bounce_rollout_lane_kernel(const GeoRT grt, const RolloutParams p) {
+bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutParams p) {
+    typedef typename G::bits B;
+    constexpr int MAXSRC = sizeof(B) == 8 ? 8 : 16;  // movable pieces = columns of one row
     __shared__ unsigned int s_hist[HIST_BINS];
-    __shared__ uint64_t s_T[8 * ROLLOUT_THREADS];
+    __shared__ __align__(16) B s_T[MAXSRC * ROLLOUT_THREADS];
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    uint64_t* T = s_T + threadIdx.x;  // T[j * ROLLOUT_THREADS] = targets of the j-th movable piece
+    B* T = s_T + threadIdx.x;  // T[j * ROLLOUT_THREADS] = targets of the j-th movable piece
     const G g(grt);
+    B plane0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) plane0[k] = make_bits<B>(p.plane0[k], p.plane0_hi[k]);
     const LaneOut out{p.moves, p.length, p.winner, p.final_grid, p.reward};
     Game<NP, G> gm;
     MoveGen<NP, G, RULES> mg;
@@ -86,7 +92,7 @@ bounce_rollout_lane_kernel(const GeoRT grt, const RolloutParams p) {
                                      p.start_winner ? (int)p.start_winner[idx] : BGS_WINNER_DRAW,
                                      p.start_ended && p.start_ended[idx]);
         else
-            gm.begin_planes(g, p.plane0);
+            gm.begin_planes(g, plane0);
         start_movegen(false, no_moves);
     };
     if (active) begin_game();
@@ -154,51 +160,57 @@ bounce_rollout_lane_kernel(const GeoRT grt, const RolloutParams p) {
 // rotation away.
 // ---------------------------------------------------------------------------------------------
 constexpr int STEP_THREADS = 64;
-typedef MoveGen<4, GeoRT, -1> StepGen;
+template <class B>
+using StepGen = MoveGen<4, GeoRTb<B>, -1>;
 
 __device__ __forceinline__ float2 reward_of(int winner) {
     return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
                        winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
 }
 
-__device__ __forceinline__ uint64_t rot180(const GeoRT& g, uint64_t x) { return brev64(x) >> g.rot_sh(); }
+template <class B>
+__device__ __forceinline__ B rot180(const GeoRTb<B>& g, B x) { return revb(x) >> g.rot_sh(); }
 
 // Value planes (ABSOLUTE orientation, cell = y*W + x; g has no guard column) of a state whose grid
 // bytes are staged in shared memory.  Returns false if a cell holds a value outside 0..15.
-__device__ __forceinline__ bool planes_from_stage(const uint8_t* mine, int HW, uint64_t (&b)[4]) {
-    uint32_t lo[4] = {0u, 0u, 0u, 0u}, hi[4] = {0u, 0u, 0u, 0u};
+template <class B>
+__device__ __forceinline__ bool planes_from_stage(const uint8_t* mine, int HW, B (&b)[4]) {
+    constexpr int NW = (int)sizeof(B) / 4;  // 32-bit words of a plane
     uint32_t bad = 0;
-    const int n_lo = HW < 32 ? HW : 32;
-    for (int c = 0; c < n_lo; ++c) {
-        const uint32_t v = mine[c], m = 1u << c;
-        bad |= v;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) lo[k] |= ((v >> k) & 1u) ? m : 0u;
+    for (int k = 0; k < 4; ++k) b[k] = 0;
+#pragma unroll
+    for (int wi = 0; wi < NW; ++wi) {
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+        const int c1 = HW < 32 * (wi + 1) ? HW : 32 * (wi + 1);
+        for (int c = 32 * wi; c < c1; ++c) {
+            const uint32_t v = mine[c], m = 1u << (c - 32 * wi);
+            bad |= v;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] |= ((v >> k) & 1u) ? m : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b[k] |= (B)acc[k] << (32 * wi);
     }
-    for (int c = 32; c < HW; ++c) {
-        const uint32_t v = mine[c], m = 1u << (c - 32);
-        bad |= v;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hi[k] |= ((v >> k) & 1u) ? m : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) b[k] = ((uint64_t)hi[k] << 32) | lo[k];
     return bad <= 15u;  // a negative int8 has bit 7 set
 }
 
 // Runs a started move generation to completion.
-__device__ __forceinline__ void run_movegen(const GeoRT& g, StepGen& mg, uint64_t* T) {
+template <class B>
+__device__ __forceinline__ void run_movegen(const GeoRTb<B>& g, StepGen<B>& mg, B* T) {
     while (!mg.done) mg.iter(g, T, STEP_THREADS);
 }
 
 // One warp per 32 consecutive states: their grids (32*H*W contiguous bytes) are staged in shared
 // memory with coalesced 128-bit loads; lane l works on state g0 + l out of the stage.
+template <class B>
 __global__ void __launch_bounds__(STEP_THREADS)
-bounce_moves_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict__ grid,
+bounce_moves_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __restrict__ grid,
                     const int8_t* __restrict__ player, const uint8_t* __restrict__ ended,
                     int8_t* source_row, uint64_t* targets, int32_t* count, bool vec) {
-    __shared__ uint64_t s_T[8 * STEP_THREADS];
-    __shared__ __align__(16) uint8_t s_stage[STEP_THREADS / 32][32 * 64];
+    constexpr int MAXSRC = sizeof(B) == 8 ? 8 : 16, MAXCELLS = (int)sizeof(B) * 8;
+    __shared__ __align__(16) B s_T[MAXSRC * STEP_THREADS];
+    __shared__ __align__(16) uint8_t s_stage[STEP_THREADS / 32][32 * MAXCELLS];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned long long g0 = ((unsigned long long)blockIdx.x * (STEP_THREADS / 32) + warp) * 32ull;
     if (g0 >= n) return;  // warp-uniform
@@ -208,8 +220,8 @@ bounce_moves_kernel(const GeoRT g, unsigned long long n, const int8_t* __restric
     __syncwarp();
     const unsigned long long i = g0 + lane;
     if (i >= n) return;
-    uint64_t* T = s_T + threadIdx.x;
-    StepGen mg;
+    B* T = s_T + threadIdx.x;
+    StepGen<B> mg;
     const bool ok = planes_from_stage(s_stage[warp] + lane * HW, HW, mg.b);
     const bool over = (ended && ended[i]) || !ok;
     const int pl = player[i] & 1;
@@ -217,31 +229,37 @@ bounce_moves_kernel(const GeoRT g, unsigned long long n, const int8_t* __restric
 #pragma unroll
         for (int k = 0; k < 4; ++k) mg.b[k] = rot180(g, mg.b[k]);
     }
-    uint64_t src = StepGen::sources(g, mg.b, over);  // movable pieces, mover-relative
+    B src = StepGen<B>::sources(g, mg.b, over);  // movable pieces, mover-relative
     mg.begin_with(g, src, false);
     run_movegen(g, mg, T);
-    for (int x = 0; x < g.W; ++x) targets[i * g.W + x] = 0ull;
+    constexpr int TW = (int)sizeof(B) / 8;  // 64-bit words of one target mask
+    for (int x = 0; x < g.W * TW; ++x) targets[i * g.W * TW + x] = 0ull;
     int row_rel = -1;
-    if (src) row_rel = g.row_of(ctz64(src));
+    if (src) row_rel = g.row_of(ctzb(src));
     for (int j = 0; src; ++j) {  // the j-th movable piece in ascending relative column
-        const int cell = ctz64(src);
-        src &= src - 1ull;
+        const int cell = ctzb(src);
+        src &= src - (B)1;
         const int x_rel = cell - row_rel * g.S;
-        const uint64_t t = T[j * STEP_THREADS];
-        targets[i * g.W + (pl ? g.W - 1 - x_rel : x_rel)] = pl ? rot180(g, t) : t;
+        B t = T[j * STEP_THREADS];
+        if (pl) t = rot180(g, t);
+        uint64_t* dst = targets + (i * g.W + (pl ? g.W - 1 - x_rel : x_rel)) * TW;
+#pragma unroll
+        for (int w = 0; w < TW; ++w) dst[w] = (uint64_t)(t >> (w * 32) >> (w * 32));
     }
     if (source_row) source_row[i] = (int8_t)(mg.total > 0 ? (pl ? g.H - 1 - row_rel : row_rel) : -1);
     if (count) count[i] = ok ? mg.total : -1;
 }
 
+template <class B>
 __global__ void __launch_bounds__(STEP_THREADS)
-bounce_step_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict__ grid,
+bounce_step_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __restrict__ grid,
                    const int8_t* __restrict__ player, const int8_t* __restrict__ winner,
                    const uint8_t* __restrict__ ended,
                    const int32_t* __restrict__ move, int8_t* grid_out, int8_t* player_out,
                    int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status, bool vec) {
-    __shared__ uint64_t s_T[8 * STEP_THREADS];
-    __shared__ __align__(16) uint8_t s_stage[STEP_THREADS / 32][32 * 64];
+    constexpr int MAXSRC = sizeof(B) == 8 ? 8 : 16, MAXCELLS = (int)sizeof(B) * 8;
+    __shared__ __align__(16) B s_T[MAXSRC * STEP_THREADS];
+    __shared__ __align__(16) uint8_t s_stage[STEP_THREADS / 32][32 * MAXCELLS];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned long long g0 = ((unsigned long long)blockIdx.x * (STEP_THREADS / 32) + warp) * 32ull;
     if (g0 >= n) return;  // warp-uniform
@@ -252,9 +270,9 @@ bounce_step_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict
     __syncwarp();
     const unsigned long long i = g0 + lane;
     if (i < n) {
-        uint64_t* T = s_T + threadIdx.x;
+        B* T = s_T + threadIdx.x;
         uint8_t* mine = s_stage[warp] + lane * HW;  // the new grid = the old one with two cells changed
-        StepGen mg;
+        StepGen<B> mg;
         const bool ok = planes_from_stage(mine, HW, mg.b);
         int pl = player[i] & 1;
         const bool over = ended && ended[i];
@@ -269,8 +287,8 @@ bounce_step_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict
             }
             const int scell_abs = sy * g.W + sx, tcell_abs = ty * g.W + tx;
             const int scell = pl ? HW - 1 - scell_abs : scell_abs, tcell = pl ? HW - 1 - tcell_abs : tcell_abs;
-            const uint64_t smask = 1ull << scell, tmask = 1ull << tcell;
-            legal = (StepGen::sources(g, mg.b, false) & smask) != 0;  // a movable piece of the mover
+            const B smask = (B)1 << scell, tmask = (B)1 << tcell;
+            legal = (StepGen<B>::sources(g, mg.b, false) & smask) != 0;  // a movable piece of the mover
             if (legal) {
                 mg.begin_with(g, smask, false);  // the targets of that piece only
                 run_movegen(g, mg, T);
@@ -280,7 +298,7 @@ bounce_step_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const bool has = (mg.b[k] & smask) != 0;
-                    mg.b[k] = (mg.b[k] & ~smask) | (has ? tmask : 0ull);
+                    mg.b[k] = (mg.b[k] & ~smask) | (has ? tmask : (B)0);
                 }
                 mine[tcell_abs] = mine[scell_abs];
                 mine[scell_abs] = 0;
@@ -288,7 +306,7 @@ bounce_step_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict
                     win = pl;
                     end_new = true;
                 } else {
-                    uint64_t own[4];
+                    B own[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         own[k] = mg.b[k];
@@ -318,8 +336,11 @@ bounce_step_kernel(const GeoRT g, unsigned long long n, const int8_t* __restrict
     warp_copy_bytes(reinterpret_cast<uint8_t*>(grid_out) + g0 * (unsigned)HW, s_stage[warp], span, lane, vec);
 }
 
+// boards that need 128-bit words
+static bool wide_board(int H, int W) { return W > 8 || H * W > 64; }
+
 static bool supported(int H, int W, int max_value) {
-    return H >= 1 && W >= 1 && W <= 8 && H * W <= 64 && max_value <= 15;
+    return H >= 1 && W >= 1 && W <= 16 && H * W <= 128 && max_value <= 15;
 }
 
 }  // namespace bounce
@@ -337,10 +358,14 @@ extern "C" int bgs_bounce_moves(int H, int W, int rules, uint64_t n, const int8_
     if (!grid || !player || !targets) return set_error(BGS_EINVAL, "bounce_moves: null required pointer");
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
-    const GeoRT g = make_geo_rt(H, W, rules, /*guard=*/false);
     const unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
-    bounce_moves_kernel<<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
-        g, n, grid, player, ended, source_row, targets, count, ((uintptr_t)grid & 15u) == 0);
+    const bool vec = ((uintptr_t)grid & 15u) == 0;
+    if (wide_board(H, W))
+        bounce_moves_kernel<u128><<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
+            make_geo_rt_b<u128>(H, W, rules, /*guard=*/false), n, grid, player, ended, source_row, targets, count, vec);
+    else
+        bounce_moves_kernel<uint64_t><<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
+            make_geo_rt(H, W, rules, /*guard=*/false), n, grid, player, ended, source_row, targets, count, vec);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }
@@ -354,11 +379,16 @@ extern "C" int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t
         return set_error(BGS_EINVAL, "bounce_step: null required pointer");
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
-    const GeoRT g = make_geo_rt(H, W, rules, /*guard=*/false);
     const unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
-    bounce_step_kernel<<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
-        g, n, grid, player, winner, ended, move, grid_out, player_out, winner_out, ended_out, reward_out, status,
-        (((uintptr_t)grid | (uintptr_t)grid_out) & 15u) == 0);
+    const bool vec = (((uintptr_t)grid | (uintptr_t)grid_out) & 15u) == 0;
+    if (wide_board(H, W))
+        bounce_step_kernel<u128><<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
+            make_geo_rt_b<u128>(H, W, rules, /*guard=*/false), n, grid, player, winner, ended, move, grid_out, player_out,
+            winner_out, ended_out, reward_out, status, vec);
+    else
+        bounce_step_kernel<uint64_t><<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
+            make_geo_rt(H, W, rules, /*guard=*/false), n, grid, player, winner, ended, move, grid_out, player_out,
+            winner_out, ended_out, reward_out, status, vec);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }
@@ -376,7 +406,7 @@ static int persistent_blocks(K kern, uint32_t n_games, int* blocks_out) {
 }
 
 template <int NP, class G, int RULES>
-static int launch_bounce_lane(const GeoRT& grt, const RolloutParams& p, cudaStream_t stream) {
+static int launch_bounce_lane(const GeoRTb<typename G::bits>& grt, const RolloutParams& p, cudaStream_t stream) {
     auto kern = bounce_rollout_lane_kernel<NP, G, RULES>;
     int blocks = 0;
     if (int rc = persistent_blocks(kern, p.n_games, &blocks)) return rc;
@@ -392,7 +422,7 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
                                void* stream_) {
     if (max_plies < 0 || max_plies > 65535) return set_error(BGS_EINVAL, "bounce_rollout: max_plies out of range");
     int maxv = 0;
-    if (grid0 && H >= 1 && W >= 1 && H * W <= 64)
+    if (grid0 && H >= 1 && W >= 1 && H * W <= 128)
         for (int c = 0; c < H * W; ++c) {
             if (grid0[c] < 0) return set_error(BGS_EINVAL, "bounce_rollout: negative cell value");
             if (grid0[c] > maxv) maxv = grid0[c];
@@ -403,13 +433,26 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const GeoRT grt = make_geo_rt(H, W, rules);
     RolloutParams p;
     p.n_games = (uint32_t)n_games; p.game_id0 = game_id0;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.max_plies = max_plies;
-    for (int i = 0; i < 4; ++i) p.plane0[i] = 0;
-    if (grid0) planes_from_grid(grt, grid0, p.plane0);
+    const bool wide = wide_board(H, W);
+    const GeoRT grt = make_geo_rt(wide ? 1 : H, wide ? 1 : W, rules);
+    const GeoRT128 grt128 = make_geo_rt_b<u128>(H, W, rules);
+    for (int i = 0; i < 4; ++i) p.plane0[i] = p.plane0_hi[i] = 0;
+    if (grid0) {
+        if (wide) {
+            u128 pl[4];
+            planes_from_grid(grt128, grid0, pl);
+            for (int i = 0; i < 4; ++i) {
+                p.plane0[i] = (uint64_t)pl[i];
+                p.plane0_hi[i] = (uint64_t)(pl[i] >> 64);
+            }
+        } else {
+            planes_from_grid(grt, grid0, p.plane0);
+        }
+    }
     p.moves = moves; p.length = length; p.winner = winner; p.final_grid = final_grid; p.reward = reward;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
     p.start_grid = start_grid; p.start_player = start_player; p.start_winner = start_winner; p.start_ended = start_ended;
@@ -419,6 +462,7 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     BGS_CUDA_TRY(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
     if (moves) BGS_CUDA_TRY(cudaMemsetAsync(moves, 0xFF, n_games * (size_t)max_plies * 2, stream));
     // per-game start grids may hold any value up to 15: use the 4-plane kernel
+    if (wide) return launch_bounce_lane<4, GeoRT128, -1>(grt128, p, stream);
     if (maxv <= 3 && !start_grid) {
         if (H == 9 && W == 6 && rules == 0) return launch_bounce_lane<2, GeoCT<9, 6>, 0>(grt, p, stream);
         return launch_bounce_lane<2, GeoRT, -1>(grt, p, stream);
@@ -452,7 +496,7 @@ extern "C" int bgs_bounce_rollout_host(int device, const int8_t* grid0, int H, i
     if (int rc = require_device()) return rc;
     BGS_CUDA_TRY(cudaSetDevice(device));
     if (n == 0) return BGS_OK;
-    if (H < 1 || W < 1 || H * W > 64) return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d", H, W);
+    if (!supported(H, W, 0)) return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d", H, W);
     const size_t HW = (size_t)H * W;
     cudaStream_t st;
     BGS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));

@@ -83,6 +83,22 @@ BGS_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
+// ---- board words: one 64-bit word (H*W <= 64, W <= 8) or an unsigned __int128 (H*W <= 128, W <= 16) ----
+typedef unsigned __int128 u128;
+BGS_HD int popcb(uint64_t x) { return popc64(x); }
+BGS_HD int popcb(u128 x) { return popc64((uint64_t)x) + popc64((uint64_t)(x >> 64)); }
+BGS_HD int ctzb(uint64_t x) { return ctz64(x); }
+BGS_HD int ctzb(u128 x) {
+    const uint64_t lo = (uint64_t)x;
+    return lo ? ctz64(lo) : 64 + ctz64((uint64_t)(x >> 64));
+}
+BGS_HD uint64_t revb(uint64_t x) { return brev64(x); }
+BGS_HD u128 revb(u128 x) { return ((u128)brev64((uint64_t)x) << 64) | (u128)brev64((uint64_t)(x >> 64)); }
+
+template <class B> BGS_HD B make_bits(uint64_t lo, uint64_t hi);
+template <> BGS_HD uint64_t make_bits<uint64_t>(uint64_t lo, uint64_t) { return lo; }
+template <> BGS_HD u128 make_bits<u128>(uint64_t lo, uint64_t hi) { return ((u128)hi << 64) | lo; }
+
 // Philox4x32-10, counter (c0..c3), key (k0, k1) -- same function as bgs_common.cuh's device copy.
 BGS_HD void philox_hd(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                       uint32_t (&out)[4]) {
@@ -106,57 +122,66 @@ BGS_HD void philox_hd(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32
 // Cell (x, y) is bit y*S + x.  S = W + 1 whenever H*(W+1) <= 64: the spare GUARD column (never part
 // of `board`) absorbs horizontal steps off the left / right edge, so that the frontier steps need no
 // edge masks (not_left / not_right are all-ones then); S = W otherwise.
-struct GeoRT {
+template <class B>
+struct GeoRTb {
+    typedef B bits;
+    static constexpr int BITS = (int)sizeof(B) * 8;
     int H, W, S, rules;
-    int rot_shift;       // 63 - (index of the last cell): rot180(x) = brev64(x) >> rot_shift
-    uint64_t board;      // the H*W valid cells
-    uint64_t not_left;   // cells with x > 0      (all-ones with a guard column)
-    uint64_t not_right;  // cells with x < W-1    (all-ones with a guard column)
-    uint64_t far;        // the mover's far goal row in mover-relative orientation = row H-1
+    int rot_shift;       // BITS-1 - (index of the last cell): rot180(x) = bit-reverse(x) >> rot_shift
+    B board;             // the H*W valid cells
+    B not_left;          // cells with x > 0      (all-ones with a guard column)
+    B not_right;         // cells with x < W-1    (all-ones with a guard column)
+    B far;               // the mover's far goal row in mover-relative orientation = row H-1
     uint32_t row0;       // (1 << W) - 1
-    uint32_t inv_s;      // ceil(2^16 / S): cell / S == (cell * inv_s) >> 16 for cell < 64, S <= 9
+    uint32_t inv_s;      // ceil(2^16 / S): cell / S == (cell * inv_s) >> 16 for cell < 128, S <= 17
     BGS_HD int h() const { return H; }
     BGS_HD int w() const { return W; }
     BGS_HD int s() const { return S; }
     BGS_HD int rot_sh() const { return rot_shift; }
-    BGS_HD uint64_t m_board() const { return board; }
-    BGS_HD uint64_t m_not_left() const { return not_left; }
-    BGS_HD uint64_t m_not_right() const { return not_right; }
-    BGS_HD uint64_t m_far() const { return far; }
+    BGS_HD B m_board() const { return board; }
+    BGS_HD B m_not_left() const { return not_left; }
+    BGS_HD B m_not_right() const { return not_right; }
+    BGS_HD B m_far() const { return far; }
     BGS_HD uint32_t m_row0() const { return row0; }
     BGS_HD int row_of(int cell) const { return (int)(((uint32_t)cell * inv_s) >> 16); }
 };
+typedef GeoRTb<uint64_t> GeoRT;
+typedef GeoRTb<u128> GeoRT128;
 
-inline GeoRT make_geo_rt(int H, int W, int rules, bool guard = true) {
-    GeoRT g;
+template <class B>
+inline GeoRTb<B> make_geo_rt_b(int H, int W, int rules, bool guard = true) {
+    GeoRTb<B> g;
     g.H = H; g.W = W; g.rules = rules;
-    g.S = (guard && H * (W + 1) <= 64) ? W + 1 : W;
-    g.rot_shift = 63 - ((H - 1) * g.S + W - 1);
+    g.S = (guard && H * (W + 1) <= GeoRTb<B>::BITS) ? W + 1 : W;
+    g.rot_shift = GeoRTb<B>::BITS - 1 - ((H - 1) * g.S + W - 1);
     g.board = 0; g.not_left = 0; g.not_right = 0;
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
-            g.board |= 1ull << (y * g.S + x);
-            if (x > 0) g.not_left |= 1ull << (y * g.S + x);
-            if (x < W - 1) g.not_right |= 1ull << (y * g.S + x);
+            g.board |= (B)1 << (y * g.S + x);
+            if (x > 0) g.not_left |= (B)1 << (y * g.S + x);
+            if (x < W - 1) g.not_right |= (B)1 << (y * g.S + x);
         }
-    if (g.S > W) g.not_left = g.not_right = ~0ull;
+    if (g.S > W) g.not_left = g.not_right = ~(B)0;
     g.row0 = (uint32_t)((1ull << W) - 1ull);
-    g.far = (uint64_t)g.row0 << ((H - 1) * g.S);
+    g.far = (B)g.row0 << ((H - 1) * g.S);
     g.inv_s = (65536u + (uint32_t)g.S - 1u) / (uint32_t)g.S;
     return g;
 }
+inline GeoRT make_geo_rt(int H, int W, int rules, bool guard = true) { return make_geo_rt_b<uint64_t>(H, W, rules, guard); }
 
 // Bit-planes of a reference-layout grid (int8[H*W], row 0 = bottom) in the layout of g.
-inline void planes_from_grid(const GeoRT& g, const int8_t* grid, uint64_t plane[4]) {
+template <class B>
+inline void planes_from_grid(const GeoRTb<B>& g, const int8_t* grid, B plane[4]) {
     for (int i = 0; i < 4; ++i) plane[i] = 0;
     for (int y = 0; y < g.H; ++y)
         for (int x = 0; x < g.W; ++x)
-            for (int i = 0; i < 4; ++i) plane[i] |= (uint64_t)((grid[y * g.W + x] >> i) & 1) << (y * g.S + x);
+            for (int i = 0; i < 4; ++i) plane[i] |= (B)((grid[y * g.W + x] >> i) & 1) << (y * g.S + x);
 }
 
 template <int H_, int W_>
 struct GeoCT {
     static_assert(H_ * W_ <= 64 && W_ <= 8 && W_ >= 1 && H_ >= 1, "board must fit one 64-bit word");
+    typedef uint64_t bits;
     static constexpr int S_ = (H_ * (W_ + 1) <= 64) ? W_ + 1 : W_;
     static constexpr uint64_t col_mask(int x0, int x1) {
         uint64_t m = 0;
@@ -214,6 +239,13 @@ BGS_HD int kth_set_bit64(uint64_t m, int k) {
     return pos;
 }
 
+BGS_HD int kth_set_bit(uint64_t m, int k) { return kth_set_bit64(m, k); }
+BGS_HD int kth_set_bit(u128 m, int k) {
+    const uint64_t lo = (uint64_t)m;
+    const int c = popc64(lo);
+    return k < c ? kth_set_bit64(lo, k) : 64 + kth_set_bit64((uint64_t)(m >> 64), k - c);
+}
+
 // Outputs of one launch (any may be null) -- the per-game part of RolloutParams.
 struct LaneOut {
     uint8_t* moves;      // [n, max_plies, 2] pre-filled 0xFF
@@ -235,8 +267,9 @@ struct LaneOut {
 // ---------------------------------------------------------------------------------------------
 template <int NP, class G, int RULES_>
 struct MoveGen {
-    uint64_t b[NP];  // value bit-planes in the mover's orientation (read-only here)
-    uint64_t occ, src_left, sbit, occS, inter, open, expanded, pending, targets;
+    typedef typename G::bits B;
+    B b[NP];  // value bit-planes in the mover's orientation (read-only here)
+    B occ, src_left, sbit, occS, inter, open, expanded, pending, targets;
     int total, nsrc;
     bool probe;  // only "does the mover have any action?" (the blocked test): no target masks
     bool found, have, done;
@@ -245,18 +278,18 @@ struct MoveGen {
 
     // The movable pieces of the mover: the occupied row nearest to it (tests/test_bounce.py:43-48,60).
     // no_moves: an ended start position (no generation at all).
-    BGS_HD static uint64_t sources(const G& g, const uint64_t* planes, bool no_moves) {
-        uint64_t o = planes[0];
+    BGS_HD static B sources(const G& g, const B* planes, bool no_moves) {
+        B o = planes[0];
         BGS_UNROLL
         for (int i = 1; i < NP; ++i) o |= planes[i];
-        if (!o || no_moves) return 0ull;
-        const int row = g.row_of(ctz64(o));
-        return o & ((uint64_t)g.m_row0() << (row * g.s()));
+        if (!o || no_moves) return (B)0;
+        const int row = g.row_of(ctzb(o));
+        return o & ((B)g.m_row0() << (row * g.s()));
     }
 
     // planes b[] already set; src = sources(g, b, no_moves), possibly computed earlier.
-    BGS_HD void begin_with(const G& g, uint64_t src, bool prb) {
-        uint64_t o = b[0];
+    BGS_HD void begin_with(const G& g, B src, bool prb) {
+        B o = b[0];
         BGS_UNROLL
         for (int i = 1; i < NP; ++i) o |= b[i];
         occ = o;
@@ -269,16 +302,16 @@ struct MoveGen {
 
     // One iteration: at most one piece boundary, then one whole segment.  T[j * stride] receives the
     // target mask (mover-relative) of the j-th movable piece.  Sets done when nothing is left.
-    BGS_HD void iter(const G& g, uint64_t* T, int stride) {
+    BGS_HD void iter(const G& g, B* T, int stride) {
         const int rl = rules(g);
         if (pending == 0) {  // piece boundary
             if (have) {
-                const uint64_t tg = (rl & BGS_BOUNCE_ALLOW_NULL_MOVE) ? targets : (targets & ~sbit);
+                const B tg = (rl & BGS_BOUNCE_ALLOW_NULL_MOVE) ? targets : (targets & ~sbit);
                 if (probe) {
                     found = tg != 0;
                 } else {
                     T[nsrc * stride] = tg;
-                    total += popc64(tg);
+                    total += popcb(tg);
                     ++nsrc;
                 }
                 have = false;
@@ -287,7 +320,7 @@ struct MoveGen {
                 done = true;
                 return;
             }
-            sbit = src_left & (~src_left + 1ull);  // next movable piece, ascending relative column
+            sbit = src_left & (~src_left + (B)1);  // next movable piece, ascending relative column
             src_left ^= sbit;
             have = true;
             const int variant = rl & 3;
@@ -300,8 +333,8 @@ struct MoveGen {
         }
         // ---- segment setup: all unexpanded landing cells holding a piece of the same value as the
         // lowest one travel together
-        const uint64_t low = pending & (~pending + 1ull);
-        uint64_t S = pending;
+        const B low = pending & (~pending + (B)1);
+        B S = pending;
         int u = 0;
         BGS_UNROLL
         for (int i = 0; i < NP; ++i) {
@@ -314,14 +347,14 @@ struct MoveGen {
         // ---- u steps, every frontier cell at once; x* = cells entered by a forward / left / right
         // step (a left step may not follow a right step and vice versa; never backwards)
         const int W = g.s();  // one row up
-        uint64_t xf = S << W;
-        uint64_t xl = (S & g.m_not_left()) >> 1;
-        uint64_t xr = (S & g.m_not_right()) << 1;
+        B xf = S << W;
+        B xl = (S & g.m_not_left()) >> 1;
+        B xr = (S & g.m_not_right()) << 1;
         // intermediate cells: empty, not the far goal row
         auto advance = [&]() {
-            const uint64_t af = (xf | xl | xr) & inter;
-            const uint64_t al = (xf | xl) & inter & g.m_not_left();
-            const uint64_t ar = (xf | xr) & inter & g.m_not_right();
+            const B af = (xf | xl | xr) & inter;
+            const B al = (xf | xl) & inter & g.m_not_left();
+            const B ar = (xf | xr) & inter & g.m_not_right();
             xf = af << W;
             xl = al >> 1;
             xr = ar << 1;
@@ -338,7 +371,7 @@ struct MoveGen {
                 if (!advance()) break;
         }
         // last step: rest on an empty cell, or bounce off a piece
-        const uint64_t land = (xf | xl | xr) & open;
+        const B land = (xf | xl | xr) & open;
         targets |= land & ~occS;
         pending |= land & occS & ~expanded;
     }
@@ -353,13 +386,14 @@ enum Next { NEXT_OVER = 0, NEXT_MOVEGEN = 1, NEXT_PROBE = 2 };
 // ---------------------------------------------------------------------------------------------
 template <int NP, class G>
 struct Game {
-    uint64_t b[NP];  // value bit-planes, oriented for `orient`
+    typedef typename G::bits B;
+    B b[NP];  // value bit-planes, oriented for `orient`
     int t;           // plies played in this rollout
     int player;      // side to move
     int orient;      // whose orientation b[] is in
     int win;
 
-    BGS_HD uint64_t rot(const G& g, uint64_t x) const { return brev64(x) >> g.rot_sh(); }
+    BGS_HD B rot(const G& g, B x) const { return revb(x) >> g.rot_sh(); }
     BGS_HD void orient_for(const G& g, int pl) {
         if (orient != pl) {
             BGS_UNROLL
@@ -368,7 +402,7 @@ struct Game {
         }
     }
 
-    BGS_HD void begin_planes(const G& g, const uint64_t* plane0) {
+    BGS_HD void begin_planes(const G& g, const B* plane0) {
         BGS_UNROLL
         for (int i = 0; i < NP; ++i) b[i] = plane0[i];
         t = 0; player = 0; orient = 0; win = BGS_WINNER_DRAW;
@@ -383,7 +417,7 @@ struct Game {
             for (int x = 0; x < g.w(); ++x) {
                 const int v = grid[y * g.w() + x];
                 BGS_UNROLL
-                for (int i = 0; i < NP; ++i) b[i] |= (uint64_t)((v >> i) & 1) << (y * g.s() + x);
+                for (int i = 0; i < NP; ++i) b[i] |= (B)((v >> i) & 1) << (y * g.s() + x);
             }
         t = 0; player = pl & 1; orient = 0; win = winner_in;
         orient_for(g, player);
@@ -394,7 +428,7 @@ struct Game {
     // its target masks, rr the draw of ply t -- read only when a move is played).  On NEXT_MOVEGEN /
     // NEXT_PROBE the planes are oriented for the player whose moves must be generated next.
     template <class Draw>
-    BGS_HD Next transition(const G& g, const uint64_t* T, int stride, int total, bool probe, bool found,
+    BGS_HD Next transition(const G& g, const B* T, int stride, int total, bool probe, bool found,
                            int max_plies, uint8_t* moves_row, Draw draw) {
         if (probe) {  // `player` is blocked; the previous mover wins unless blocked too (draw)
             win = found ? 1 - player : BGS_WINNER_DRAW;
@@ -412,15 +446,15 @@ struct Game {
         int k = (int)mulhi32(draw(t), (uint32_t)total);
         if (player) k = total - 1 - k;  // canonical (absolute) order is the reverse of the rotated one
         // k-th action in ascending relative (source, target) order
-        uint64_t occ = b[0];
+        B occ = b[0];
         BGS_UNROLL
         for (int i = 1; i < NP; ++i) occ |= b[i];
-        const int base = g.row_of(ctz64(occ)) * g.s();
+        const int base = g.row_of(ctzb(occ)) * g.s();
         uint32_t sm = (uint32_t)(occ >> base) & g.m_row0();
-        uint64_t tm = T[0];
+        B tm = T[0];
         int j = 0;
         for (;;) {
-            const int c = popc64(tm);
+            const int c = popcb(tm);
             if (k < c) break;
             k -= c;
             ++j;
@@ -428,17 +462,17 @@ struct Game {
             tm = T[j * stride];
         }
         const int scell = base + ctz32(sm);
-        const int tcell = kth_set_bit64(tm, k);
+        const int tcell = kth_set_bit(tm, k);
         if (moves_row) {
             const int HW1 = g.h() * g.w() - 1, sp = pub_cell(g, scell), tp = pub_cell(g, tcell);
             moves_row[2 * t] = (uint8_t)(player ? HW1 - sp : sp);
             moves_row[2 * t + 1] = (uint8_t)(player ? HW1 - tp : tp);
         }
-        const uint64_t smask = 1ull << scell, tmask = 1ull << tcell;
+        const B smask = (B)1 << scell, tmask = (B)1 << tcell;
         BGS_UNROLL
         for (int i = 0; i < NP; ++i) {
             const bool has = (b[i] & smask) != 0;
-            b[i] = (b[i] & ~smask) | (has ? tmask : 0ull);
+            b[i] = (b[i] & ~smask) | (has ? tmask : (B)0);
         }
         ++t;
         const bool goal = (tmask & g.m_far()) != 0;
@@ -453,7 +487,7 @@ struct Game {
         const int c = orient ? (g.h() - 1 - y) * g.s() + (g.w() - 1 - x) : y * g.s() + x;
         int v = 0;
         BGS_UNROLL
-        for (int i = 0; i < NP; ++i) v |= (int)((b[i] >> c) & 1ull) << i;
+        for (int i = 0; i < NP; ++i) v |= (int)((b[i] >> c) & (B)1) << i;
         return v;
     }
 

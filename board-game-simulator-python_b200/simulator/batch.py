@@ -380,7 +380,7 @@ def _bounce_check(L, g):
     if g.min() < 0 or not L.bgs_bounce_supported(H, W, int(g.max())):
         raise RuntimeError(
             f"Bounce {H}x{W} with values up to {int(g.max())} is not supported by the CUDA kernels "
-            "(need H*W <= 64, W <= 8, values 0..15)"
+            "(need H*W <= 128, W <= 16, values 0..15)"
         )
 
 
@@ -473,12 +473,14 @@ class BounceBatch:
     def moves(self):
         """``(source_row int8[n], targets int64[n,W], count int32[n])``: bit ``y*W+x`` of
         ``targets[i, sx]`` is set iff ``(sx, source_row[i]) -> (x, y)`` is legal (reference
-        bounce.cpp:40-41).  ``count`` is -1 for a grid with values outside 0..15."""
+        bounce.cpp:40-41).  ``count`` is -1 for a grid with values outside 0..15.  Boards of more than
+        64 cells or more than 8 columns use two words per mask: ``targets int64[n,W,2]`` (low, high)."""
         torch = N.require_cuda()
         n, H, W = self.grid.shape
         dev = self.grid.device
         row = torch.empty(n, dtype=torch.int8, device=dev)
-        targets = torch.empty((n, W), dtype=torch.int64, device=dev)
+        wide = W > 8 or H * W > 64
+        targets = torch.empty((n, W, 2) if wide else (n, W), dtype=torch.int64, device=dev)
         count = torch.empty(n, dtype=torch.int32, device=dev)
         N.check(
             N.lib().bgs_bounce_moves(

@@ -116,7 +116,11 @@ class State:
             )
             _batch._bounce_check(N.lib(), self._grid)
             row, targets, count = b.moves()
-            masks = [int(m) & 0xFFFFFFFFFFFFFFFF for m in targets[0].cpu().tolist()]
+            t0 = targets[0].cpu().tolist()
+            if targets.dim() == 3:  # boards on 128-bit words: (low, high) per source column
+                masks = [(int(lo) & 0xFFFFFFFFFFFFFFFF) | ((int(hi) & 0xFFFFFFFFFFFFFFFF) << 64) for lo, hi in t0]
+            else:
+                masks = [int(m) & 0xFFFFFFFFFFFFFFFF for m in t0]
             self._moves = (int(row.item()), masks)
             if self._ended is None:
                 self._ended = int(count.item()) == 0

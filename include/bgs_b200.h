@@ -147,14 +147,16 @@ int bgs_connect_rollout_host(int device, int H, int W, int K, uint64_t n_games, 
 
 /* ----------------------------------------------------------------------------------------------
  * Bounce   --  replaces game::bounce::{Config,State,Action} as bound in bounce.cpp:24-53
- * Boards with H*W <= 64 cells, W <= 8, piece values 1..15.
+ * Boards with H*W <= 128 cells, W <= 16, piece values 1..15 (one 64-bit board word per value plane up to
+ * 64 cells and 8 columns, an unsigned __int128 beyond).
  * -------------------------------------------------------------------------------------------- */
 
 int bgs_bounce_supported(int H, int W, int max_value);
 
 /* State::get_actions / get_actions_at (bounce.cpp:40-41) for n states:
  * source_row int8[n]  row of the mover's movable pieces (-1: none / ended)
- * targets uint64[n,W] bit (y*W+x) of targets[i][sx] set <=> (sx, source_row) -> (x, y) is legal
+ * targets uint64[n,W] bit (y*W+x) of targets[i][sx] set <=> (sx, source_row) -> (x, y) is legal;
+ *         boards with W > 8 or H*W > 64 use two words per mask: uint64[n,W,2] (bits 0..63, bits 64..127)
  * count   optional int32[n] total number of legal actions. `ended` optional uint8[n]. */
 int bgs_bounce_moves(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
                      const uint8_t* ended, int8_t* source_row, uint64_t* targets, int32_t* count,

@@ -11,10 +11,10 @@
 using namespace bgs::bounce;
 
 template <int NP, class G, int RULES>
-static void play(const G& g, const uint64_t* plane0, const int8_t* start_grid, const int8_t* start_player,
+static void play(const G& g, const typename G::bits* plane0, const int8_t* start_grid, const int8_t* start_player,
                  const int8_t* start_winner, const uint8_t* start_ended, int max_plies, uint64_t n, uint64_t gid0,
                  uint64_t seed, const LaneOut& out, int64_t* stats) {
-    std::vector<uint64_t> T(8);
+    std::vector<typename G::bits> T(16);
     for (uint64_t idx = 0; idx < n; ++idx) {
         Game<NP, G> game;
         MoveGen<NP, G, RULES> mg;
@@ -58,15 +58,24 @@ extern "C" int bgs_lane_host_bounce_rollout(int mode, const int8_t* grid0, const
                                             uint64_t n, uint64_t gid0, uint64_t seed, uint8_t* moves,
                                             uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward,
                                             int64_t* stats) {
-    if (H < 1 || W < 1 || W > 8 || H * W > 64) return -1;
-    const GeoRT g = make_geo_rt(H, W, rules);
-    uint64_t plane0[4] = {0, 0, 0, 0};
+    if (H < 1 || W < 1 || W > 16 || H * W > 128) return -1;
     int maxv = 0;
-    if (grid0) {
+    if (grid0)
         for (int c = 0; c < H * W; ++c)
             if (grid0[c] > maxv) maxv = grid0[c];
-        planes_from_grid(g, grid0, plane0);
+    if (W > 8 || H * W > 64) {  // 128-bit board words
+        if (mode == 1) return -2;
+        const GeoRT128 g = make_geo_rt_b<u128>(H, W, rules);
+        u128 plane0[4] = {0, 0, 0, 0};
+        if (grid0) planes_from_grid(g, grid0, plane0);
+        if (moves) memset(moves, 0xFF, n * (size_t)max_plies * 2);
+        const LaneOut out{moves, length, winner, final_grid, reward};
+        play<4, GeoRT128, -1>(g, plane0, start_grid, start_player, start_winner, start_ended, max_plies, n, gid0, seed, out, stats);
+        return 0;
     }
+    const GeoRT g = make_geo_rt(H, W, rules);
+    uint64_t plane0[4] = {0, 0, 0, 0};
+    if (grid0) planes_from_grid(g, grid0, plane0);
     if (moves) memset(moves, 0xFF, n * (size_t)max_plies * 2);
     const LaneOut out{moves, length, winner, final_grid, reward};
     if (mode == 1) {

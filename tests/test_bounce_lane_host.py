@@ -116,3 +116,21 @@ def test_lane_rollouts_from_positions_equal_oracle(host, oracle):
         got = lane_rollout(host, None, n, cap, 40, 8, rules, start=(grids, player, winner_in, ended_in))
         ref = oracle.bounce_rollout_from(grids, player, winner_in, ended_in, max_plies=cap, gid0=40, seed=8, rules=rules)
         assert_same(got, ref, f"rules {rules}")
+
+
+def test_lane_large_boards_equal_oracle(host, oracle):
+    """Boards of more than 64 cells or more than 8 columns (up to 128 cells, 16 columns): the same state
+    machine on unsigned __int128 board words."""
+    rng = np.random.default_rng(11)
+    shapes = [(8, 9), (10, 10), (9, 12), (16, 8), (8, 16), (12, 10), (11, 11), (5, 16), (14, 9), (3, 13)]
+    for trial, (H, W) in enumerate(shapes):
+        assert H * W <= 128 and W <= 16 and (H * W > 64 or W > 8)
+        grid0 = np.zeros((H, W), dtype=np.int8)
+        maxv = int(rng.choice([3, 3, 5, 9, 15]))
+        cells = rng.random((H - 2, W)) < rng.uniform(0.1, 0.4)
+        grid0[1:-1][cells] = rng.integers(1, maxv + 1, size=int(cells.sum()))
+        rules = int(rng.choice([0, 0, 1, 2, 4, 6]))
+        n, cap = 200, 64
+        got = lane_rollout(host, grid0, n, cap, 5 * trial, trial, rules)
+        ref = oracle.bounce_rollout(grid0, n, max_plies=cap, gid0=5 * trial, seed=trial, rules=rules)
+        assert_same(got, ref, f"trial {trial} {H}x{W} rules {rules}")

@@ -225,6 +225,87 @@ def test_truncation_and_unsupported_boards():
     assert s["truncated"] > 0 and s["truncated"] == int((res.winner == -2).sum())
     assert int(res.length.max()) == 6
     with pytest.raises(RuntimeError):
-        batch.bounce_rollout(np.ones((9, 9), np.int8), 10)
+        batch.bounce_rollout(np.ones((12, 11), np.int8), 10)  # 132 cells
+    with pytest.raises(RuntimeError):
+        batch.bounce_rollout(np.ones((4, 17), np.int8), 10)  # 17 columns
     with pytest.raises(RuntimeError):
         batch.bounce_rollout(np.full((4, 4), 16, np.int8), 10)
+
+
+LARGE_SHAPES = [(8, 9), (10, 10), (9, 12), (16, 8), (8, 16), (12, 10), (11, 11), (5, 16)]
+
+
+def _large_grid(rng, H, W):
+    grid0 = np.zeros((H, W), dtype=np.int8)
+    maxv = int(rng.choice([3, 3, 5, 9, 15]))
+    cells = rng.random((H - 2, W)) < rng.uniform(0.1, 0.4)
+    grid0[1:-1][cells] = rng.integers(1, maxv + 1, size=int(cells.sum()))
+    return grid0
+
+
+def test_large_board_rollouts_equal_oracle(oracle):
+    """Boards of more than 64 cells / more than 8 columns (128-bit board words): rollouts and rollouts from
+    positions equal the oracle's."""
+    from simulator import batch
+
+    rng = np.random.default_rng(11)
+    for trial, (H, W) in enumerate(LARGE_SHAPES):
+        grid0 = _large_grid(rng, H, W)
+        rules = int(rng.choice([0, 0, 1, 2, 4, 6]))
+        n, cap = 300, 64
+        res = batch.bounce_rollout(grid0, n, seed=trial, game_id0=5 * trial, max_plies=cap, rules=rules,
+                                   moves=True, final_grid=True, reward=True)
+        ref = oracle.bounce_rollout(grid0, n, max_plies=cap, gid0=5 * trial, seed=trial, rules=rules)
+        for got, key in ((res.actions, "moves"), (res.winner, "winner"), (res.final_grid, "final_grid"),
+                         (res.reward, "reward"), (res.stats, "stats")):
+            np.testing.assert_array_equal(got.cpu().numpy(), ref[key], err_msg=f"{key} trial {trial} {H}x{W}")
+        np.testing.assert_array_equal(res.length.cpu().numpy().astype(np.uint16), ref["length"])
+
+
+def test_large_board_moves_and_step_equal_oracle(oracle):
+    """BounceBatch.moves / step and the object API on a 10x10 and an 8x16 board, against the oracle."""
+    from simulator import batch
+    from simulator.game.bounce import Config
+
+    rng = np.random.default_rng(5)
+    for H, W in ((10, 10), (8, 16), (9, 12)):
+        grid0 = _large_grid(rng, H, W)
+        n = 64
+        b = batch.BounceBatch.initial(grid0, n)
+        grids = [grid0.copy() for _ in range(n)]
+        players, ended = [0] * n, [False] * n
+        for ply in range(6):
+            row, targets, count = (t.cpu().numpy() for t in b.moves())
+            assert targets.shape == (n, W, 2)
+            mv = np.zeros((n, 4), dtype=np.int32)
+            for i in range(n):
+                ref = [tuple(a) for a in oracle.bounce_actions(grids[i], players[i], ended[i])]
+                got = []
+                for sx in range(W):
+                    m = (int(targets[i, sx, 0]) & (2**64 - 1)) | ((int(targets[i, sx, 1]) & (2**64 - 1)) << 64)
+                    for cell in range(H * W):
+                        if (m >> cell) & 1:
+                            got.append((sx, int(row[i]), cell % W, cell // W))
+                assert sorted(got) == sorted(ref), (H, W, ply, i)
+                assert int(count[i]) == len(ref)
+                if ref:
+                    mv[i] = ref[int(rng.integers(len(ref)))]
+                else:
+                    mv[i] = (0, 0, 0, 0)
+            nb, status = b.step(torch.from_numpy(mv))
+            st = status.cpu().numpy()
+            for i in range(n):
+                nxt = oracle.bounce_next(grids[i], players[i], ended[i], *[int(v) for v in mv[i]])
+                if nxt is None:
+                    assert st[i] == 1
+                    continue
+                assert st[i] == 0
+                grids[i], players[i], _, ended[i] = nxt
+            np.testing.assert_array_equal(nb.grid.cpu().numpy(), np.stack(grids))
+            np.testing.assert_array_equal(nb.player.cpu().numpy(), np.array(players, dtype=np.int8))
+            np.testing.assert_array_equal(nb.has_ended.cpu().numpy().astype(bool), np.array(ended))
+            b = nb
+        # the reference's object loop on the same board
+        state = Config(grid0).sample_initial_state()
+        ref = [tuple(a) for a in oracle.bounce_actions(grid0, 0, False)]
+        assert [(*a.source.tolist(), *a.target.tolist()) for a in state.actions] == ref

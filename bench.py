@@ -263,7 +263,8 @@ def other_configs(torch, batch, N, dev):
     out["bounce_default_9x6"] = {
         "games": n, "max_plies": 512, "ms_per_launch": ms, "env_steps_per_s": steps / ms * 1e3,
         "kernel": "bounce_rollout_lane_kernel<2, GeoCT<9,6>, 0>",
-        "frac_of_int_issue_peak_at_1400_ops_per_step": steps / ms * 1e3 * 1400 / (148 * 128 * 1.965e9),
+        "frac_of_int_issue_peak_at_1400_ops_per_step":
+            steps / ms * 1e3 * 1400 / (torch.cuda.get_device_properties(dev).multi_processor_count * 128 * SM_MAX_MHZ_FALLBACK * 1e6),
     }
     for cfg, bytes_per_game in (((8, 9, 5), 154), ((10, 12, 6), 250)):
         res = [None]
@@ -421,6 +422,8 @@ def run_b200(args):
     # the same path with separate length / winner arrays (2 bytes per game), pipelined and synchronous
     host2 = batch.HostRollout(CONFIG, n, depth=3)
     host2.run(SEED, 39_000 * total + rank * n)
+    for _ in host2.stream(SEED, 39_500 * total + rank * n * 4, 4):  # touch every buffer set before timing
+        pass
     t0 = time.perf_counter()
     un_steps = 0
     for st, _, _ in host2.stream(SEED, 40_000 * total + rank * n * args.steps, args.steps):

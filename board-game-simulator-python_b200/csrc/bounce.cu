@@ -5,8 +5,9 @@
 // Action::sample_next_state, State::has_ended / get_reward / get_grid).  The rules are restated in
 // SURVEY.md 4.4 from tests/test_bounce.py (the engine source is not part of the reference tree).
 //
-// Data layout: a board of H*W <= 64 cells is held in registers as NP bit-planes of the piece values
-// (plane b, bit cell = bit b of the value; NP = 2 for values <= 3, 4 for values <= 15).  Move
+// Data layout: a board is held in registers as NP bit-planes of the piece values (plane b, bit cell =
+// bit b of the value; NP = 2 for values <= 3, 4 for values <= 15); a plane is one 64-bit word for
+// boards of up to 64 cells and 8 columns, an unsigned __int128 up to 128 cells and 16 columns.  Move
 // generation is bit-parallel reachability, not a recursive search:
 //   * one "segment" of u steps keeps three frontier masks keyed by the last direction
 //     (forward / left / right) and advances all cells at once with a shift + mask per direction;

@@ -50,11 +50,15 @@ struct RolloutParams {
 };
 
 constexpr int ROLLOUT_THREADS = 128;
-constexpr int PLY_BATCH = 12;  // lanes that must be ready before the ply transition runs (8: 13.0 ms, 12: 12.45, 16: 12.6, 24: 13.3)
+// Lanes that must be ready before the ply transition runs, and move-generation segments per readiness
+// check (straight-line copies; a run-time loop is slower).  Frontier-propagation kernels: batch 8 / 12 /
+// 16 / 24 -> 13.0 / 12.45 / 12.6 / 13.3 ms, segments 1 / 2 -> 12.8 / 11.9 ms.  Table-driven kernel
+// (cheaper segments): (2,12) 11.0 ms, (3,12) 10.7, (4,12) 10.6, (3,14) 10.56, (3,16) 10.57, (4,14) 10.65.
+template <bool LUT> struct Tune { static constexpr int PLY_BATCH = LUT ? 14 : 12, SEGMENTS = LUT ? 3 : 2; };
 
 // ---------------------------------------------------------------------------------------------
 // rollout kernel, lane formulation: one game per lane (Game + MoveGen of bounce_lane.cuh in
-// registers).  Lanes whose move generation is complete wait until PLY_BATCH of them can run the
+// registers).  Lanes whose move generation is complete wait until Tune::PLY_BATCH of them can run the
 // ply transition together.
 // ---------------------------------------------------------------------------------------------
 template <int NP, class G, int RULES>
@@ -68,6 +72,12 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     __syncthreads();
     B* T = s_T + threadIdx.x;  // T[j * ROLLOUT_THREADS] = targets of the j-th movable piece
     const G g(grt);
+    constexpr bool USE_LUT = G::LUT && NP == 2;
+    __shared__ uint32_t s_lut[USE_LUT ? SEG_LUT_WORDS : 1];  // landing sets of a segment, [value][passable neighbours]
+    if (USE_LUT) {
+        for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[i] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
+        __syncthreads();
+    }
     B plane0[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) plane0[k] = make_bits<B>(p.plane0[k], p.plane0_hi[k]);
@@ -75,6 +85,7 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     Game<NP, G> gm;
     MoveGen<NP, G, RULES> mg;
     mg.done = false;
+    mg.lut = s_lut;
     uint32_t r[4] = {0, 0, 0, 0};
     uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
     unsigned long long acc_steps = 0;
@@ -102,7 +113,7 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
         const unsigned am = __ballot_sync(0xffffffffu, active);
         if (!am) break;
         const unsigned wm = __ballot_sync(0xffffffffu, active && mg.done);
-        if (__popc(wm) >= PLY_BATCH || wm == am) {
+        if (__popc(wm) >= Tune<USE_LUT>::PLY_BATCH || wm == am) {
             if (active && mg.done) {
                 uint8_t* row = p.moves ? p.moves + (size_t)idx * p.max_plies * 2ull : nullptr;
                 const Next nx = gm.transition(g, T, ROLLOUT_THREADS, mg.total, mg.probe, mg.found, p.max_plies, row,
@@ -132,7 +143,9 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
         }
         if (active && !mg.done) {
             mg.iter(g, T, ROLLOUT_THREADS);
-            if (!mg.done) mg.iter(g, T, ROLLOUT_THREADS);  // two segments per readiness check: 12.8 -> 11.9 ms
+#pragma unroll
+            for (int q = 1; q < Tune<USE_LUT>::SEGMENTS; ++q)  // straight-line copies (a run-time loop is slower)
+                if (!mg.done) mg.iter(g, T, ROLLOUT_THREADS);
         }
     }
     __syncwarp();
@@ -223,6 +236,7 @@ bounce_moves_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __res
     if (i >= n) return;
     B* T = s_T + threadIdx.x;
     StepGen<B> mg;
+    mg.lut = nullptr;
     const bool ok = planes_from_stage(s_stage[warp] + lane * HW, HW, mg.b);
     const bool over = (ended && ended[i]) || !ok;
     const int pl = player[i] & 1;
@@ -274,6 +288,7 @@ bounce_step_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __rest
         B* T = s_T + threadIdx.x;
         uint8_t* mine = s_stage[warp] + lane * HW;  // the new grid = the old one with two cells changed
         StepGen<B> mg;
+    mg.lut = nullptr;
         const bool ok = planes_from_stage(mine, HW, mg.b);
         int pl = player[i] & 1;
         const bool over = ended && ended[i];
@@ -465,7 +480,10 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     // per-game start grids may hold any value up to 15: use the 4-plane kernel
     if (wide) return launch_bounce_lane<4, GeoRT128, -1>(grt128, p, stream);
     if (maxv <= 3 && !start_grid) {
-        if (H == 9 && W == 6 && rules == 0) return launch_bounce_lane<2, GeoCT<9, 6>, 0>(grt, p, stream);
+        // the table-driven segments of the default-board kernel assume that the goal rows hold no piece
+        bool goal_rows_empty = true;
+        for (int x = 0; x < W; ++x) goal_rows_empty = goal_rows_empty && grid0[x] == 0 && grid0[(H - 1) * W + x] == 0;
+        if (H == 9 && W == 6 && rules == 0 && goal_rows_empty) return launch_bounce_lane<2, GeoCT<9, 6>, 0>(grt, p, stream);
         return launch_bounce_lane<2, GeoRT, -1>(grt, p, stream);
     }
     return launch_bounce_lane<4, GeoRT, -1>(grt, p, stream);

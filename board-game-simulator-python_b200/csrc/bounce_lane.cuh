@@ -126,6 +126,7 @@ template <class B>
 struct GeoRTb {
     typedef B bits;
     static constexpr int BITS = (int)sizeof(B) * 8;
+    static constexpr bool LUT = false;  // segments by frontier propagation
     int H, W, S, rules;
     int rot_shift;       // BITS-1 - (index of the last cell): rot180(x) = bit-reverse(x) >> rot_shift
     B board;             // the H*W valid cells
@@ -183,6 +184,8 @@ struct GeoCT {
     static_assert(H_ * W_ <= 64 && W_ <= 8 && W_ >= 1 && H_ >= 1, "board must fit one 64-bit word");
     typedef uint64_t bits;
     static constexpr int S_ = (H_ * (W_ + 1) <= 64) ? W_ + 1 : W_;
+    // segments by table look-up (seg_lut_entry): needs the guard column and a 32-bit landing window
+    static constexpr bool LUT = S_ > W_ && 3 * S_ + 3 <= 31;
     static constexpr uint64_t col_mask(int x0, int x1) {
         uint64_t m = 0;
         for (int y = 0; y < H_; ++y)
@@ -255,6 +258,43 @@ struct LaneOut {
     float* reward;       // [n, 2]
 };
 
+// ---------------------------------------------------------------------------------------------
+// Segment look-up table for small piece values (<= 3) on a layout with a guard column.
+// The cells a segment of u <= 3 steps from cell c can LAND on depend only on which of the 8 cells at
+// distance 1 and 2 ahead / beside c may be passed through: offsets {-2, -1, +1, +2, S-1, S, S+1, 2S}
+// <-> bits 0..7 of idx (1 = passable).  The entry is the landing set as a window mask, bit 3 = cell c
+// (offsets -3 .. 3S -> bits 0 .. 3S+3).  Same rules as the frontier propagation in MoveGen::iter:
+// forward / left / right, no left<->right reversal inside a segment, never backwards; cells off the
+// left / right edge are guard cells (never passable, never a landing cell once masked with the board).
+// ---------------------------------------------------------------------------------------------
+constexpr int SEG_LUT_WORDS = 4 * 256;  // [u][idx], u = 0 unused
+BGS_HD uint32_t seg_lut_entry(int S, int u, uint32_t idx) {
+    if (u < 1 || u > 3) return 0u;
+    const int off[8] = {-2, -1, 1, 2, S - 1, S, S + 1, 2 * S};
+    const int dir[3] = {S, -1, 1};  // forward, left, right
+    uint32_t mask = 0;
+    for (int d1 = 0; d1 < 3; ++d1) {
+        const int p1 = dir[d1];
+        if (u == 1) { mask |= 1u << (3 + p1); continue; }
+        bool ok1 = false;
+        for (int k = 0; k < 8; ++k) ok1 = ok1 || (off[k] == p1 && ((idx >> k) & 1u));
+        if (!ok1) continue;
+        for (int d2 = 0; d2 < 3; ++d2) {
+            if ((d1 == 1 && d2 == 2) || (d1 == 2 && d2 == 1)) continue;
+            const int p2 = p1 + dir[d2];
+            if (u == 2) { mask |= 1u << (3 + p2); continue; }
+            bool ok2 = false;
+            for (int k = 0; k < 8; ++k) ok2 = ok2 || (off[k] == p2 && ((idx >> k) & 1u));
+            if (!ok2) continue;
+            for (int d3 = 0; d3 < 3; ++d3) {
+                if ((d2 == 1 && d3 == 2) || (d2 == 2 && d3 == 1)) continue;
+                mask |= 1u << (3 + p2 + dir[d3]);
+            }
+        }
+    }
+    return mask;
+}
+
 #if defined(__CUDA_ARCH__)
 #define BGS_UNROLL _Pragma("unroll")
 #else
@@ -273,6 +313,7 @@ struct MoveGen {
     int total, nsrc;
     bool probe;  // only "does the mover have any action?" (the blocked test): no target masks
     bool found, have, done;
+    const uint32_t* lut;  // seg_lut_entry table [4][256] when G::LUT (shared memory in the kernel)
 
     BGS_HD int rules(const G& g) const { return RULES_ >= 0 ? RULES_ : g.rules; }
 
@@ -331,9 +372,24 @@ struct MoveGen {
             targets = 0;
             pending = sbit;  // the first segment = a "bounce" off the piece itself
         }
+        const B low = pending & (~pending + (B)1);
+        if (G::LUT && NP == 2) {
+            // ---- one pending cell per segment, its landing set from the table: no step loop, no
+            // dependence on the piece value, so every lane of the warp executes the same instructions
+            const int c = ctzb(low);
+            const int u = (int)((b[0] >> c) & (B)1) | ((int)((b[1] >> c) & (B)1) << 1);
+            pending ^= low;
+            expanded |= low;
+            const int S = g.s();
+            const uint32_t x = (uint32_t)(inter >> (c - 3));  // window around c, bit 3 = c (c >= S: no piece in row 0)
+            const uint32_t idx = ((x >> 1) & 3u) | ((x >> 2) & 0xCu) | ((x >> (S - 2)) & 0x70u) | ((x >> (2 * S - 4)) & 0x80u);
+            const B land = ((B)lut[u * 256 + (int)idx] << (c - 3)) & open;
+            targets |= land & ~occS;
+            pending |= land & occS & ~expanded;
+            return;
+        }
         // ---- segment setup: all unexpanded landing cells holding a piece of the same value as the
         // lowest one travel together
-        const B low = pending & (~pending + (B)1);
         B S = pending;
         int u = 0;
         BGS_UNROLL

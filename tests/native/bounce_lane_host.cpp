@@ -15,9 +15,12 @@ static void play(const G& g, const typename G::bits* plane0, const int8_t* start
                  const int8_t* start_winner, const uint8_t* start_ended, int max_plies, uint64_t n, uint64_t gid0,
                  uint64_t seed, const LaneOut& out, int64_t* stats) {
     std::vector<typename G::bits> T(16);
+    std::vector<uint32_t> lut(SEG_LUT_WORDS);
+    for (int i = 0; i < SEG_LUT_WORDS; ++i) lut[i] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
     for (uint64_t idx = 0; idx < n; ++idx) {
         Game<NP, G> game;
         MoveGen<NP, G, RULES> mg;
+        mg.lut = lut.data();
         bool no_moves = false;
         if (start_grid)
             no_moves = game.begin_grid(g, start_grid + idx * (size_t)(g.h() * g.w()), start_player[idx],

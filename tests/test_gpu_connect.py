@@ -368,7 +368,7 @@ def test_c_abi_argument_validation():
     assert L.bgs_connect_export(6, 7, 4, None, None, N.ptr(buf), None, st) == -1
     assert L.bgs_connect_rollout_from(6, 7, 4, 4, 0, 0, None, None, None, None, None, None, None, None, None, st) == -1
     assert L.bgs_bounce_rollout(None, 9, 6, 0, 64, 4, 0, 0, None, None, None, None, None, None, st) == -1
-    assert L.bgs_bounce_moves(9, 9, 0, 1, N.ptr(buf), N.ptr(buf), None, None, N.ptr(buf), None, st) == -2
+    assert L.bgs_bounce_moves(12, 11, 0, 1, N.ptr(buf), N.ptr(buf), None, None, N.ptr(buf), None, st) == -2
     # zero games is a no-op
     assert L.bgs_connect_rollout(6, 7, 4, 0, 0, 0, None, None, None, None, None, st) == 0
     torch.cuda.synchronize()

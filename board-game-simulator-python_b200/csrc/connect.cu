@@ -84,7 +84,8 @@ static DynGeo make_dyn_geo(int H, int W, int K) {
     DynGeo g;
     g.h = H; g.w = W; g.k = K;
     for (int i = 0; i < 4; ++i) {
-        const u128 m = valid_starts<u128>(H, W, K, dir_dc(i), dir_dr(i));
+        // boards beyond the bit-word limits only use H / W / K of this struct (byte-scanning kernels)
+        const u128 m = (H <= 15 && W <= 16 && H * W <= 128) ? valid_starts<u128>(H, W, K, dir_dc(i), dir_dr(i)) : (u128)0;
         g.v[i][0] = (uint64_t)m;
         g.v[i][1] = (uint64_t)(m >> 64);
     }
@@ -971,6 +972,115 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
 }
 
+// ---- byte-board kernel: boards beyond the bit-word limits (up to 255 cells, 32 columns) ----------
+// Correctness fallback, not a tuned path: the board is a per-thread byte array (local memory), the
+// playable columns a 32-bit mask, the k-in-a-row test a scan of the <= 8*(K-1) cells around the new
+// stone.  Same draws, same action order, same outputs as the bitboard kernels; `final_packed` receives
+// the grid bytes themselves (row 0 bottom, 0xFF empty), (H*W+7)/8 words per game.
+constexpr int BYTES_THREADS = 128;
+
+__device__ __forceinline__ int kth_set_bit32(uint32_t w, int k) {
+    int pos = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t low = w & ((1u << s) - 1u);
+        const int c = __popc(low);
+        if (k >= c) { k -= c; w >>= s; pos += s; } else { w = low; }
+    }
+    return pos;
+}
+
+__global__ void __launch_bounds__(BYTES_THREADS)
+connect_rollout_bytes_kernel(int H, int W, int K, const RolloutParams p) {
+    __shared__ unsigned int s_hist[HIST_BINS];
+    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int HW = H * W;
+    const int PB = ((HW + 7) / 8) * 8;  // bytes of one final_packed record
+    const uint32_t all = W >= 32 ? 0xFFFFFFFFu : ((1u << W) - 1u);
+    uint8_t board[256];
+    uint8_t hts[32];
+    uint32_t legal = 0, t = 0, idx = 0, pool_next = 0, pool_cnt = 0;
+    int res = BGS_WINNER_DRAW;
+    bool alive = false, retired = false;
+    uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0;
+    unsigned long long acc_steps = 0;
+    for (;;) {
+        if (!alive && t != 0) {  // retire the finished game
+            p.length[idx] = (uint8_t)t;
+            p.winner[idx] = (int8_t)res;
+            if (p.final_packed) {
+                uint8_t* out = reinterpret_cast<uint8_t*>(p.final_packed) + (size_t)idx * PB;
+                for (int c = 0; c < HW; ++c) out[c] = board[c];
+            }
+            acc_w0 += (res == 0); acc_w1 += (res == 1); acc_dr += (res < 0);
+            acc_steps += t;
+            atomicAdd(&s_hist[hist_bin((int)t)], 1u);
+            t = 0;
+        }
+        const bool need = !alive && !retired;
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
+            if (need) {
+                if (id < p.n_games) {
+                    idx = id;
+                    for (int c = 0; c < HW; ++c) board[c] = 0xFFu;
+                    for (int c = 0; c < W; ++c) hts[c] = 0;
+                    legal = all; res = BGS_WINNER_DRAW; alive = true;
+                } else {
+                    retired = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+        const unsigned long long gid = p.game_id0 + idx;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+        uint8_t* act_row = p.actions ? p.actions + (size_t)idx * HW : nullptr;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            if (!alive) break;
+            const int col = kth_set_bit32(legal, (int)__umulhi(r[j], (uint32_t)__popc(legal)));
+            const int row = hts[col];
+            const uint8_t pl = (uint8_t)(t & 1u);
+            board[row * W + col] = pl;
+            hts[col] = (uint8_t)(row + 1);
+            if (row + 1 == H) legal &= ~(1u << col);
+            if (act_row) act_row[t] = (uint8_t)col;
+            ++t;
+            auto run = [&](int dr, int dc) {
+                int cnt = 0, rr = row + dr, cc = col + dc;
+                while (cnt < K - 1 && rr >= 0 && rr < H && cc >= 0 && cc < W && board[rr * W + cc] == pl) {
+                    ++cnt; rr += dr; cc += dc;
+                }
+                return cnt;
+            };
+            if (1 + run(0, 1) + run(0, -1) >= K || 1 + run(-1, 0) >= K || 1 + run(1, 1) + run(-1, -1) >= K ||
+                1 + run(1, -1) + run(-1, 1) >= K) {
+                res = pl;
+                alive = false;
+            } else if (legal == 0u) {
+                alive = false;  // full board: draw
+            }
+        }
+    }
+    __syncwarp();
+    if (p.stats) {
+        const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr), st = warp_sum(acc_steps);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr);
+            atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
+            atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
+            atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
+            atomicAdd(&p.stats[BGS_STAT_STEPS], st);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&p.stats[BGS_STAT_HIST0 + i], (unsigned long long)s_hist[i]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // export: per-game records -> the reference's row layouts.  HBM-bound.
 //   MODE_GRID    packed boards (16 / 32 B per game)      -> int8[n,H,W] grids (-1 / 0 / 1)
@@ -1545,8 +1655,13 @@ connect_query_kernel(int H, int W, unsigned long long n, const int8_t* __restric
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static bool supported(int H, int W, int K) {
+// boards the bit-word kernels cover
+static bool bitboard_supported(int H, int W, int K) {
     return H >= 1 && W >= 1 && K >= 1 && H <= 15 && W <= 16 && H * W <= 128;
+}
+// ... and the byte-board fallback beyond them (length is a uint8, the playable columns a 32-bit mask)
+static bool supported(int H, int W, int K) {
+    return H >= 1 && W >= 1 && K >= 1 && W <= 32 && H * W <= 255;
 }
 
 template <typename Kern, typename... Args>
@@ -1680,7 +1795,10 @@ using namespace bgs::connect;
 
 extern "C" int bgs_connect_supported(int H, int W, int K) { return supported(H, W, K) ? 1 : 0; }
 
-extern "C" int bgs_connect_packed_words(int H, int W) { return 2 * (H * W <= 64 ? 1 : 2); }
+extern "C" int bgs_connect_packed_words(int H, int W) {
+    if (!bitboard_supported(H, W, 1)) return (H * W + 7) / 8;  // byte boards: the grid itself, padded to 8 bytes
+    return 2 * (H * W <= 64 ? 1 : 2);
+}
 
 // Set BGS_CONNECT_GENERIC=1 to force the generic kernel on the 6x7x4 board (A/B measurements).
 static bool force_generic() {
@@ -1714,7 +1832,9 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
     unsigned int* counter = nullptr;
     int rc = next_counter(&counter);
     cudaError_t e = cudaSuccess;
-    const int act_mode = actions ? actions_mode(H, W) : 0;
+    const bool bytes_board = !bitboard_supported(H, W, K);
+    if (bytes_board && start) return set_error(BGS_EUNSUPPORTED, "connect: rollouts from positions need a board of at most 128 cells, 16 columns, 15 rows (%dx%d)", H, W);
+    const int act_mode = actions ? (bytes_board ? 1 : actions_mode(H, W)) : 0;
     if (rc == BGS_OK && act_mode == 1) {
         e = cudaMemsetAsync(actions, 0xFF, n_games * HW, stream);
         if (e != cudaSuccess) rc = cuda_error(e, "cudaMemsetAsync");
@@ -1735,7 +1855,15 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
         p.start = start ? start + off * start_words((int)HW) : nullptr;
         e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) { rc = cuda_error(e, "cudaMemsetAsync"); break; }
-        if (H == 6 && W == 7 && K == 4 && force_lines() && !start) rc = launch_rollout_lines<6, 7, 4>(p, stream);
+        if (bytes_board) {
+            const unsigned long long want = ((unsigned long long)p.n_games + BYTES_THREADS - 1) / BYTES_THREADS;
+            unsigned long long blocks = (unsigned long long)sm_count() * 8;
+            if (want < blocks) blocks = want;
+            connect_rollout_bytes_kernel<<<(unsigned)blocks, BYTES_THREADS, 0, stream>>>(H, W, K, p);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) rc = cuda_error(e, "connect_rollout_bytes_kernel");
+        }
+        else if (H == 6 && W == 7 && K == 4 && force_lines() && !start) rc = launch_rollout_lines<6, 7, 4>(p, stream);
         else if (H == 6 && W == 7 && K == 4 && !force_generic() && !start) rc = launch_rollout_lut<6, 7, 4>(p, stream);
         else if (H == 6 && W == 7 && K == 4) rc = launch_rollout(StaticGeo<6, 7, 4>(), p, stream);
         else if (H == 8 && W == 9 && K == 5 && !force_generic() && !start) rc = launch_rollout_lines<8, 9, 5>(p, stream);
@@ -1762,7 +1890,7 @@ extern "C" int bgs_connect_rollout_from(int H, int W, int K, uint64_t n_games, u
                                         const int8_t* grid, const int8_t* player, const int8_t* winner_in,
                                         uint64_t* workspace, uint8_t* actions, uint8_t* length, int8_t* winner,
                                         uint64_t* final_packed, int64_t* stats, void* stream_) {
-    if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
+    if (!bitboard_supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
     if (!grid || !player || !workspace) return set_error(BGS_EINVAL, "connect_rollout_from: null required pointer");
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
@@ -1787,7 +1915,10 @@ extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* pack
     const int sms = sm_count();
     if (grid) {
         if (!packed) return set_error(BGS_EINVAL, "connect_export: grid requested without packed boards");
-        if (int rc = launch_export_rows<MODE_GRID>(H, W, n, packed, nullptr, reinterpret_cast<uint8_t*>(grid), stream))
+        if (!bitboard_supported(H, W, 1)) {  // byte boards: the record is the grid, padded to 8 bytes
+            BGS_CUDA_TRY(cudaMemcpy2DAsync(grid, (size_t)H * W, packed, (size_t)bgs_connect_packed_words(H, W) * 8,
+                                           (size_t)H * W, n, cudaMemcpyDeviceToDevice, stream));
+        } else if (int rc = launch_export_rows<MODE_GRID>(H, W, n, packed, nullptr, reinterpret_cast<uint8_t*>(grid), stream))
             return rc;
     }
     if (reward) {
@@ -1803,7 +1934,7 @@ extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* pack
 
 extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, const uint8_t* actions,
                                            const uint8_t* length, int8_t* grids, void* stream_) {
-    if (!supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
+    if (!bitboard_supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
     if (!actions || !length || !grids) return set_error(BGS_EINVAL, "connect_trajectory_grids: null pointer");
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
@@ -1854,6 +1985,8 @@ extern "C" int bgs_connect_step(int H, int W, int K, uint64_t n, const int8_t* g
     if (n == 0) return BGS_OK;
     const DynGeo g = make_dyn_geo(H, W, K);
     const size_t smem = (size_t)(STEP_THREADS / 32) * 32 * H * W;
+    if (smem > 48 * 1024)  // boards of more than 192 cells: opt in to the large carve-out
+        BGS_CUDA_TRY(cudaFuncSetAttribute(connect_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
     const unsigned long long cap = (unsigned long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;

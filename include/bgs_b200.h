@@ -69,12 +69,17 @@ int bgs_device_count(void);
  * Connect-k   --  replaces game::connect::{Config,State,Action} as bound in connect.cpp:24-54
  * -------------------------------------------------------------------------------------------- */
 
-/* 1 if (H, W, K) is covered by the kernels (H*W <= 128, H <= 15, W <= 16, K >= 1), else 0. */
+/* 1 if (H, W, K) is covered by the kernels, else 0: K >= 1 and H*W <= 255, W <= 32.  Boards with
+ * H*W <= 128, H <= 15, W <= 16 run on bit-word kernels (the tuned path); larger ones on a byte-board
+ * fallback that supports bgs_connect_rollout / _rollout_host / _export / _step / _query but not
+ * bgs_connect_rollout_from and bgs_connect_trajectory_grids (BGS_EUNSUPPORTED). */
 int bgs_connect_supported(int H, int W, int K);
 
 /* Number of uint64 words per game in the packed board format used by *_packed / export:
  * [stones of player 0 | stones of player 1], each (H*W <= 64 ? 1 : 2) words, little-endian word order,
- * bit index of cell (row, col) = (H-1-row)*W + col (the top row occupies bits 0..W-1). */
+ * bit index of cell (row, col) = (H-1-row)*W + col (the top row occupies bits 0..W-1).
+ * Byte-board fallback: the record is the int8 grid itself (row 0 = bottom, -1 empty), padded to a
+ * multiple of 8 bytes: (H*W + 7) / 8 words. */
 int bgs_connect_packed_words(int H, int W);
 
 /* The whole rollout loop of README.md:49-72 for n_games independent games from the empty board:

@@ -61,13 +61,15 @@ def test_version_and_argument_validation(lib):
     assert L.bgs_version() == 100
     assert L.bgs_connect_supported(6, 7, 4) == 1
     assert L.bgs_connect_supported(8, 9, 5) == 1 and L.bgs_connect_supported(10, 12, 6) == 1
-    assert L.bgs_connect_supported(16, 7, 4) == 0 and L.bgs_connect_supported(12, 12, 4) == 0
+    assert L.bgs_connect_supported(16, 7, 4) == 1 and L.bgs_connect_supported(12, 12, 4) == 1  # byte-board fallback
+    assert L.bgs_connect_supported(16, 16, 4) == 0 and L.bgs_connect_supported(4, 33, 4) == 0  # > 255 cells, > 32 columns
     assert L.bgs_connect_packed_words(6, 7) == 2 and L.bgs_connect_packed_words(10, 12) == 4
+    assert L.bgs_connect_packed_words(12, 12) == 18  # byte boards: the grid itself, padded to 8 bytes
     assert L.bgs_bounce_supported(9, 6, 3) == 1 and L.bgs_bounce_supported(9, 9, 3) == 1  # 81 cells: 128-bit words
     assert L.bgs_bounce_supported(12, 11, 3) == 0 and L.bgs_bounce_supported(5, 17, 3) == 0  # > 128 cells, > 16 columns
     assert L.bgs_bounce_supported(9, 6, 16) == 0
     # unsupported configurations are reported through the status code + bgs_last_error, never a crash
-    rc = L.bgs_connect_rollout(20, 20, 4, 10, 0, 0, None, None, None, None, None, None)
+    rc = L.bgs_connect_rollout(20, 20, 4, 10, 0, 0, None, None, None, None, None, None)  # 400 cells
     assert rc == -2 and "unsupported" in N.last_error()
 
 

@@ -360,7 +360,10 @@ def test_c_abi_argument_validation():
     assert L.bgs_connect_rollout(6, 7, 4, 8, 0, 0, N.ptr(buf), None, None, None, None, st) == -1
     assert "length" in N.last_error()
     # unsupported boards
-    assert L.bgs_connect_rollout(16, 16, 4, 8, 0, 0, None, None, None, None, None, st) == -2
+    assert L.bgs_connect_rollout(16, 16, 4, 8, 0, 0, None, None, None, None, None, st) == -2  # 256 cells
+    assert L.bgs_connect_rollout(4, 33, 4, 8, 0, 0, None, None, None, None, None, st) == -2  # 33 columns
+    assert L.bgs_connect_rollout_from(12, 12, 4, 4, 0, 0, N.ptr(buf), N.ptr(buf), None, N.ptr(buf), None, None, None, None, None, st) == -2
+    assert L.bgs_connect_trajectory_grids(12, 12, 1, N.ptr(buf), N.ptr(buf), N.ptr(buf), st) == -2
     assert L.bgs_connect_step(0, 7, 4, 1, *([N.ptr(buf)] * 12), st) == -2
     # missing required pointers
     assert L.bgs_connect_step(6, 7, 4, 1, None, None, None, None, None, None, None, None, None, None, None, st) == -1
@@ -453,3 +456,56 @@ def test_dlpack_export():
     cap = torch.utils.dlpack.to_dlpack(res.actions)
     back = torch.utils.dlpack.from_dlpack(cap)
     assert back.data_ptr() == res.actions.data_ptr() and back.shape == (1000, 42)
+
+
+@pytest.mark.parametrize("cfg", [(12, 12, 5), (15, 15, 5), (16, 7, 4), (5, 32, 4), (17, 15, 6), (3, 20, 3), (51, 5, 4)])
+def test_boards_beyond_the_bitboard_limits_equal_oracle(oracle, cfg):
+    """More than 128 cells / 16 columns / 15 rows (up to 255 cells, 32 columns): the byte-board fallback
+    kernel gives the oracle's trajectories, lengths, winners, final grids, rewards and statistics."""
+    from simulator import batch
+
+    H, W, K = cfg
+    n = 700
+    res = batch.connect_rollout(cfg, n, seed=5, game_id0=31, per_game=True, actions=True, final_grid=True, reward=True)
+    torch.cuda.synchronize()
+    ref = oracle.connect_rollout(H, W, K, n, gid0=31, seed=5)
+    for got, key in ((res.actions, "actions"), (res.length, "length"), (res.winner, "winner"),
+                     (res.final_grid, "final_grid"), (res.reward, "reward"), (res.stats, "stats")):
+        np.testing.assert_array_equal(got.cpu().numpy(), ref[key], err_msg=f"{key} {cfg}")
+    # no trajectory requested: lengths / winners / statistics only
+    res2 = batch.connect_rollout(cfg, n, seed=5, game_id0=31, per_game=True)
+    np.testing.assert_array_equal(res2.length.cpu().numpy(), ref["length"])
+    np.testing.assert_array_equal(res2.stats.cpu().numpy(), ref["stats"])
+
+
+def test_large_board_step_and_object_api(oracle):
+    """ConnectBatch.step / query and the reference's object loop on a 15x15x5 board (225 cells)."""
+    from simulator import batch
+    from simulator.game.connect import Config
+
+    cfg = (15, 15, 5)
+    H, W, K = cfg
+    n = 256
+    rng = np.random.default_rng(2)
+    b = batch.ConnectBatch.initial(cfg, n)
+    grids = [np.full((H, W), -1, np.int8) for _ in range(n)]
+    players, winners = [0] * n, [-1] * n
+    for ply in range(40):
+        acts = rng.integers(-1, W + 1, size=n).astype(np.int32)
+        nb, status = b.step(torch.from_numpy(acts).cuda())
+        st = status.cpu().numpy()
+        for i in range(n):
+            nxt = oracle.connect_next(grids[i], K, players[i], winners[i], int(acts[i])) if 0 <= acts[i] < W else None
+            if nxt is None:
+                assert st[i] == 1, (ply, i)
+                continue
+            assert st[i] == 0, (ply, i)
+            grids[i], players[i], winners[i] = nxt
+        np.testing.assert_array_equal(nb.grid.cpu().numpy(), np.stack(grids))
+        np.testing.assert_array_equal(nb.winner.cpu().numpy(), np.array(winners, dtype=np.int8))
+        b = nb
+    state = Config(*cfg).sample_initial_state()
+    for col in (7, 7, 8, 7):
+        state = state.action_at(col).sample_next_state()
+    assert state.grid[0, 7] == 0 and state.grid[1, 7] == 1 and state.grid[0, 8] == 0 and state.grid[2, 7] == 1
+    assert len(state.actions) == W and not state.has_ended

@@ -72,9 +72,11 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     __syncthreads();
     B* T = s_T + threadIdx.x;  // T[j * ROLLOUT_THREADS] = targets of the j-th movable piece
     const G g(grt);
-    constexpr bool USE_LUT = G::LUT && NP == 2;
-    __shared__ uint32_t s_lut[USE_LUT ? SEG_LUT_WORDS : 1];  // landing sets of a segment, [value][passable neighbours]
-    if (USE_LUT) {
+    constexpr bool USE_LUT = G::LUT && NP == 2;                  // compile-time: the default board
+    constexpr bool MAY_LUT = NP == 2 && sizeof(B) == 8;          // run-time: any small board with a guard column
+    const bool lut_on = USE_LUT || (MAY_LUT && g.lut_rt());
+    __shared__ uint32_t s_lut[MAY_LUT ? SEG_LUT_WORDS : 1];  // landing sets of a segment, [value][passable neighbours]
+    if (lut_on) {
         for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[i] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
         __syncthreads();
     }
@@ -85,7 +87,7 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     Game<NP, G> gm;
     MoveGen<NP, G, RULES> mg;
     mg.done = false;
-    mg.lut = s_lut;
+    mg.lut = lut_on ? s_lut : nullptr;
     uint32_t r[4] = {0, 0, 0, 0};
     uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
     unsigned long long acc_steps = 0;
@@ -480,11 +482,13 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     // per-game start grids may hold any value up to 15: use the 4-plane kernel
     if (wide) return launch_bounce_lane<4, GeoRT128, -1>(grt128, p, stream);
     if (maxv <= 3 && !start_grid) {
-        // the table-driven segments of the default-board kernel assume that the goal rows hold no piece
+        // the table-driven segments assume that the goal rows hold no piece (a window never starts below cell 3)
         bool goal_rows_empty = true;
         for (int x = 0; x < W; ++x) goal_rows_empty = goal_rows_empty && grid0[x] == 0 && grid0[(H - 1) * W + x] == 0;
         if (H == 9 && W == 6 && rules == 0 && goal_rows_empty) return launch_bounce_lane<2, GeoCT<9, 6>, 0>(grt, p, stream);
-        return launch_bounce_lane<2, GeoRT, -1>(grt, p, stream);
+        GeoRT g2 = grt;
+        g2.lut_ok = g2.lut_ok && goal_rows_empty;
+        return launch_bounce_lane<2, GeoRT, -1>(g2, p, stream);
     }
     return launch_bounce_lane<4, GeoRT, -1>(grt, p, stream);
 }

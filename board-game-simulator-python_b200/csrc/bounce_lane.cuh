@@ -126,7 +126,8 @@ template <class B>
 struct GeoRTb {
     typedef B bits;
     static constexpr int BITS = (int)sizeof(B) * 8;
-    static constexpr bool LUT = false;  // segments by frontier propagation
+    static constexpr bool LUT = false;  // no compile-time guarantee; lut_ok decides at run time
+    bool lut_ok;         // table-driven segments possible: guard column, landing window within 32 bits
     int H, W, S, rules;
     int rot_shift;       // BITS-1 - (index of the last cell): rot180(x) = bit-reverse(x) >> rot_shift
     B board;             // the H*W valid cells
@@ -145,6 +146,7 @@ struct GeoRTb {
     BGS_HD B m_far() const { return far; }
     BGS_HD uint32_t m_row0() const { return row0; }
     BGS_HD int row_of(int cell) const { return (int)(((uint32_t)cell * inv_s) >> 16); }
+    BGS_HD bool lut_rt() const { return lut_ok; }
 };
 typedef GeoRTb<uint64_t> GeoRT;
 typedef GeoRTb<u128> GeoRT128;
@@ -166,6 +168,10 @@ inline GeoRTb<B> make_geo_rt_b(int H, int W, int rules, bool guard = true) {
     g.row0 = (uint32_t)((1ull << W) - 1ull);
     g.far = (B)g.row0 << ((H - 1) * g.S);
     g.inv_s = (65536u + (uint32_t)g.S - 1u) / (uint32_t)g.S;
+    // table-driven segments (seg_lut_entry): 64-bit words, a guard column, the landing window of a 3-step
+    // segment within 32 bits.  The caller clears the flag when the goal rows hold pieces or values exceed 3.
+    // (S >= 3: the lowest piece cell is S, and the window starts 3 cells below the piece.)
+    g.lut_ok = GeoRTb<B>::BITS == 64 && g.S > W && g.S >= 3 && 3 * g.S + 3 <= 31;
     return g;
 }
 inline GeoRT make_geo_rt(int H, int W, int rules, bool guard = true) { return make_geo_rt_b<uint64_t>(H, W, rules, guard); }
@@ -185,7 +191,7 @@ struct GeoCT {
     typedef uint64_t bits;
     static constexpr int S_ = (H_ * (W_ + 1) <= 64) ? W_ + 1 : W_;
     // segments by table look-up (seg_lut_entry): needs the guard column and a 32-bit landing window
-    static constexpr bool LUT = S_ > W_ && 3 * S_ + 3 <= 31;
+    static constexpr bool LUT = S_ > W_ && S_ >= 3 && 3 * S_ + 3 <= 31;
     static constexpr uint64_t col_mask(int x0, int x1) {
         uint64_t m = 0;
         for (int y = 0; y < H_; ++y)
@@ -209,6 +215,7 @@ struct GeoCT {
     BGS_HD uint64_t m_far() const { return kFar; }
     BGS_HD uint32_t m_row0() const { return kRow0; }
     BGS_HD int row_of(int cell) const { return cell / S_; }
+    BGS_HD bool lut_rt() const { return LUT; }
 };
 
 // public cell index y*W + x of internal cell y*S + x
@@ -373,7 +380,7 @@ struct MoveGen {
             pending = sbit;  // the first segment = a "bounce" off the piece itself
         }
         const B low = pending & (~pending + (B)1);
-        if (G::LUT && NP == 2) {
+        if (NP == 2 && sizeof(B) == 8 && (G::LUT || (g.lut_rt() && lut != nullptr))) {
             // ---- one pending cell per segment, its landing set from the table: no step loop, no
             // dependence on the piece value, so every lane of the warp executes the same instructions
             const int c = ctzb(low);

@@ -76,7 +76,12 @@ extern "C" int bgs_lane_host_bounce_rollout(int mode, const int8_t* grid0, const
         play<4, GeoRT128, -1>(g, plane0, start_grid, start_player, start_winner, start_ended, max_plies, n, gid0, seed, out, stats);
         return 0;
     }
-    const GeoRT g = make_geo_rt(H, W, rules);
+    GeoRT g = make_geo_rt(H, W, rules);
+    // table-driven segments only when the goal rows hold no piece (as the kernel's host code decides)
+    bool goal_rows_empty = grid0 != nullptr;
+    if (grid0)
+        for (int x = 0; x < W; ++x) goal_rows_empty = goal_rows_empty && grid0[x] == 0 && grid0[(H - 1) * W + x] == 0;
+    g.lut_ok = g.lut_ok && goal_rows_empty;
     uint64_t plane0[4] = {0, 0, 0, 0};
     if (grid0) planes_from_grid(g, grid0, plane0);
     if (moves) memset(moves, 0xFF, n * (size_t)max_plies * 2);

@@ -262,7 +262,7 @@ def other_configs(torch, batch, N, dev):
     ms, steps = timed(lambda i: batch.bounce_rollout(grid, n, SEED, i * n, max_plies=512, stats=stats), stats)
     out["bounce_default_9x6"] = {
         "games": n, "max_plies": 512, "ms_per_launch": ms, "env_steps_per_s": steps / ms * 1e3,
-        "kernel": "bounce_rollout_lane_kernel<2, GeoCT<9,6>, 0>",
+        "kernel": "bounce_rollout_slots_kernel<2, GeoCT<9,6>, 0, 64>",
         "frac_of_int_issue_peak_at_1400_ops_per_step":
             steps / ms * 1e3 * 1400 / (torch.cuda.get_device_properties(dev).multi_processor_count * 128 * SM_MAX_MHZ_FALLBACK * 1e6),
     }

@@ -47,6 +47,7 @@ struct RolloutParams {
     const int8_t* start_player;   // [n]
     const int8_t* start_winner;   // [n] or null
     const uint8_t* start_ended;   // [n] or null
+    int ply_batch, idle_batch;    // slot kernel: waiting slots / idle lanes that trigger the transition pass
 };
 
 constexpr int ROLLOUT_THREADS = 128;
@@ -57,8 +58,8 @@ constexpr int ROLLOUT_THREADS = 128;
 template <bool LUT> struct Tune { static constexpr int PLY_BATCH = LUT ? 14 : 12, SEGMENTS = LUT ? 3 : 2; };
 
 // ---------------------------------------------------------------------------------------------
-// rollout kernel, lane formulation: one game per lane (Game + MoveGen of bounce_lane.cuh in
-// registers).  Lanes whose move generation is complete wait until Tune::PLY_BATCH of them can run the
+// rollout kernel, lane formulation (used for boards on 128-bit words): one game per lane (Game +
+// MoveGen of bounce_lane.cuh in registers).  Lanes whose move generation is complete wait until Tune::PLY_BATCH of them can run the
 // ply transition together.
 // ---------------------------------------------------------------------------------------------
 template <int NP, class G, int RULES>
@@ -156,6 +157,226 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
         const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
         const unsigned long long tr = warp_sum(acc_tr), st = warp_sum(acc_steps);
         if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr + tr);
+            atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
+            atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
+            atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
+            atomicAdd(&p.stats[BGS_STAT_TRUNCATED], tr);
+            atomicAdd(&p.stats[BGS_STAT_STEPS], st);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&p.stats[BGS_STAT_HIST0 + i], (unsigned long long)s_hist[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rollout kernel, slot formulation.
+//
+// A warp owns M = 64 game SLOTS in shared memory.  A game alternates between two kinds of work:
+//   * its move generation (MoveGen): ~9 segments, the number varies from 1 to 40 between positions;
+//   * its ply transition (Game::transition): ~300 instructions, once per ply.
+// Lanes are not tied to games.  A lane without work takes any slot from the warp's READY ring and runs
+// that position's move generation; when it is done the slot goes to the WAITING ring and the lane
+// takes the next ready slot.  When 32 slots are waiting (or lanes starve), the whole warp runs the
+// transition for up to 32 of them at once and they become ready again (a finished game's slot is
+// refilled from the global game counter).  With M - 32 >= the batch size no lane ever idles and the
+// transition always runs on full warps; the rings are warp-private, their heads and counts are
+// warp-uniform registers derived from ballots, so there are no atomics besides the game counter (one
+// per 64 games) and the final statistics.
+// ---------------------------------------------------------------------------------------------
+template <int NP, int M, int MAXSRC>
+struct WarpSlots {
+    uint64_t b[NP][M];      // planes, oriented for the player whose moves are generated next
+    uint64_t src[M];        // that player's movable pieces (MoveGen::sources), 0 for an ended start position
+    uint64_t T[MAXSRC][M];  // target masks of the j-th movable piece
+    uint32_t r[4][M];       // Philox block of plies 4*(t>>2) .. +3
+    uint32_t idx[M];        // game index in [0, n)
+    uint32_t meta[M];       // t:16 | total:9 | player | orient | probe | found | win+2:2
+    uint8_t rq[64];         // READY ring (slot ids)
+    uint8_t wq[64];         // WAITING ring
+};
+
+constexpr uint32_t META_TOTAL_SHIFT = 16, META_PLAYER = 1u << 25, META_ORIENT = 1u << 26, META_PROBE = 1u << 27,
+                   META_FOUND = 1u << 28, META_WIN_SHIFT = 29;
+
+template <int NP, class G, int RULES, int M>
+__global__ void __launch_bounds__(ROLLOUT_THREADS)
+bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
+    static_assert(M > 32 && M <= 64, "slot ids are ring entries of 64");
+    constexpr int MAXSRC = 8, SEGMENTS = 3;  // segments per trip: 3 / 4 / 5 / 6 / 8 -> 9.83 / 10.0 / 9.9 / 10.1 / 10.6 ms
+    __shared__ unsigned int s_hist[HIST_BINS];
+    __shared__ WarpSlots<NP, M, MAXSRC> s_slots[ROLLOUT_THREADS / 32];
+    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    const G g(grt);
+    constexpr bool USE_LUT = G::LUT && NP == 2;
+    const bool lut_on = USE_LUT || (NP == 2 && g.lut_rt());
+    __shared__ uint32_t s_lut[NP == 2 ? SEG_LUT_WORDS : 1];
+    if (lut_on)
+        for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[i] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
+    __syncthreads();
+    WarpSlots<NP, M, MAXSRC>& S = s_slots[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const LaneOut out{p.moves, p.length, p.winner, p.final_grid, p.reward};
+    uint64_t plane0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) plane0[k] = p.plane0[k];
+    uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
+    unsigned long long acc_steps = 0;
+    uint32_t pool_next = 0, pool_cnt = 0;
+    int rq_head = 0, rq_cnt = 0, wq_head = 0, wq_cnt = 0;  // warp-uniform
+    bool more = true;                                        // the game counter may still have games
+
+    auto pack_meta = [](const Game<NP, G>& gm, bool probe) {
+        return (uint32_t)gm.t | (gm.player ? META_PLAYER : 0u) | (gm.orient ? META_ORIENT : 0u) |
+               (probe ? META_PROBE : 0u) | ((uint32_t)(gm.win + 2) << META_WIN_SHIFT);
+    };
+    auto park = [&](int s, const Game<NP, G>& gm, bool probe, bool no_moves) {  // -> ready for its move generation
+#pragma unroll
+        for (int i = 0; i < NP; ++i) S.b[i][s] = gm.b[i];
+        S.src[s] = MoveGen<NP, G, RULES>::sources(g, gm.b, no_moves);
+        S.meta[s] = pack_meta(gm, probe);
+    };
+    auto new_game = [&](int s, uint32_t idx) {
+        Game<NP, G> gm;
+        bool no_moves = false;
+        if (p.start_grid)
+            no_moves = gm.begin_grid(g, p.start_grid + (size_t)idx * (g.h() * g.w()), p.start_player[idx],
+                                     p.start_winner ? (int)p.start_winner[idx] : BGS_WINNER_DRAW,
+                                     p.start_ended && p.start_ended[idx]);
+        else
+            gm.begin_planes(g, plane0);
+        S.idx[s] = idx;
+        park(s, gm, false, no_moves);
+    };
+
+    // ---- initial fill of the slots
+    for (int s0 = 0; s0 < M; s0 += 32) {
+        const int s = s0 + (int)lane;
+        const bool want = s < M;
+        const unsigned m = __ballot_sync(0xffffffffu, want);
+        const uint32_t idx = claim_index<64>(m, p.counter, pool_next, pool_cnt);
+        const bool ok = want && idx < p.n_games;
+        if (ok) new_game(s, idx);
+        const unsigned okm = __ballot_sync(0xffffffffu, ok);
+        if (ok) S.rq[(rq_head + rq_cnt + __popc(okm & lt)) & 63] = (uint8_t)s;
+        rq_cnt += __popc(okm);
+        if (okm != m) more = false;
+    }
+    __syncwarp();
+
+    MoveGen<NP, G, RULES> mg;
+    mg.lut = lut_on ? s_lut : nullptr;
+    bool has_work = false;
+    int slot = 0;
+    uint32_t me = 0;  // meta word of the slot in work
+    for (;;) {
+        // ---- (1) lanes without work take ready slots
+        const unsigned need = __ballot_sync(0xffffffffu, !has_work);
+        if (need != 0u && rq_cnt > 0) {
+            const int rank = __popc(need & lt);
+            if (!has_work && rank < rq_cnt) {
+                slot = S.rq[(rq_head + rank) & 63];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) mg.b[i] = S.b[i][slot];
+                me = S.meta[slot];
+                mg.begin_with(g, S.src[slot], (me & META_PROBE) != 0u);
+                has_work = true;
+            }
+            const int take = min(__popc(need), rq_cnt);
+            rq_head = (rq_head + take) & 63;
+            rq_cnt -= take;
+        }
+        const unsigned wk = __ballot_sync(0xffffffffu, has_work);
+        // ---- (2) the ply transition of up to 32 waiting slots, whole warp
+        if (wq_cnt > 0 && (wq_cnt >= p.ply_batch || wk == 0u || (rq_cnt == 0 && __popc(~wk) >= p.idle_batch))) {
+            const int nproc = min(32, wq_cnt);
+            bool ready = false, over = false;
+            int ws = 0;
+            if ((int)lane < nproc) {
+                ws = S.wq[(wq_head + (int)lane) & 63];
+                Game<NP, G> gm;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) gm.b[i] = S.b[i][ws];
+                const uint32_t mw = S.meta[ws];
+                const uint32_t gidx = S.idx[ws];
+                gm.t = (int)(mw & 0xffffu);
+                gm.player = (mw & META_PLAYER) ? 1 : 0;
+                gm.orient = (mw & META_ORIENT) ? 1 : 0;
+                gm.win = (int)((mw >> META_WIN_SHIFT) & 3u) - 2;
+                uint8_t* row = p.moves ? p.moves + (size_t)gidx * p.max_plies * 2ull : nullptr;
+                const Next nx = gm.transition(
+                    g, &S.T[0][ws], M, (int)((mw >> META_TOTAL_SHIFT) & 0x1ffu), (mw & META_PROBE) != 0u,
+                    (mw & META_FOUND) != 0u, p.max_plies, row, [&](int t) -> uint32_t {
+                        if ((t & 3) == 0) {
+                            const unsigned long long gid = p.game_id0 + gidx;
+                            uint32_t r[4];
+                            philox_hd((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2, DOMAIN_BOUNCE, p.seed_lo,
+                                      p.seed_hi, r);
+                            S.r[1][ws] = r[1]; S.r[2][ws] = r[2]; S.r[3][ws] = r[3];
+                            return r[0];
+                        }
+                        return S.r[t & 3][ws];
+                    });
+                if (nx == NEXT_OVER) {
+                    gm.write_result(g, out, gidx);
+                    acc_w0 += (gm.win == 0);
+                    acc_w1 += (gm.win == 1);
+                    acc_dr += (gm.win == BGS_WINNER_DRAW);
+                    acc_tr += (gm.win == BGS_WINNER_TRUNCATED);
+                    acc_steps += (unsigned)gm.t;
+                    atomicAdd(&s_hist[hist_bin(gm.t)], 1u);
+                    over = true;
+                } else {
+                    park(ws, gm, nx == NEXT_PROBE, false);
+                    ready = true;
+                }
+            }
+            wq_head = (wq_head + nproc) & 63;
+            wq_cnt -= nproc;
+            const unsigned ov = __ballot_sync(0xffffffffu, over);
+            if (ov != 0u && more) {  // refill the slots of finished games
+                const uint32_t nidx = claim_index<64>(ov, p.counter, pool_next, pool_cnt);
+                const bool ok = over && nidx < p.n_games;
+                if (ok) {
+                    new_game(ws, nidx);
+                    ready = true;
+                }
+                if (__ballot_sync(0xffffffffu, ok) != ov) more = false;
+            }
+            const unsigned pr = __ballot_sync(0xffffffffu, ready);
+            if (ready) S.rq[(rq_head + rq_cnt + __popc(pr & lt)) & 63] = (uint8_t)ws;
+            rq_cnt += __popc(pr);
+            __syncwarp();
+            continue;
+        }
+        if (wk == 0u) break;  // no work in flight, nothing waiting, nothing ready
+        // ---- (3) up to SEGMENTS move-generation segments
+        bool fin = false;
+        if (has_work) {
+            mg.iter(g, &S.T[0][slot], M);
+#pragma unroll
+            for (int q = 1; q < SEGMENTS; ++q)
+                if (!mg.done) mg.iter(g, &S.T[0][slot], M);
+            if (mg.done) {
+                S.meta[slot] = me | ((uint32_t)mg.total << META_TOTAL_SHIFT) | (mg.found ? META_FOUND : 0u);
+                has_work = false;
+                fin = true;
+            }
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, fin);
+        if (fm != 0u) {
+            if (fin) S.wq[(wq_head + wq_cnt + __popc(fm & lt)) & 63] = (uint8_t)slot;
+            wq_cnt += __popc(fm);
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+
+    if (p.stats) {
+        const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
+        const unsigned long long tr = warp_sum(acc_tr), st = warp_sum(acc_steps);
+        if (lane == 0) {
             atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr + tr);
             atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
             atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
@@ -433,6 +654,21 @@ static int launch_bounce_lane(const GeoRTb<typename G::bits>& grt, const Rollout
     return BGS_OK;
 }
 
+// 64-bit boards run on the slot kernel (2 Mi games, slot / lane kernel: default board 5.51 / 5.89 ms, 8x7 4.47 /
+// 5.08 ms, values up to 7 3.69 / 4.07 ms, 6x3 1.84 / 1.87 ms); boards on 128-bit words keep the lane kernel,
+// whose per-warp state fits the 48 KB of static shared memory.
+template <int NP, class G, int RULES>
+static int launch_bounce_slots(const GeoRT& grt, RolloutParams p, cudaStream_t stream) {
+    p.ply_batch = 32;  // 20 / 24 / 28 / 32 waiting slots: 10.35 / 10.08 / 9.83 / 9.83 ms per 4 Mi default games
+    p.idle_batch = 8;  // 4 / 8 / 16 idle lanes: 9.90 / 9.83 / 9.99 ms
+    auto kern = bounce_rollout_slots_kernel<NP, G, RULES, 64>;
+    int blocks = 0;
+    if (int rc = persistent_blocks(kern, p.n_games, &blocks)) return rc;
+    kern<<<(unsigned)blocks, ROLLOUT_THREADS, 0, stream>>>(grt, p);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
 static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, const int8_t* start_player,
                                const int8_t* start_winner, const uint8_t* start_ended, int H, int W, int rules,
                                int max_plies, uint64_t n_games, uint64_t game_id0, uint64_t seed, uint8_t* moves,
@@ -485,12 +721,12 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
         // the table-driven segments assume that the goal rows hold no piece (a window never starts below cell 3)
         bool goal_rows_empty = true;
         for (int x = 0; x < W; ++x) goal_rows_empty = goal_rows_empty && grid0[x] == 0 && grid0[(H - 1) * W + x] == 0;
-        if (H == 9 && W == 6 && rules == 0 && goal_rows_empty) return launch_bounce_lane<2, GeoCT<9, 6>, 0>(grt, p, stream);
+        if (H == 9 && W == 6 && rules == 0 && goal_rows_empty) return launch_bounce_slots<2, GeoCT<9, 6>, 0>(grt, p, stream);
         GeoRT g2 = grt;
         g2.lut_ok = g2.lut_ok && goal_rows_empty;
-        return launch_bounce_lane<2, GeoRT, -1>(g2, p, stream);
+        return launch_bounce_slots<2, GeoRT, -1>(g2, p, stream);
     }
-    return launch_bounce_lane<4, GeoRT, -1>(grt, p, stream);
+    return launch_bounce_slots<4, GeoRT, -1>(grt, p, stream);
 }
 
 extern "C" int bgs_bounce_rollout(const int8_t* grid0, int H, int W, int rules, int max_plies, uint64_t n_games,

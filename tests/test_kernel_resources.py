@@ -47,7 +47,7 @@ def test_headline_kernel_keeps_its_register_budget(usage):
 
 
 def test_rollout_kernels_do_not_spill(usage):
-    for part in ("connect_rollout_kernel", "connect_rollout_lines_kernel", "bounce_rollout_lane_kernel"):
+    for part in ("connect_rollout_kernel", "connect_rollout_lines_kernel", "bounce_rollout_lane_kernel", "bounce_rollout_slots_kernel"):
         for k in _find(usage, part):
             reg, stack, shared, local = usage[k]
             assert stack == 0 and local == 0, (k, usage[k])

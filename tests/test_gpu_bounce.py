@@ -309,3 +309,18 @@ def test_large_board_moves_and_step_equal_oracle(oracle):
         state = Config(grid0).sample_initial_state()
         ref = [tuple(a) for a in oracle.bounce_actions(grid0, 0, False)]
         assert [(*a.source.tolist(), *a.target.tolist()) for a in state.actions] == ref
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 65, 129, 4097])
+def test_small_and_ragged_batches_equal_oracle(oracle, n):
+    """Fewer games than a warp has slots / lanes, and counts that leave the last warp partly empty."""
+    from simulator import batch
+
+    for grid0, cap in ((GRID, 80), (BIG_VALUES, 40), (SMALL, 1)):
+        res = batch.bounce_rollout(grid0, n, seed=4, game_id0=1000, max_plies=cap, moves=True, final_grid=True, reward=True)
+        ref = oracle.bounce_rollout(grid0, n, max_plies=cap, gid0=1000, seed=4)
+        np.testing.assert_array_equal(res.actions.cpu().numpy(), ref["moves"])
+        np.testing.assert_array_equal(res.length.cpu().numpy().astype(np.uint16), ref["length"])
+        np.testing.assert_array_equal(res.winner.cpu().numpy(), ref["winner"])
+        np.testing.assert_array_equal(res.final_grid.cpu().numpy(), ref["final_grid"])
+        np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"])

@@ -190,7 +190,7 @@ struct WarpSlots {
     uint64_t b[NP][M];      // planes, oriented for the player whose moves are generated next
     uint64_t src[M];        // that player's movable pieces (MoveGen::sources), 0 for an ended start position
     uint64_t T[MAXSRC][M];  // target masks of the j-th movable piece
-    uint32_t r[4][M];       // Philox block of plies 4*(t>>2) .. +3
+    uint32_t r[3][M];       // words 1..3 of the Philox block of plies 4*(t>>2) .. +3 (word 0 is used at once)
     uint32_t idx[M];        // game index in [0, n)
     uint32_t meta[M];       // t:16 | total:9 | player | orient | probe | found | win+2:2
     uint8_t rq[64];         // READY ring (slot ids)
@@ -201,10 +201,12 @@ constexpr uint32_t META_TOTAL_SHIFT = 16, META_PLAYER = 1u << 25, META_ORIENT = 
                    META_FOUND = 1u << 28, META_WIN_SHIFT = 29;
 
 template <int NP, class G, int RULES, int M>
-__global__ void __launch_bounds__(ROLLOUT_THREADS)
+// resident CTAs per SM that the shared-memory footprint allows (30 / 34 / 38 KB per CTA): the register budget follows
+__global__ void __launch_bounds__(ROLLOUT_THREADS, (NP == 2 ? (G::MAX_SOURCES <= 6 ? 7 : 6) : 5))
 bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     static_assert(M > 32 && M <= 64, "slot ids are ring entries of 64");
-    constexpr int MAXSRC = 8, SEGMENTS = 3;  // segments per trip: 3 / 4 / 5 / 6 / 8 -> 9.83 / 10.0 / 9.9 / 10.1 / 10.6 ms
+    constexpr int MAXSRC = G::MAX_SOURCES;   // movable pieces = columns of one row
+    constexpr int SEGMENTS = 3;              // segments per trip: 3 / 4 / 5 / 6 / 8 -> 9.83 / 10.0 / 9.9 / 10.1 / 10.6 ms
     __shared__ unsigned int s_hist[HIST_BINS];
     __shared__ WarpSlots<NP, M, MAXSRC> s_slots[ROLLOUT_THREADS / 32];
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
@@ -313,10 +315,10 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
                             uint32_t r[4];
                             philox_hd((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)t >> 2, DOMAIN_BOUNCE, p.seed_lo,
                                       p.seed_hi, r);
-                            S.r[1][ws] = r[1]; S.r[2][ws] = r[2]; S.r[3][ws] = r[3];
+                            S.r[0][ws] = r[1]; S.r[1][ws] = r[2]; S.r[2][ws] = r[3];
                             return r[0];
                         }
-                        return S.r[t & 3][ws];
+                        return S.r[(t & 3) - 1][ws];
                     });
                 if (nx == NEXT_OVER) {
                     gm.write_result(g, out, gidx);

@@ -127,6 +127,7 @@ struct GeoRTb {
     typedef B bits;
     static constexpr int BITS = (int)sizeof(B) * 8;
     static constexpr bool LUT = false;  // no compile-time guarantee; lut_ok decides at run time
+    static constexpr int MAX_SOURCES = sizeof(B) == 8 ? 8 : 16;  // columns of one row
     bool lut_ok;         // table-driven segments possible: guard column, landing window within 32 bits
     int H, W, S, rules;
     int rot_shift;       // BITS-1 - (index of the last cell): rot180(x) = bit-reverse(x) >> rot_shift
@@ -190,6 +191,7 @@ struct GeoCT {
     static_assert(H_ * W_ <= 64 && W_ <= 8 && W_ >= 1 && H_ >= 1, "board must fit one 64-bit word");
     typedef uint64_t bits;
     static constexpr int S_ = (H_ * (W_ + 1) <= 64) ? W_ + 1 : W_;
+    static constexpr int MAX_SOURCES = W_;
     // segments by table look-up (seg_lut_entry): needs the guard column and a 32-bit landing window
     static constexpr bool LUT = S_ > W_ && S_ >= 3 && 3 * S_ + 3 <= 31;
     static constexpr uint64_t col_mask(int x0, int x1) {

@@ -121,6 +121,42 @@ def python_api_throughput(n_games: int = 300):
     return steps / dt
 
 
+_PYTHON_API_WORKER = r"""
+import os, random, sys, time
+root, n_games, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+sys.path.insert(0, os.path.join(root, "oracle", "pyapi"))
+sys.path.insert(0, root)
+from simulator.game import connect  # the oracle's object-API stand-in
+random.seed(seed)
+config = connect.Config(6, 7, 4)
+steps = 0
+t0 = time.perf_counter()
+for _ in range(n_games):
+    state = config.sample_initial_state()
+    while not state.has_ended:
+        state = random.choice(state.actions).sample_next_state()
+        steps += 1
+print(steps, time.perf_counter() - t0)
+"""
+
+
+def python_api_all_cores(n_games: int = 150):
+    """The README loop (README.md:52-69) in os.cpu_count() processes with disjoint seeds -- SURVEY.md 8d (ii):
+    the reference holds the GIL, so processes are its only way to use more cores.  Aggregate steps divided by
+    the slowest worker's time."""
+    import subprocess
+
+    procs = os.cpu_count() or 1
+    ps = [subprocess.Popen([sys.executable, "-c", _PYTHON_API_WORKER, ROOT, str(n_games), str(1000 + i)],
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i in range(procs)]
+    res = []
+    for pr in ps:
+        out, _ = pr.communicate(timeout=300)
+        st, sec = out.split()
+        res.append((int(st), float(sec)))
+    return sum(r[0] for r in res) / max(r[1] for r in res), procs
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -538,6 +574,9 @@ def run_b200(args):
             cb.pop("seconds"), cb.pop("steps")
             try:
                 cb["python_api_1thread_steps_per_s"] = python_api_throughput(200)
+                v, procs = python_api_all_cores(150)
+                cb["python_api_all_cores_steps_per_s"] = v
+                cb["python_api_processes"] = procs
             except Exception as e:  # never let the yardstick break the bench line
                 cb["python_api_error"] = repr(e)
             line["cpu_baseline"] = cb

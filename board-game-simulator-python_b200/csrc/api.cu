@@ -57,6 +57,7 @@ struct DeviceWorkspace {
     unsigned next = 0;
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    cudaMemPool_t pool = nullptr;  // stream-ordered temporaries (kept across synchronisations)
 };
 DeviceWorkspace g_ws[kMaxDevices];
 std::mutex g_ws_mutex;
@@ -76,7 +77,10 @@ int next_counter(unsigned int** out) {
 }
 
 // Write-only scratch of at least `bytes` bytes (contents are never read, so sharing it between
-// concurrent launches is harmless).
+// concurrent launches is harmless).  A buffer that has been handed out is NEVER freed while the
+// library is loaded: another host thread may still be launching kernels that write to it, so a
+// larger request allocates a new buffer (at least twice the old size, which bounds the retired
+// memory by the final size) and the old one stays allocated.
 int scratch_buffer(size_t bytes, void** out) {
     int dev = 0;
     BGS_CUDA_TRY(cudaGetDevice(&dev));
@@ -84,14 +88,51 @@ int scratch_buffer(size_t bytes, void** out) {
     std::lock_guard<std::mutex> lock(g_ws_mutex);
     DeviceWorkspace& w = g_ws[dev];
     if (w.scratch_bytes < bytes) {
-        if (w.scratch) BGS_CUDA_TRY(cudaFree(w.scratch));
-        w.scratch = nullptr;
-        w.scratch_bytes = 0;
-        BGS_CUDA_TRY(cudaMalloc(&w.scratch, bytes));
-        w.scratch_bytes = bytes;
+        size_t want = bytes > 2 * w.scratch_bytes ? bytes : 2 * w.scratch_bytes;
+        void* fresh = nullptr;
+        cudaError_t e = cudaMalloc(&fresh, want);
+        if (e != cudaSuccess && want > bytes) {  // no room for the doubled size: take exactly what is needed
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&fresh, want);
+        }
+        if (e != cudaSuccess) return cuda_error(e, "cudaMalloc(scratch)");
+        w.scratch = fresh;  // the previous buffer, if any, is retired, not freed (see above)
+        w.scratch_bytes = want;
     }
     *out = w.scratch;
     return BGS_OK;
+}
+
+// Stream-ordered temporary from the library's own per-device pool.  The pool's release threshold is
+// unlimited, so freed blocks stay with the pool across synchronisations instead of going back to the
+// driver (the default pool, threshold 0, costs milliseconds per re-allocation).
+int temp_alloc(void** out, size_t bytes, cudaStream_t stream) {
+    int dev = 0;
+    BGS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return set_error(BGS_EINVAL, "device index %d out of range", dev);
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_ws_mutex);
+        DeviceWorkspace& w = g_ws[dev];
+        if (!w.pool) {
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            BGS_CUDA_TRY(cudaMemPoolCreate(&w.pool, &props));
+            unsigned long long keep = ~0ull;
+            BGS_CUDA_TRY(cudaMemPoolSetAttribute(w.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        pool = w.pool;
+    }
+    BGS_CUDA_TRY(cudaMallocFromPoolAsync(out, bytes ? bytes : 1, pool, stream));
+    return BGS_OK;
+}
+
+void temp_free(void* ptr, cudaStream_t stream) {
+    if (ptr) cudaFreeAsync(ptr, stream);
 }
 
 }  // namespace bgs

@@ -24,12 +24,28 @@ int require_device();  // BGS_OK or BGS_ENODEVICE
         if (_e != cudaSuccess) return ::bgs::cuda_error(_e, #expr); \
     } while (0)
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards.
+struct DeviceGuard {
+    int prev = -1, rc = BGS_OK;
+    explicit DeviceGuard(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e == cudaSuccess) e = cudaSetDevice(device);
+        if (e != cudaSuccess) { rc = cuda_error(e, "cudaSetDevice"); prev = -1; }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // Number of SMs of the current device (cached per device).
 int sm_count();
 
 // Per-device workspace (api.cu): a zeroable claim counter for one launch, and write-only scratch.
 int next_counter(unsigned int** out);
 int scratch_buffer(size_t bytes, void** out);
+// Stream-ordered temporaries from the library's own memory pool (api.cu).
+int temp_alloc(void** out, size_t bytes, cudaStream_t stream);
+void temp_free(void* ptr, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG (Salmon et al., SC'11).  One call yields the 4 draws of plies
@@ -66,9 +82,14 @@ constexpr uint32_t DOMAIN_BOUNCE = 1u;
 // consecutive indices from it; ONE atomic per CHUNK (>= 32) indices.  Returns this lane's index
 // (meaningful only for lanes in `m`); indices >= n_games mean "no more work".
 // ---------------------------------------------------------------------------------------------
-template <int CHUNK>
+struct NoChunkHook {
+    __device__ __forceinline__ void operator()(uint32_t) const {}
+};
+
+// `on_new_chunk(base)` runs warp-convergently right after a fresh chunk [base, base + CHUNK) was claimed.
+template <int CHUNK, class Hook = NoChunkHook>
 __device__ __forceinline__ uint32_t claim_index(unsigned m, unsigned int* counter, uint32_t& pool_next,
-                                                uint32_t& pool_cnt) {
+                                                uint32_t& pool_cnt, Hook on_new_chunk = Hook()) {
     static_assert(CHUNK >= 32, "one chunk must cover a whole warp");
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t want = __popc(m);
@@ -78,6 +99,7 @@ __device__ __forceinline__ uint32_t claim_index(unsigned m, unsigned int* counte
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(counter, (unsigned)CHUNK);
         base = __shfl_sync(0xffffffffu, base, 0);
+        on_new_chunk(base);
         if (rank >= pool_cnt) id = base + (rank - pool_cnt);
         pool_next = base + (want - pool_cnt);
         pool_cnt = CHUNK - (want - pool_cnt);

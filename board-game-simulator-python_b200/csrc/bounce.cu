@@ -755,7 +755,8 @@ extern "C" int bgs_bounce_rollout_host(int device, const int8_t* grid0, int H, i
                                        uint16_t* length, int8_t* winner, int8_t* final_grid, float* reward,
                                        int64_t* stats) {
     if (int rc = require_device()) return rc;
-    BGS_CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);  // the caller's current device is restored on every exit path
+    if (guard.rc != BGS_OK) return guard.rc;
     if (n == 0) return BGS_OK;
     if (!supported(H, W, 0)) return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d", H, W);
     const size_t HW = (size_t)H * W;

@@ -139,6 +139,8 @@ struct RolloutParams {
     unsigned long long* stats;  // [BGS_STATS_LEN] or null
     unsigned int* counter;      // zero-initialised claim counter
     const uint64_t* start;      // START variants: [n, start_words] records written by connect_import_kernel
+    int8_t* final_grid;         // fused export (line kernel, GRID): int8[n, H, W] written once, at the end of each game
+    float* reward;              // fused export: float[n, 2] or null
     uint32_t one;               // always 1: an IMAD multiplier ptxas cannot fold (keeps adds on the FMA pipe)
 };
 
@@ -779,6 +781,11 @@ connect_rollout_lut_kernel(const RolloutParams p) {
     if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
 }
 
+__device__ __forceinline__ float2 reward_of(int winner) {
+    return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
+                       winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
+}
+
 // ---- line kernel: boards of more than 64 cells (8x9x5, 10x12x6) -----------------------------------
 // On a two-word (unsigned __int128) board the shift-and-AND run test costs ~100 ALU instructions per
 // ply.  This kernel keeps no bitboard at all: every line of the board (H rows, W columns, H+W-1
@@ -790,9 +797,6 @@ connect_rollout_lut_kernel(const RolloutParams p) {
 // warp is bank-conflict free whatever lines its lanes touch (measured 9 % faster than a
 // [4 lines][thread][4] layout that resets a game with 128-bit stores).
 constexpr int LINES_THREADS = 128;
-#ifndef BGS_LINES_LAYOUT
-#define BGS_LINES_LAYOUT 1  // 1: [line][thread] (every access conflict-free; measured 9 % faster), 0: [4 lines][thread][4] (128-bit reset)
-#endif
 
 template <int H, int W>
 struct LineGeo {
@@ -830,11 +834,7 @@ __device__ __forceinline__ uint32_t run_bits(uint32_t x) {
 // OR `bit` into line `li` of this thread and return the K-run indicator of the updated word.
 template <int K>
 __device__ __forceinline__ uint32_t line_update(uint32_t lines, uint32_t li, uint32_t bit) {
-#if BGS_LINES_LAYOUT == 1
     const uint32_t addr = lines + li * (LINES_THREADS * 4);
-#else
-    const uint32_t addr = lines + (li >> 2) * (LINES_THREADS * 16) + (li & 3u) * 4u;
-#endif
     const uint32_t x = lds_u32(addr) | bit;
     sts_u32(addr, x);
     return run_bits<K>(x);
@@ -861,6 +861,8 @@ __device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint64_t& hts, uint3
     if (h == (uint32_t)(H - 1)) toprow |= 1u << c;
     if (ACT == 1) act_row[t] = (uint8_t)c;
     if (ACT == 2) blk |= c << (4 * J);
+    // fused export: byte J of the block word = the column (one PRMT); unplayed slots keep their 0xFF
+    if (ACT == 3) blk = __byte_perm(blk, c, J == 0 ? 0x3214 : (J == 1 ? 0x3240 : (J == 2 ? 0x3410 : 0x4210)));
     t += 1;
     const uint32_t bc = 1u << (c + 16u * P), bh = 1u << (h + 16u * P);
     uint32_t w = line_update<K>(lines, h, bc);                                // row h, position c
@@ -872,16 +874,31 @@ __device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint64_t& hts, uint3
     return !(won || t == (uint32_t)(H * W));
 }
 
-template <int H, int W, int K, int ACT, bool PACKED>
+// ACT: 0 no trajectory / 1 one byte per ply into the pre-filled row / 2 16-bit blocks of 4-bit columns
+// (expanded in place by connect_expand_actions_kernel) / 3 FUSED: the warp pre-fills the rows of every
+// chunk of 64 game ids it claims with 0xFF (coalesced 128-bit stores) and a lane stores the 4 columns of
+// a 4-ply block as ONE 32-bit word in the final uint8[n, H*W] layout -- no expansion pass.
+// GRID (fused final grids, int8[n,H,W] in the reference's layout, tensor.hpp:69-87): the H row lines of a
+// finished game ARE its board (player 0 in bits 0..W-1, player 1 in bits 16..16+W-1), so when lanes
+// retire the whole warp turns the finished lanes' row lines into grid bytes -- lane q produces 8
+// consecutive cells of one finished game (two look-ups in a 256-entry table [4 bits of player 0 | 4 bits
+// of player 1] -> 4 grid bytes) and writes them with one 64-bit store: every output byte is written
+// exactly once, straight from the rollout kernel, and no packed board ever goes through HBM.
+template <int H, int W, int K, int ACT, bool PACKED, bool GRID = false>
 __global__ void __launch_bounds__(LINES_THREADS)
 connect_rollout_lines_kernel(const RolloutParams p) {
     typedef LineGeo<H, W> LG;
     static_assert(H <= 15 && W <= 15, "bit 15 of each half word must stay free");
     constexpr int HW = H * W;
+    constexpr bool FUSED = GRID || ACT == 3;
+    static_assert(!FUSED || HW % 8 == 0, "fused export: rows are written in 8-byte units");
+    static_assert(!(FUSED && PACKED), "fused export replaces the packed boards");
     __shared__ unsigned int s_hist[HIST_BINS];
     __shared__ unsigned int s_draws;
     __shared__ uint8_t s_lut8[256 * 8];  // [byte mask][k] -> index of the k-th set bit
-    __shared__ __align__(16) uint32_t s_lines[LG::NG * LINES_THREADS * 4];
+    __shared__ __align__(16) uint32_t s_lines[LG::NL * LINES_THREADS];  // [line][thread]: conflict-free whatever lines the lanes touch
+    __shared__ uint32_t s_cell4[GRID ? 256 : 1];                    // [p0 nibble | p1 nibble << 4] -> 4 grid bytes
+    __shared__ uint8_t s_fin[GRID ? LINES_THREADS / 32 : 1][32];     // the lanes retiring now, in ascending order
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) s_draws = 0;
     for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
@@ -893,14 +910,17 @@ connect_rollout_lines_kernel(const RolloutParams p) {
             }
         s_lut8[i] = (uint8_t)(c < 8 ? c : 0);
     }
+    if (GRID)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            uint32_t v = 0;
+            for (int j = 0; j < 4; ++j) v |= (((i >> j) & 1) ? 0u : (((i >> (4 + j)) & 1) ? 1u : 0xFFu)) << (8 * j);
+            s_cell4[i] = v;
+        }
     __syncthreads();
     const uint32_t lut8 = (uint32_t)__cvta_generic_to_shared(s_lut8);
-#if BGS_LINES_LAYOUT == 1
     uint32_t* my_lines = s_lines + threadIdx.x;  // line li at my_lines[li * LINES_THREADS]
-#else
-    uint4* my_lines = reinterpret_cast<uint4*>(s_lines) + threadIdx.x;  // group g at my_lines[g * LINES_THREADS]
-#endif
     const uint32_t lines = (uint32_t)__cvta_generic_to_shared(my_lines);
+    const unsigned lane = threadIdx.x & 31u;
 
     uint32_t toprow = 0, t = 0;
     uint64_t hts = 0;
@@ -910,18 +930,16 @@ connect_rollout_lines_kernel(const RolloutParams p) {
 
     for (;;) {
         // ---- warp-convergent: retire finished games, claim new ones -------------------------
-        if (!alive && t != 0) {
+        const bool fin = !alive && t != 0;
+        if (fin) {
             p.length[idx] = (uint8_t)t;
             p.winner[idx] = (int8_t)res;
+            if (FUSED && p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(res);
             if (PACKED) {  // rebuild the two bitboards from the row lines
                 u128 b0 = 0, b1 = 0;
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
-#if BGS_LINES_LAYOUT == 1
                     const uint32_t x = lds_u32(lines + r * (LINES_THREADS * 4));
-#else
-                    const uint32_t x = lds_u32(lines + (r >> 2) * (LINES_THREADS * 16) + (r & 3) * 4);
-#endif
                     b0 |= (u128)(x & 0xFFFFu) << ((H - 1 - r) * W);
                     b1 |= (u128)(x >> 16) << ((H - 1 - r) * W);
                 }
@@ -931,20 +949,57 @@ connect_rollout_lines_kernel(const RolloutParams p) {
             if (res < 0) atomicAdd(&s_draws, 1u);
             t = 0;
         }
+        if (GRID) {
+            const unsigned fm = __ballot_sync(0xffffffffu, fin);
+            if (fm) {  // warp-uniform: the whole warp writes the final grids of the lanes in fm
+                uint8_t* list = s_fin[threadIdx.x >> 5];
+                if (fin) list[__popc(fm & ((1u << lane) - 1u))] = (uint8_t)lane;
+                __syncwarp();
+                constexpr unsigned UPG = HW / 8;  // 8-byte units per game
+                constexpr uint32_t MW = (1u << W) - 1u;
+                const unsigned total = (unsigned)__popc(fm) * UPG;
+                const uint32_t warp_lines = lines - lane * 4u;  // row line 0 of lane 0
+                const uint32_t cell4 = (uint32_t)__cvta_generic_to_shared(s_cell4);
+                for (unsigned q0 = 0; q0 < total; q0 += 32) {  // warp-uniform trip count (the shuffle needs every lane)
+                    const unsigned q = q0 + lane;
+                    const bool valid = q < total;
+                    const unsigned j = valid ? q / UPG : 0u, u = q - j * UPG;
+                    const unsigned from = list[j];
+                    const uint32_t gidx = __shfl_sync(0xffffffffu, idx, from);
+                    if (valid) {
+                        const unsigned r0 = (8u * u) / (unsigned)W, c0 = 8u * u - r0 * (unsigned)W;
+                        const unsigned r1 = r0 + 1u < (unsigned)H ? r0 + 1u : r0;  // cells 8u .. 8u+7 span at most two rows
+                        const uint32_t src = warp_lines + from * 4u;
+                        const uint32_t x0 = lds_u32(src + r0 * (LINES_THREADS * 4)), x1 = lds_u32(src + r1 * (LINES_THREADS * 4));
+                        const uint32_t a = ((x0 & MW) | ((x1 & MW) << W)) >> c0;    // player 0's stones on cells 8u ..
+                        const uint32_t b = ((x0 >> 16) | ((x1 >> 16) << W)) >> c0;  // player 1's
+                        const uint32_t lo = lds_u32(cell4 + 4u * ((a & 0xFu) | ((b & 0xFu) << 4)));
+                        const uint32_t hi = lds_u32(cell4 + 4u * (((a >> 4) & 0xFu) | (b & 0xF0u)));
+                        *reinterpret_cast<uint2*>(p.final_grid + (size_t)gidx * HW + 8u * u) = make_uint2(lo, hi);
+                    }
+                }
+                __syncwarp();  // the row lines are read before their lanes reset them below
+            }
+        }
         const bool need = !alive && !retired;
         const unsigned m = __ballot_sync(0xffffffffu, need);
         if (m) {
-            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt);
+            const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt, [&](uint32_t base) {
+                if (ACT == 3 && base < p.n_games) {  // a fresh chunk of ids: 0xFF over its trajectory rows
+                    const uint32_t rows = (p.n_games - base) < (uint32_t)CLAIM_CHUNK ? (p.n_games - base) : (uint32_t)CLAIM_CHUNK;
+                    uint8_t* dst = p.actions + (size_t)base * HW;  // 16-byte aligned: base is a multiple of 64
+                    const uint32_t bytes = rows * (uint32_t)HW, n16 = bytes >> 4;
+                    for (uint32_t q = lane; q < n16; q += 32)
+                        reinterpret_cast<uint4*>(dst)[q] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    if ((bytes & 8u) && lane == 0) *reinterpret_cast<uint2*>(dst + (n16 << 4)) = make_uint2(~0u, ~0u);
+                    __syncwarp();  // orders the fill before the block stores of the lanes that get these ids
+                }
+            });
             if (need) {
                 if (id < p.n_games) {
                     idx = id;
-#if BGS_LINES_LAYOUT == 1
 #pragma unroll
                     for (int li = 0; li < LG::NL; ++li) my_lines[li * LINES_THREADS] = 0u;
-#else
-#pragma unroll
-                    for (int g = 0; g < LG::NG; ++g) my_lines[g * LINES_THREADS] = make_uint4(0u, 0u, 0u, 0u);
-#endif
                     toprow = 0; hts = 0; res = BGS_WINNER_DRAW;
                     alive = true;
                 } else {
@@ -961,12 +1016,13 @@ connect_rollout_lines_kernel(const RolloutParams p) {
         uint8_t* act_row = ACT ? p.actions + (size_t)idx * HW : nullptr;
         const bool started = alive;
         const uint32_t tb = t;
-        uint32_t blk = 0;
+        uint32_t blk = ACT == 3 ? 0xFFFFFFFFu : 0u;
         if (alive) alive = lines_ply<H, W, K, 0, ACT>(toprow, hts, r[0], t, res, lut8, lines, act_row, blk);
         if (alive) alive = lines_ply<H, W, K, 1, ACT>(toprow, hts, r[1], t, res, lut8, lines, act_row, blk);
         if (alive) alive = lines_ply<H, W, K, 2, ACT>(toprow, hts, r[2], t, res, lut8, lines, act_row, blk);
         if (alive) alive = lines_ply<H, W, K, 3, ACT>(toprow, hts, r[3], t, res, lut8, lines, act_row, blk);
         if (ACT == 2 && started) *reinterpret_cast<uint16_t*>(act_row + (tb >> 1)) = (uint16_t)blk;
+        if (ACT == 3 && started) *reinterpret_cast<uint32_t*>(act_row + tb) = blk;
     }
     __syncthreads();
     if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
@@ -1464,11 +1520,6 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
     }
 }
 
-__device__ __forceinline__ float2 reward_of(int winner) {
-    return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
-                       winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
-}
-
 // length (<= 63) and winner of every game in one byte: bits 0..5 length, bits 6..7 winner + 1.
 // Halves the device->host traffic of the per-game results (16 bytes per thread in, 16 out).
 __global__ void __launch_bounds__(256)
@@ -1682,12 +1733,6 @@ static int launch_persistent(Kern kern, const RolloutParams& p, cudaStream_t str
 // of at least 4 bytes; other boards store one byte per ply into the pre-filled row
 static int actions_mode(int H, int W) { return ((H * W) % 2 == 0 && H * W >= 4) ? 2 : 1; }
 
-// BGS_CONNECT_NO_OPENING=1 disables the opening phase of the generic kernel (A/B measurements).
-static bool no_opening() {
-    static const bool v = [] { const char* e = getenv("BGS_CONNECT_NO_OPENING"); return e && e[0] == '1'; }();
-    return v;
-}
-
 template <class G, bool START, bool OPEN>
 static int launch_rollout_s(const G& g, const RolloutParams& p, cudaStream_t stream) {
     const int act = p.actions ? actions_mode(g.H(), g.W()) : 0;
@@ -1705,7 +1750,7 @@ template <class G>
 static int launch_rollout(const G& g, const RolloutParams& p, cudaStream_t stream) {
     if (p.start) return launch_rollout_s<G, true, false>(g, p, stream);
     // the opening phase plays 8 plies unconditionally: the board must not be able to fill up in them
-    if (g.H() * g.W() >= 12 && !no_opening()) return launch_rollout_s<G, false, true>(g, p, stream);
+    if (g.H() * g.W() >= 12) return launch_rollout_s<G, false, true>(g, p, stream);
     return launch_rollout_s<G, false, false>(g, p, stream);
 }
 
@@ -1732,7 +1777,17 @@ static int launch_persistent_n(Kern kern, int threads, const RolloutParams& p, c
 }
 
 template <int H, int W, int K>
-static int launch_rollout_lines(const RolloutParams& p, cudaStream_t stream) {
+static int launch_rollout_lines(const RolloutParams& p, cudaStream_t stream, bool fused = false) {
+    if (fused) {  // trajectory rows / final grids / rewards straight from the rollout kernel
+        if constexpr ((H * W) % 8 == 0) {
+            if (p.actions && p.final_grid) return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 3, false, true>, LINES_THREADS, p, stream);
+            if (p.actions) return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 3, false, false>, LINES_THREADS, p, stream);
+            if (p.final_grid) return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 0, false, true>, LINES_THREADS, p, stream);
+            return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 0, false, false>, LINES_THREADS, p, stream);
+        } else {
+            return set_error(BGS_EUNSUPPORTED, "connect: no fused export for this board");
+        }
+    }
     const int act = p.actions ? actions_mode(H, W) : 0;
     if (p.final_packed) {
         if (act == 2) return launch_persistent_n(connect_rollout_lines_kernel<H, W, K, 2, true>, LINES_THREADS, p, stream);
@@ -1800,21 +1855,18 @@ extern "C" int bgs_connect_packed_words(int H, int W) {
     return 2 * (H * W <= 64 ? 1 : 2);
 }
 
-// Set BGS_CONNECT_GENERIC=1 to force the generic kernel on the 6x7x4 board (A/B measurements).
-static bool force_generic() {
-    static const bool v = [] { const char* e = getenv("BGS_CONNECT_GENERIC"); return e && e[0] == '1'; }();
-    return v;
+// Boards whose rollout kernel also writes trajectories / final grids / rewards in the reference's
+// layouts (fused export): the line kernel of the two larger BASELINE boards.
+static bool fused_export_board(int H, int W, int K) {
+    return (H == 8 && W == 9 && K == 5) || (H == 10 && W == 12 && K == 6);
 }
 
-// BGS_CONNECT_LINES=1 runs the 6x7x4 board through the line kernel (A/B measurements).
-static bool force_lines() {
-    static const bool v = [] { const char* e = getenv("BGS_CONNECT_LINES"); return e && e[0] == '1'; }();
-    return v;
-}
-
+// `fused`: final_grid / reward (and the trajectories) come straight from the rollout kernel
+// (fused_export_board only; the caller checked the pointer alignment).
 static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
                         const uint64_t* start, uint8_t* actions, uint8_t* length, int8_t* winner,
-                        uint64_t* final_packed, int64_t* stats, void* stream_) {
+                        uint64_t* final_packed, int64_t* stats, void* stream_, bool fused = false,
+                        int8_t* final_grid = nullptr, float* reward = nullptr) {
     if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
@@ -1834,7 +1886,7 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
     cudaError_t e = cudaSuccess;
     const bool bytes_board = !bitboard_supported(H, W, K);
     if (bytes_board && start) return set_error(BGS_EUNSUPPORTED, "connect: rollouts from positions need a board of at most 128 cells, 16 columns, 15 rows (%dx%d)", H, W);
-    const int act_mode = actions ? (bytes_board ? 1 : actions_mode(H, W)) : 0;
+    const int act_mode = actions ? (fused ? 3 : (bytes_board ? 1 : actions_mode(H, W))) : 0;
     if (rc == BGS_OK && act_mode == 1) {
         e = cudaMemsetAsync(actions, 0xFF, n_games * HW, stream);
         if (e != cudaSuccess) rc = cuda_error(e, "cudaMemsetAsync");
@@ -1853,6 +1905,8 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
         p.counter = counter;
         p.one = 1u;
         p.start = start ? start + off * start_words((int)HW) : nullptr;
+        p.final_grid = (fused && final_grid) ? final_grid + off * HW : nullptr;
+        p.reward = (fused && reward) ? reward + off * 2 : nullptr;
         e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) { rc = cuda_error(e, "cudaMemsetAsync"); break; }
         if (bytes_board) {
@@ -1863,11 +1917,10 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
             e = cudaGetLastError();
             if (e != cudaSuccess) rc = cuda_error(e, "connect_rollout_bytes_kernel");
         }
-        else if (H == 6 && W == 7 && K == 4 && force_lines() && !start) rc = launch_rollout_lines<6, 7, 4>(p, stream);
-        else if (H == 6 && W == 7 && K == 4 && !force_generic() && !start) rc = launch_rollout_lut<6, 7, 4>(p, stream);
+        else if (H == 6 && W == 7 && K == 4 && !start) rc = launch_rollout_lut<6, 7, 4>(p, stream);
         else if (H == 6 && W == 7 && K == 4) rc = launch_rollout(StaticGeo<6, 7, 4>(), p, stream);
-        else if (H == 8 && W == 9 && K == 5 && !force_generic() && !start) rc = launch_rollout_lines<8, 9, 5>(p, stream);
-        else if (H == 10 && W == 12 && K == 6 && !force_generic() && !start) rc = launch_rollout_lines<10, 12, 6>(p, stream);
+        else if (H == 8 && W == 9 && K == 5 && !start) rc = launch_rollout_lines<8, 9, 5>(p, stream, fused);
+        else if (H == 10 && W == 12 && K == 6 && !start) rc = launch_rollout_lines<10, 12, 6>(p, stream, fused);
         else if (H == 8 && W == 9 && K == 5) rc = launch_rollout(StaticGeo<8, 9, 5>(), p, stream);
         else if (H == 10 && W == 12 && K == 6) rc = launch_rollout(StaticGeo<10, 12, 6>(), p, stream);
         else rc = launch_rollout(make_dyn_geo(H, W, K), p, stream);
@@ -1882,6 +1935,33 @@ extern "C" int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64
                                    uint8_t* actions, uint8_t* length, int8_t* winner,
                                    uint64_t* final_packed, int64_t* stats, void* stream_) {
     return rollout_impl(H, W, K, n_games, game_id0, seed, nullptr, actions, length, winner, final_packed, stats, stream_);
+}
+
+extern "C" int bgs_connect_rollout_export(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                                          uint8_t* actions, uint8_t* length, int8_t* winner, int8_t* final_grid,
+                                          float* reward, int64_t* stats, void* stream_) {
+    if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
+    if (actions && !length) return set_error(BGS_EINVAL, "connect_rollout_export: `actions` requires `length`");
+    if (int rc = require_device()) return rc;
+    if (n_games == 0) return BGS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // single pass: every output byte is written once, by the rollout kernel itself
+    if (fused_export_board(H, W, K) && ((uintptr_t)actions & 15u) == 0 && ((uintptr_t)final_grid & 7u) == 0 &&
+        ((uintptr_t)reward & 7u) == 0)
+        return rollout_impl(H, W, K, n_games, game_id0, seed, nullptr, actions, length, winner, nullptr, stats, stream_,
+                            /*fused=*/true, final_grid, reward);
+    // other boards: rollout (packed final boards) + export, with stream-ordered temporaries
+    uint64_t* packed = nullptr;
+    int8_t* win_tmp = nullptr;
+    int rc = BGS_OK;
+    if (final_grid) rc = temp_alloc((void**)&packed, n_games * (size_t)bgs_connect_packed_words(H, W) * 8, stream);
+    if (rc == BGS_OK && reward && !winner) rc = temp_alloc((void**)&win_tmp, n_games, stream);
+    int8_t* win = winner ? winner : win_tmp;
+    if (rc == BGS_OK) rc = rollout_impl(H, W, K, n_games, game_id0, seed, nullptr, actions, length, win, packed, stats, stream_);
+    if (rc == BGS_OK && (final_grid || reward)) rc = bgs_connect_export(H, W, n_games, packed, win, final_grid, reward, stream_);
+    temp_free(packed, stream);
+    temp_free(win_tmp, stream);
+    return rc;
 }
 
 extern "C" int bgs_connect_start_words(int H, int W) { return start_words(H * W); }
@@ -2015,33 +2095,28 @@ extern "C" int bgs_connect_rollout_host(int device, int H, int W, int K, uint64_
                                         int8_t* final_grid, float* reward, int64_t* stats) {
     if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
     if (int rc = require_device()) return rc;
-    BGS_CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);  // the caller's current device is restored on every exit path
+    if (guard.rc != BGS_OK) return guard.rc;
     if (n == 0) return BGS_OK;
     const size_t HW = (size_t)H * W;
-    const int PW = bgs_connect_packed_words(H, W);
     cudaStream_t st;
     BGS_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     uint8_t *d_act = nullptr, *d_len = nullptr;
     int8_t *d_win = nullptr, *d_grid = nullptr;
-    uint64_t* d_packed = nullptr;
     float* d_rew = nullptr;
     int64_t* d_stats = nullptr;
     int rc = BGS_OK;
     auto fail = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == BGS_OK) rc = cuda_error(e, what); };
     if (actions) fail(cudaMallocAsync((void**)&d_act, n * HW, st), "alloc actions");
-    if (length) fail(cudaMallocAsync((void**)&d_len, n, st), "alloc length");
-    if (winner || reward) fail(cudaMallocAsync((void**)&d_win, n, st), "alloc winner");
-    if (final_grid) {
-        fail(cudaMallocAsync((void**)&d_packed, n * PW * sizeof(uint64_t), st), "alloc packed");
-        fail(cudaMallocAsync((void**)&d_grid, n * HW, st), "alloc grid");
-    }
+    if (length || actions) fail(cudaMallocAsync((void**)&d_len, n, st), "alloc length");
+    if (winner) fail(cudaMallocAsync((void**)&d_win, n, st), "alloc winner");
+    if (final_grid) fail(cudaMallocAsync((void**)&d_grid, n * HW, st), "alloc grid");
     if (reward) fail(cudaMallocAsync((void**)&d_rew, n * 2 * sizeof(float), st), "alloc reward");
     if (stats) {
         fail(cudaMallocAsync((void**)&d_stats, BGS_STATS_LEN * sizeof(int64_t), st), "alloc stats");
         if (rc == BGS_OK) fail(cudaMemcpyAsync(d_stats, stats, BGS_STATS_LEN * sizeof(int64_t), cudaMemcpyHostToDevice, st), "h2d stats");
     }
-    if (rc == BGS_OK) rc = bgs_connect_rollout(H, W, K, n, game_id0, seed, d_act, d_len, d_win, d_packed, d_stats, st);
-    if (rc == BGS_OK && (final_grid || reward)) rc = bgs_connect_export(H, W, n, d_packed, d_win, d_grid, d_rew, st);
+    if (rc == BGS_OK) rc = bgs_connect_rollout_export(H, W, K, n, game_id0, seed, d_act, d_len, d_win, d_grid, d_rew, d_stats, st);
     if (rc == BGS_OK) {
         if (actions) fail(cudaMemcpyAsync(actions, d_act, n * HW, cudaMemcpyDeviceToHost, st), "d2h actions");
         if (length) fail(cudaMemcpyAsync(length, d_len, n, cudaMemcpyDeviceToHost, st), "d2h length");
@@ -2050,7 +2125,7 @@ extern "C" int bgs_connect_rollout_host(int device, int H, int W, int K, uint64_
         if (reward) fail(cudaMemcpyAsync(reward, d_rew, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st), "d2h reward");
         if (stats) fail(cudaMemcpyAsync(stats, d_stats, BGS_STATS_LEN * sizeof(int64_t), cudaMemcpyDeviceToHost, st), "d2h stats");
     }
-    void* bufs[] = {d_act, d_len, d_win, d_grid, d_packed, d_rew, d_stats};
+    void* bufs[] = {d_act, d_len, d_win, d_grid, d_rew, d_stats};
     for (void* b : bufs)
         if (b) cudaFreeAsync(b, st);
     fail(cudaStreamSynchronize(st), "sync");

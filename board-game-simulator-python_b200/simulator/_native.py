@@ -28,6 +28,7 @@ _SIGNATURES = {
     "bgs_connect_supported": (C.c_int, [_i32, _i32, _i32]),
     "bgs_connect_packed_words": (C.c_int, [_i32, _i32]),
     "bgs_connect_rollout": (C.c_int, [_i32, _i32, _i32, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bgs_connect_rollout_export": (C.c_int, [_i32, _i32, _i32, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bgs_connect_start_words": (C.c_int, [_i32, _i32]),
     "bgs_connect_rollout_from": (C.c_int, [_i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 10),
     "bgs_connect_export": (C.c_int, [_i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),

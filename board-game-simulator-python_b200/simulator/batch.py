@@ -127,6 +127,23 @@ def connect_rollout(
     res.actions = buf("actions", (n, H * W), torch.uint8, actions)
     res.final_grid = buf("final_grid", (n, H, W), torch.int8, final_grid)
     res.reward = buf("reward", (n, 2), torch.float32, reward)
+    if stats is None:
+        stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
+    res.stats = stats
+    st = N.stream_ptr(torch)
+    seed64 = int(seed) & 0xFFFFFFFFFFFFFFFF
+    if start is None:
+        # one call: every output already in the reference's layouts; a single pass (the rollout kernel
+        # writes trajectory rows, final grids and rewards itself) on the boards that have a fused kernel
+        N.check(
+            L.bgs_connect_rollout_export(
+                H, W, K, n, int(game_id0), seed64, N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner),
+                N.ptr(res.final_grid), N.ptr(res.reward), N.ptr(stats), st,
+            )
+        )
+        return res
+    if start.n != n or tuple(start.grid.shape[1:]) != (H, W):
+        raise ValueError("start must hold n_games positions of this configuration")
     packed = None
     if final_grid:
         pw = L.bgs_connect_packed_words(H, W)
@@ -134,30 +151,16 @@ def connect_rollout(
         if packed is None or tuple(packed.shape) != (n, pw) or packed.device != dev:
             packed = torch.empty((n, pw), dtype=torch.int64, device=dev)
         res.extra["packed"] = packed
-    if stats is None:
-        stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
-    res.stats = stats
-    st = N.stream_ptr(torch)
-    if start is None:
-        N.check(
-            L.bgs_connect_rollout(
-                H, W, K, n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
-            )
+    work = torch.empty((n, L.bgs_connect_start_words(H, W)), dtype=torch.int64, device=dev)
+    grid0 = start.grid.contiguous()
+    N.check(
+        L.bgs_connect_rollout_from(
+            H, W, K, n, int(game_id0), seed64,
+            N.ptr(grid0), N.ptr(start.player.contiguous()), N.ptr(start.winner.contiguous()), N.ptr(work),
+            N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
         )
-    else:
-        if start.n != n or tuple(start.grid.shape[1:]) != (H, W):
-            raise ValueError("start must hold n_games positions of this configuration")
-        work = torch.empty((n, L.bgs_connect_start_words(H, W)), dtype=torch.int64, device=dev)
-        grid0 = start.grid.contiguous()
-        N.check(
-            L.bgs_connect_rollout_from(
-                H, W, K, n, int(game_id0), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                N.ptr(grid0), N.ptr(start.player.contiguous()), N.ptr(start.winner.contiguous()), N.ptr(work),
-                N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
-            )
-        )
-        res.extra["workspace"] = work
+    )
+    res.extra["workspace"] = work
     if final_grid or reward:
         N.check(
             L.bgs_connect_export(H, W, n, N.ptr(packed), N.ptr(res.winner), N.ptr(res.final_grid), N.ptr(res.reward), st)

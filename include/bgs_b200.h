@@ -96,6 +96,21 @@ int bgs_connect_rollout(int H, int W, int K, uint64_t n_games, uint64_t game_id0
                         uint8_t* actions, uint8_t* length, int8_t* winner, uint64_t* final_packed,
                         int64_t* stats, void* stream);
 
+/* bgs_connect_rollout + bgs_connect_export in ONE call, with every output in the reference's own
+ * layouts (State::get_grid / get_reward, connect.cpp:41-42; arrays as tensor.hpp:69-87 hands them to
+ * numpy): the loop of README.md:49-72 for n_games games, then per game
+ *   actions    optional uint8[n_games, H*W]  column per ply, 0xFF after the end (requires `length`)
+ *   length     optional uint8[n_games]; winner optional int8[n_games]
+ *   final_grid optional int8[n_games, H, W]  row 0 = bottom, -1 / 0 / 1
+ *   reward     optional float[n_games, 2]
+ * For Connect(8,9,5) and Connect(10,12,6) -- BASELINE.json configs[3] -- this is a single pass: the
+ * rollout kernel itself writes every output byte once (needs `actions` 16-byte and `final_grid` /
+ * `reward` 8-byte aligned, else the two-step path runs).  Other boards: rollout + export with
+ * stream-ordered temporaries for the packed boards. */
+int bgs_connect_rollout_export(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                               uint8_t* actions, uint8_t* length, int8_t* winner, int8_t* final_grid,
+                               float* reward, int64_t* stats, void* stream);
+
 /* The same loop from caller-supplied positions (the State objects of connect.cpp:36-46 as tensors:
  * grid int8[n,H,W], player int8[n] = side to move, winner_in optional int8[n], -1 = nobody has won):
  * State::from_json -> while !has_ended: actions -> uniform choice -> sample_next_state.

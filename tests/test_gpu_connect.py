@@ -509,3 +509,64 @@ def test_large_board_step_and_object_api(oracle):
         state = state.action_at(col).sample_next_state()
     assert state.grid[0, 7] == 0 and state.grid[1, 7] == 1 and state.grid[0, 8] == 0 and state.grid[2, 7] == 1
     assert len(state.actions) == W and not state.has_ended
+
+
+@pytest.mark.parametrize("cfg", [(8, 9, 5), (10, 12, 6), (6, 7, 4), (4, 4, 3)])
+def test_single_pass_export_every_output_combination(oracle, cfg):
+    """bgs_connect_rollout_export (BASELINE.json configs[3]): trajectory rows, final grids and rewards in
+    the reference's layouts (tensor.hpp:69-87) from one call -- on 8x9x5 / 10x12x6 the rollout kernel
+    writes them itself.  Every subset of the optional outputs, ragged batch sizes around the 64-id
+    claim chunks, all bit-exact against the oracle."""
+    from simulator import batch
+
+    H, W, K = cfg
+    for n in (1, 31, 63, 64, 65, 129, 1003, 4099):
+        ref = oracle.connect_rollout(H, W, K, n, gid0=17, seed=3)
+        for acts, grid, rew in ((1, 1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1)):
+            res = batch.connect_rollout(cfg, n, 3, 17, per_game=True, actions=bool(acts), final_grid=bool(grid),
+                                        reward=bool(rew))
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(res.length.cpu().numpy(), ref["length"])
+            np.testing.assert_array_equal(res.winner.cpu().numpy(), ref["winner"])
+            np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"])
+            if acts:
+                np.testing.assert_array_equal(res.actions.cpu().numpy(), ref["actions"], err_msg=f"n={n}")
+            if grid:
+                np.testing.assert_array_equal(res.final_grid.cpu().numpy(), ref["final_grid"], err_msg=f"n={n}")
+            if rew:
+                np.testing.assert_array_equal(res.reward.cpu().numpy(), ref["reward"])
+
+
+@pytest.mark.parametrize("cfg", [(8, 9, 5), (10, 12, 6), (6, 7, 4)])
+@pytest.mark.parametrize("misalign", [0, 8])
+def test_single_pass_export_stays_inside_its_buffers(oracle, cfg, misalign):
+    """Raw C-ABI call with interior pointers between canaries; `misalign` = 8 puts `actions` off the
+    16-byte boundary the fused kernel needs, so the two-step path must take over -- same bytes."""
+    from simulator import _native as N
+
+    H, W, K = cfg
+    n, HW, pad = 1003, H * W, 4096
+    L = N.lib()
+    sizes = {"actions": n * HW, "length": n, "winner": n, "grid": n * HW, "reward": n * 8}
+    off, total = {}, pad
+    for k, v in sizes.items():
+        off[k] = total + (misalign if k == "actions" else 0)
+        total += (v + pad + 255) // 256 * 256
+    buf = torch.full((total,), 0x5A, dtype=torch.uint8, device="cuda")
+    base = buf.data_ptr()
+    stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda")
+    N.check(L.bgs_connect_rollout_export(H, W, K, n, 5, 9, base + off["actions"], base + off["length"],
+                                         base + off["winner"], base + off["grid"], base + off["reward"],
+                                         N.ptr(stats), N.stream_ptr(torch)))
+    torch.cuda.synchronize()
+    used = torch.zeros(total, dtype=torch.bool, device="cuda")
+    for k, v in sizes.items():
+        used[off[k]: off[k] + v] = True
+    assert bool((buf[~used] == 0x5A).all()), "a kernel wrote outside its output buffer"
+    ref = oracle.connect_rollout(H, W, K, n, gid0=5, seed=9)
+    host = buf.cpu().numpy()
+    np.testing.assert_array_equal(host[off["actions"]: off["actions"] + n * HW].reshape(n, HW), ref["actions"])
+    np.testing.assert_array_equal(host[off["grid"]: off["grid"] + n * HW].view(np.int8).reshape(n, H, W), ref["final_grid"])
+    np.testing.assert_array_equal(host[off["reward"]: off["reward"] + n * 8].view(np.float32).reshape(n, 2), ref["reward"])
+    np.testing.assert_array_equal(host[off["length"]: off["length"] + n], ref["length"])
+    np.testing.assert_array_equal(stats.cpu().numpy(), ref["stats"])

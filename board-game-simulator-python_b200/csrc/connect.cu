@@ -155,9 +155,9 @@ constexpr int CLAIM_CHUNK = 64;
 // player 1, so the win counters need no per-game arithmetic at all.
 template <bool PARITY_WINS = true>
 __device__ __forceinline__ void flush_stats(const unsigned int* s_hist, unsigned int s_draws, int HW,
-                                            unsigned long long* stats) {
+                                            unsigned long long* stats, int nbins = HIST_BINS) {
     unsigned long long games = 0, steps = 0, odd = 0, even = 0;
-    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) {
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
         const unsigned long long h = s_hist[i];
         if (h) {
             atomicAdd(&stats[BGS_STAT_HIST0 + i], h);
@@ -782,8 +782,8 @@ connect_rollout_lut_kernel(const RolloutParams p) {
 }
 
 __device__ __forceinline__ float2 reward_of(int winner) {
-    return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),
-                       winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f));
+    const float r0 = winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f);
+    return make_float2(r0, 0.f - r0);  // 0 - 0 = +0: a draw is [0, 0], not [0, -0]
 }
 
 // ---- line kernel: boards of more than 64 cells (8x9x5, 10x12x6) -----------------------------------
@@ -831,13 +831,12 @@ __device__ __forceinline__ uint32_t run_bits(uint32_t x) {
     return m;
 }
 
-// OR `bit` into line `li` of this thread and return the K-run indicator of the updated word.
-template <int K>
-__device__ __forceinline__ uint32_t line_update(uint32_t lines, uint32_t li, uint32_t bit) {
+// OR `bit` into line `li` of this thread and return the updated word.
+__device__ __forceinline__ uint32_t line_or(uint32_t lines, uint32_t li, uint32_t bit) {
     const uint32_t addr = lines + li * (LINES_THREADS * 4);
     const uint32_t x = lds_u32(addr) | bit;
     sts_u32(addr, x);
-    return run_bits<K>(x);
+    return x;
 }
 
 template <int H, int W, int K, int J, int ACT>
@@ -865,11 +864,14 @@ __device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint64_t& hts, uint3
     if (ACT == 3) blk = __byte_perm(blk, c, J == 0 ? 0x3214 : (J == 1 ? 0x3240 : (J == 2 ? 0x3410 : 0x4210)));
     t += 1;
     const uint32_t bc = 1u << (c + 16u * P), bh = 1u << (h + 16u * P);
-    uint32_t w = line_update<K>(lines, h, bc);                                // row h, position c
-    w |= line_update<K>(lines, LG::COL0 + c, bh);                             // column c, position h
-    w |= line_update<K>(lines, LG::DIA0 + c + (uint32_t)(H - 1) - h, bc);      // diagonal (c - h const)
-    w |= line_update<K>(lines, LG::ANT0 + c + h, bc);                         // anti-diagonal (c + h const)
-    const bool won = w != 0;
+    const uint32_t xr = line_or(lines, h, bc);                                // row h, position c
+    const uint32_t xc = line_or(lines, LG::COL0 + c, bh);                     // column c, position h
+    const uint32_t xd = line_or(lines, LG::DIA0 + c + (uint32_t)(H - 1) - h, bc);  // diagonal (c - h const)
+    const uint32_t xa = line_or(lines, LG::ANT0 + c + h, bc);                 // anti-diagonal (c + h const)
+    // Two lines per run test: the mover's 16-bit halves of two line words side by side (one PRMT).  Bit 15
+    // of a half is never set (lines are at most 15 long), so no run can cross from one half into the other.
+    constexpr uint32_t SEL = P ? 0x7632u : 0x5410u;
+    const bool won = (run_bits<K>(__byte_perm(xr, xc, SEL)) | run_bits<K>(__byte_perm(xd, xa, SEL))) != 0u;
     if (won) res = P;
     return !(won || t == (uint32_t)(H * W));
 }
@@ -893,13 +895,13 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     constexpr bool FUSED = GRID || ACT == 3;
     static_assert(!FUSED || HW % 8 == 0, "fused export: rows are written in 8-byte units");
     static_assert(!(FUSED && PACKED), "fused export replaces the packed boards");
-    __shared__ unsigned int s_hist[HIST_BINS];
+    __shared__ unsigned int s_hist[HW + 1];  // a game lasts at most H*W plies
     __shared__ unsigned int s_draws;
     __shared__ uint8_t s_lut8[256 * 8];  // [byte mask][k] -> index of the k-th set bit
     __shared__ __align__(16) uint32_t s_lines[LG::NL * LINES_THREADS];  // [line][thread]: conflict-free whatever lines the lanes touch
     __shared__ uint32_t s_cell4[GRID ? 256 : 1];                    // [p0 nibble | p1 nibble << 4] -> 4 grid bytes
-    __shared__ uint8_t s_fin[GRID ? LINES_THREADS / 32 : 1][32];     // the lanes retiring now, in ascending order
-    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    __shared__ uint8_t s_list[GRID ? LINES_THREADS / 32 : 1][32];   // the lanes retiring now, in ascending order
+    for (int i = threadIdx.x; i < HW + 1; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) s_draws = 0;
     for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
         int mask = i >> 3, k = i & 7, c = 0;
@@ -920,7 +922,20 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     const uint32_t lut8 = (uint32_t)__cvta_generic_to_shared(s_lut8);
     uint32_t* my_lines = s_lines + threadIdx.x;  // line li at my_lines[li * LINES_THREADS]
     const uint32_t lines = (uint32_t)__cvta_generic_to_shared(my_lines);
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t warp_lines = lines - lane * 4u;  // line 0 of lane 0
+    uint8_t* list = s_list[GRID ? (threadIdx.x >> 5) : 0];
+
+    // Grid flush geometry, fixed per lane: a pass serves GPP finished games with LPG lanes each; lane
+    // (fg, fu) writes the 8-byte unit fu (cells 8*fu .. 8*fu+7, at most two board rows) of the pass's game fg.
+    constexpr unsigned UPG = HW / 8;                                          // 8-byte units per game
+    constexpr unsigned LPG = UPG <= 8 ? 8u : (UPG <= 10 ? 10u : 16u);         // 8x9: 10 lanes (3 games a pass), 10x12: 16 (2)
+    constexpr unsigned GPP = 32u / LPG;
+    static_assert(!GRID || UPG <= 16, "fused grids: at most 128 cells");
+    const unsigned fg = lane / LPG, fu = lane - fg * LPG;
+    const bool f_on = fg < GPP && fu < UPG;
+    const unsigned fr0 = (8u * fu) / (unsigned)W, fc0 = 8u * fu - fr0 * (unsigned)W;
+    const uint32_t f_x0 = fr0 * (LINES_THREADS * 4), f_x1 = (fr0 + 1u < (unsigned)H ? fr0 + 1u : fr0) * (LINES_THREADS * 4);
 
     uint32_t toprow = 0, t = 0;
     uint64_t hts = 0;
@@ -934,7 +949,7 @@ connect_rollout_lines_kernel(const RolloutParams p) {
         if (fin) {
             p.length[idx] = (uint8_t)t;
             p.winner[idx] = (int8_t)res;
-            if (FUSED && p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(res);
+            if (p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(res);  // set by the fused-export entry only
             if (PACKED) {  // rebuild the two bitboards from the row lines
                 u128 b0 = 0, b1 = 0;
 #pragma unroll
@@ -952,33 +967,30 @@ connect_rollout_lines_kernel(const RolloutParams p) {
         if (GRID) {
             const unsigned fm = __ballot_sync(0xffffffffu, fin);
             if (fm) {  // warp-uniform: the whole warp writes the final grids of the lanes in fm
-                uint8_t* list = s_fin[threadIdx.x >> 5];
-                if (fin) list[__popc(fm & ((1u << lane) - 1u))] = (uint8_t)lane;
+                if (fin) list[__popc(fm & lt)] = (uint8_t)lane;
                 __syncwarp();
-                constexpr unsigned UPG = HW / 8;  // 8-byte units per game
                 constexpr uint32_t MW = (1u << W) - 1u;
-                const unsigned total = (unsigned)__popc(fm) * UPG;
-                const uint32_t warp_lines = lines - lane * 4u;  // row line 0 of lane 0
+                const unsigned nfin = (unsigned)__popc(fm);
                 const uint32_t cell4 = (uint32_t)__cvta_generic_to_shared(s_cell4);
-                for (unsigned q0 = 0; q0 < total; q0 += 32) {  // warp-uniform trip count (the shuffle needs every lane)
-                    const unsigned q = q0 + lane;
-                    const bool valid = q < total;
-                    const unsigned j = valid ? q / UPG : 0u, u = q - j * UPG;
-                    const unsigned from = list[j];
+                unsigned g0 = 0;
+#pragma unroll 1
+                do {  // warp-uniform trip count (the shuffle needs every lane); one pass in most iterations
+                    const unsigned gi = g0 + fg;
+                    const bool on = f_on && gi < nfin;
+                    const unsigned from = list[gi & 31u];
                     const uint32_t gidx = __shfl_sync(0xffffffffu, idx, from);
-                    if (valid) {
-                        const unsigned r0 = (8u * u) / (unsigned)W, c0 = 8u * u - r0 * (unsigned)W;
-                        const unsigned r1 = r0 + 1u < (unsigned)H ? r0 + 1u : r0;  // cells 8u .. 8u+7 span at most two rows
+                    if (on) {
                         const uint32_t src = warp_lines + from * 4u;
-                        const uint32_t x0 = lds_u32(src + r0 * (LINES_THREADS * 4)), x1 = lds_u32(src + r1 * (LINES_THREADS * 4));
-                        const uint32_t a = ((x0 & MW) | ((x1 & MW) << W)) >> c0;    // player 0's stones on cells 8u ..
-                        const uint32_t b = ((x0 >> 16) | ((x1 >> 16) << W)) >> c0;  // player 1's
+                        const uint32_t x0 = lds_u32(src + f_x0), x1 = lds_u32(src + f_x1);
+                        const uint32_t a = ((x0 & MW) | ((x1 & MW) << W)) >> fc0;    // player 0's stones on cells 8*fu ..
+                        const uint32_t b = ((x0 >> 16) | ((x1 >> 16) << W)) >> fc0;  // player 1's
                         const uint32_t lo = lds_u32(cell4 + 4u * ((a & 0xFu) | ((b & 0xFu) << 4)));
                         const uint32_t hi = lds_u32(cell4 + 4u * (((a >> 4) & 0xFu) | (b & 0xF0u)));
-                        *reinterpret_cast<uint2*>(p.final_grid + (size_t)gidx * HW + 8u * u) = make_uint2(lo, hi);
+                        *reinterpret_cast<uint2*>(p.final_grid + ((size_t)gidx * HW + 8u * fu)) = make_uint2(lo, hi);
                     }
-                }
-                __syncwarp();  // the row lines are read before their lanes reset them below
+                    g0 += GPP;
+                } while (g0 < nfin);
+                __syncwarp();  // the row lines are read before they are reset below
             }
         }
         const bool need = !alive && !retired;
@@ -998,6 +1010,8 @@ connect_rollout_lines_kernel(const RolloutParams p) {
             if (need) {
                 if (id < p.n_games) {
                     idx = id;
+                    // (a cooperative reset -- 8 lanes per starting game, NL/8 stores per pass -- was measured
+                    // slower: 0.852 against 0.804 ms per 4 Mi 8x9 games; the 8-way bank conflicts stall the warp)
 #pragma unroll
                     for (int li = 0; li < LG::NL; ++li) my_lines[li * LINES_THREADS] = 0u;
                     toprow = 0; hts = 0; res = BGS_WINNER_DRAW;
@@ -1025,7 +1039,7 @@ connect_rollout_lines_kernel(const RolloutParams p) {
         if (ACT == 3 && started) *reinterpret_cast<uint32_t*>(act_row + tb) = blk;
     }
     __syncthreads();
-    if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);
+    if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats, HW + 1);
 }
 
 // ---- byte-board kernel: boards beyond the bit-word limits (up to 255 cells, 32 columns) ----------

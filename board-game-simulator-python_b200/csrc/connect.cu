@@ -140,7 +140,6 @@ struct RolloutParams {
     unsigned int* counter;      // zero-initialised claim counter
     const uint64_t* start;      // START variants: [n, start_words] records written by connect_import_kernel
     int8_t* final_grid;         // fused export (line kernel, GRID): int8[n, H, W] written once, at the end of each game
-    float* reward;              // fused export: float[n, 2] or null
     uint32_t one;               // always 1: an IMAD multiplier ptxas cannot fold (keeps adds on the FMA pipe)
 };
 
@@ -804,6 +803,10 @@ struct LineGeo {
     static constexpr int NL = H + W + 2 * D;  // rows | columns | diagonals | anti-diagonals
     static constexpr int NG = (NL + 3) / 4;
     static constexpr int COL0 = H, DIA0 = H + W, ANT0 = H + W + D;
+    // "k-th playable column" table: one look-up for W <= 8, else two halves of HALF_BITS bits (a half has at
+    // most 8 bits, so its k-th set bit still fits the [mask][8] table)
+    static constexpr int HALF_BITS = W <= 8 ? W : (W + 1) / 2;
+    static constexpr int LUT_ROWS = 1 << HALF_BITS;
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
@@ -847,12 +850,13 @@ __device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint64_t& hts, uint3
     const uint32_t freem = ~toprow & ((1u << W) - 1u);
     const uint32_t k = __umulhi(r, (uint32_t)__popc(freem));
     uint32_t c;
+    constexpr int HB = LG::HALF_BITS;
     if (W <= 8) {
         c = lds_u8(lut8 + freem * 8u + k);
-    } else {  // k-th set bit of a 16-bit mask from the table of its two bytes
-        const uint32_t lo8 = freem & 0xFFu, nlo = (uint32_t)__popc(lo8);
+    } else {  // k-th set bit of the W-bit mask from the table of its two HB-bit halves
+        const uint32_t lo = freem & ((1u << HB) - 1u), nlo = (uint32_t)__popc(lo);
         const bool hi = k >= nlo;
-        c = lds_u8(lut8 + (hi ? (freem >> 8) : lo8) * 8u + (hi ? k - nlo : k)) + (hi ? 8u : 0u);
+        c = lds_u8(lut8 + (hi ? (freem >> HB) : lo) * 8u + (hi ? k - nlo : k)) + (hi ? (uint32_t)HB : 0u);
     }
     const uint32_t sh = 4u * c;
     const uint32_t h = (uint32_t)(hts >> sh) & 15u;
@@ -897,13 +901,13 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     static_assert(!(FUSED && PACKED), "fused export replaces the packed boards");
     __shared__ unsigned int s_hist[HW + 1];  // a game lasts at most H*W plies
     __shared__ unsigned int s_draws;
-    __shared__ uint8_t s_lut8[256 * 8];  // [byte mask][k] -> index of the k-th set bit
+    __shared__ uint8_t s_lut8[LG::LUT_ROWS * 8];  // [mask of HALF_BITS bits][k] -> index of the k-th set bit
     __shared__ __align__(16) uint32_t s_lines[LG::NL * LINES_THREADS];  // [line][thread]: conflict-free whatever lines the lanes touch
     __shared__ uint32_t s_cell4[GRID ? 256 : 1];                    // [p0 nibble | p1 nibble << 4] -> 4 grid bytes
-    __shared__ uint8_t s_list[GRID ? LINES_THREADS / 32 : 1][32];   // the lanes retiring now, in ascending order
+    __shared__ uint2 s_list[GRID ? LINES_THREADS / 32 : 1][32];     // (lane, game index) of the lanes retiring now
     for (int i = threadIdx.x; i < HW + 1; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) s_draws = 0;
-    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+    for (int i = threadIdx.x; i < LG::LUT_ROWS * 8; i += blockDim.x) {
         int mask = i >> 3, k = i & 7, c = 0;
         for (; c < 8; ++c)
             if ((mask >> c) & 1) {
@@ -924,7 +928,7 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     const uint32_t lines = (uint32_t)__cvta_generic_to_shared(my_lines);
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const uint32_t warp_lines = lines - lane * 4u;  // line 0 of lane 0
-    uint8_t* list = s_list[GRID ? (threadIdx.x >> 5) : 0];
+    uint2* list = s_list[GRID ? (threadIdx.x >> 5) : 0];
 
     // Grid flush geometry, fixed per lane: a pass serves GPP finished games with LPG lanes each; lane
     // (fg, fu) writes the 8-byte unit fu (cells 8*fu .. 8*fu+7, at most two board rows) of the pass's game fg.
@@ -949,7 +953,6 @@ connect_rollout_lines_kernel(const RolloutParams p) {
         if (fin) {
             p.length[idx] = (uint8_t)t;
             p.winner[idx] = (int8_t)res;
-            if (p.reward) reinterpret_cast<float2*>(p.reward)[idx] = reward_of(res);  // set by the fused-export entry only
             if (PACKED) {  // rebuild the two bitboards from the row lines
                 u128 b0 = 0, b1 = 0;
 #pragma unroll
@@ -967,20 +970,19 @@ connect_rollout_lines_kernel(const RolloutParams p) {
         if (GRID) {
             const unsigned fm = __ballot_sync(0xffffffffu, fin);
             if (fm) {  // warp-uniform: the whole warp writes the final grids of the lanes in fm
-                if (fin) list[__popc(fm & lt)] = (uint8_t)lane;
+                if (fin) list[__popc(fm & lt)] = make_uint2(lane, idx);
                 __syncwarp();
                 constexpr uint32_t MW = (1u << W) - 1u;
                 const unsigned nfin = (unsigned)__popc(fm);
                 const uint32_t cell4 = (uint32_t)__cvta_generic_to_shared(s_cell4);
                 unsigned g0 = 0;
 #pragma unroll 1
-                do {  // warp-uniform trip count (the shuffle needs every lane); one pass in most iterations
+                do {  // one pass in most iterations
                     const unsigned gi = g0 + fg;
-                    const bool on = f_on && gi < nfin;
-                    const unsigned from = list[gi & 31u];
-                    const uint32_t gidx = __shfl_sync(0xffffffffu, idx, from);
-                    if (on) {
-                        const uint32_t src = warp_lines + from * 4u;
+                    if (f_on && gi < nfin) {
+                        const uint2 e = list[gi];
+                        const uint32_t gidx = e.y;
+                        const uint32_t src = warp_lines + e.x * 4u;
                         const uint32_t x0 = lds_u32(src + f_x0), x1 = lds_u32(src + f_x1);
                         const uint32_t a = ((x0 & MW) | ((x1 & MW) << W)) >> fc0;    // player 0's stones on cells 8*fu ..
                         const uint32_t b = ((x0 >> 16) | ((x1 >> 16) << W)) >> fc0;  // player 1's
@@ -1880,7 +1882,7 @@ static bool fused_export_board(int H, int W, int K) {
 static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
                         const uint64_t* start, uint8_t* actions, uint8_t* length, int8_t* winner,
                         uint64_t* final_packed, int64_t* stats, void* stream_, bool fused = false,
-                        int8_t* final_grid = nullptr, float* reward = nullptr) {
+                        int8_t* final_grid = nullptr) {
     if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
@@ -1920,7 +1922,6 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
         p.one = 1u;
         p.start = start ? start + off * start_words((int)HW) : nullptr;
         p.final_grid = (fused && final_grid) ? final_grid + off * HW : nullptr;
-        p.reward = (fused && reward) ? reward + off * 2 : nullptr;
         e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
         if (e != cudaSuccess) { rc = cuda_error(e, "cudaMemsetAsync"); break; }
         if (bytes_board) {
@@ -1959,20 +1960,22 @@ extern "C" int bgs_connect_rollout_export(int H, int W, int K, uint64_t n_games,
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    // single pass: every output byte is written once, by the rollout kernel itself
-    if (fused_export_board(H, W, K) && ((uintptr_t)actions & 15u) == 0 && ((uintptr_t)final_grid & 7u) == 0 &&
-        ((uintptr_t)reward & 7u) == 0)
-        return rollout_impl(H, W, K, n_games, game_id0, seed, nullptr, actions, length, winner, nullptr, stats, stream_,
-                            /*fused=*/true, final_grid, reward);
-    // other boards: rollout (packed final boards) + export, with stream-ordered temporaries
+    // fused boards: trajectory rows and final grids are written once, by the rollout kernel itself; rewards
+    // (a pure function of the winner: 1 byte read, 8 written per game) come from reward_kernel -- measured
+    // cheaper than a 64-bit store per retiring lane inside the rollout kernel (9 us against 13 - 27 us per 4 Mi games).
+    // Other boards: rollout (packed final boards) + export, with stream-ordered temporaries.
+    const bool fused = fused_export_board(H, W, K) && ((uintptr_t)actions & 15u) == 0 && ((uintptr_t)final_grid & 7u) == 0;
     uint64_t* packed = nullptr;
     int8_t* win_tmp = nullptr;
     int rc = BGS_OK;
-    if (final_grid) rc = temp_alloc((void**)&packed, n_games * (size_t)bgs_connect_packed_words(H, W) * 8, stream);
+    if (final_grid && !fused) rc = temp_alloc((void**)&packed, n_games * (size_t)bgs_connect_packed_words(H, W) * 8, stream);
     if (rc == BGS_OK && reward && !winner) rc = temp_alloc((void**)&win_tmp, n_games, stream);
     int8_t* win = winner ? winner : win_tmp;
-    if (rc == BGS_OK) rc = rollout_impl(H, W, K, n_games, game_id0, seed, nullptr, actions, length, win, packed, stats, stream_);
-    if (rc == BGS_OK && (final_grid || reward)) rc = bgs_connect_export(H, W, n_games, packed, win, final_grid, reward, stream_);
+    if (rc == BGS_OK)
+        rc = rollout_impl(H, W, K, n_games, game_id0, seed, nullptr, actions, length, win, packed, stats, stream_, fused,
+                          fused ? final_grid : nullptr);
+    if (rc == BGS_OK && ((final_grid && !fused) || reward))
+        rc = bgs_connect_export(H, W, n_games, packed, win, fused ? nullptr : final_grid, reward, stream_);
     temp_free(packed, stream);
     temp_free(win_tmp, stream);
     return rc;

@@ -490,13 +490,34 @@ bounce_moves_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __res
     if (count) count[i] = ok ? mg.total : -1;
 }
 
+// Weighted action choice (bgs_bounce_sample_step): `random.choices(actions, weights)` of the reference's
+// agent loop (textual/examples/arena.py:64-68) inside the transition kernel.  probs[i, sx, ty*W + tx] is the
+// weight of moving the piece in column sx of the mover's source row to cell (tx, ty); quantisation, draw and
+// choice exactly as for Connect (connect.cu, StepPolicy) over the legal actions in canonical order
+// (ascending sx, then target cell), RNG domain 1, t = draw_index[i] (0 if NULL).  Equal weights reproduce
+// the uniform choice of the rollout kernels: action mulhi32(r, n_actions).
+struct SamplePolicy {
+    const float* probs;           // [n, W, H*W] or null (moves come from `move`)
+    const uint64_t* game_ids;     // [n] or null (global id = game_id0 + i)
+    const int32_t* draw_index;    // [n] or null
+    unsigned long long game_id0;
+    uint32_t seed_lo, seed_hi;
+    int32_t* move_out;            // [n, 4] the chosen (sx, sy, tx, ty), -1s when there was nothing to choose; or null
+};
+
+__device__ __forceinline__ uint32_t quantize_weight(float w, float wmax) {
+    return (uint32_t)__fadd_rn(__fmul_rn(__fdiv_rn(w, wmax), 65535.0f), 0.5f);
+}
+__device__ __forceinline__ float sane_weight(float w) { return w > 0.0f ? fminf(w, 3.402823466e+38f) : 0.0f; }
+
 template <class B>
 __global__ void __launch_bounds__(STEP_THREADS)
 bounce_step_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __restrict__ grid,
                    const int8_t* __restrict__ player, const int8_t* __restrict__ winner,
                    const uint8_t* __restrict__ ended,
                    const int32_t* __restrict__ move, int8_t* grid_out, int8_t* player_out,
-                   int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status, bool vec) {
+                   int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status, bool vec,
+                   const SamplePolicy pol) {
     constexpr int MAXSRC = sizeof(B) == 8 ? 8 : 16, MAXCELLS = (int)sizeof(B) * 8;
     __shared__ __align__(16) B s_T[MAXSRC * STEP_THREADS];
     __shared__ __align__(16) uint8_t s_stage[STEP_THREADS / 32][32 * MAXCELLS];
@@ -517,7 +538,73 @@ bounce_step_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __rest
         const bool ok = planes_from_stage(mine, HW, mg.b);
         int pl = player[i] & 1;
         const bool over = ended && ended[i];
-        const int sx = move[4 * i + 0], sy = move[4 * i + 1], tx = move[4 * i + 2], ty = move[4 * i + 3];
+        int sx = -1, sy = -1, tx = -1, ty = -1;
+        if (pol.probs) {
+            if (ok && !over) {  // every legal action of the mover, then the weighted draw
+                B keep[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    keep[k] = mg.b[k];
+                    if (pl) mg.b[k] = rot180(g, mg.b[k]);
+                }
+                B src = StepGen<B>::sources(g, mg.b, false);
+                const int row_rel = src ? g.row_of(ctzb(src)) : 0;
+                mg.begin_with(g, src, false);
+                run_movegen(g, mg, T);
+                if (mg.total > 0) {
+                    // absolute target masks by absolute source column (rotate back for player 1), in local registers
+                    B A[MAXSRC];
+#pragma unroll
+                    for (int x = 0; x < MAXSRC; ++x) A[x] = 0;
+                    for (int j = 0; src; ++j) {
+                        const int x_rel = ctzb(src) - row_rel * g.S;
+                        src &= src - (B)1;
+                        const B tm = T[j * STEP_THREADS];
+                        const int xa = pl ? g.W - 1 - x_rel : x_rel;
+#pragma unroll
+                        for (int x = 0; x < MAXSRC; ++x)
+                            if (x == xa) A[x] = pl ? rot180(g, tm) : tm;
+                    }
+                    const float* pw = pol.probs + i * (unsigned long long)(g.W * HW);
+                    float wmax = 0.0f;
+#pragma unroll
+                    for (int x = 0; x < MAXSRC; ++x)
+                        for (B m = A[x]; m; m &= m - (B)1) wmax = fmaxf(wmax, sane_weight(pw[x * HW + ctzb(m)]));
+                    uint64_t total = 0;
+#pragma unroll
+                    for (int x = 0; x < MAXSRC; ++x)
+                        for (B m = A[x]; m; m &= m - (B)1)
+                            total += wmax > 0.0f ? quantize_weight(sane_weight(pw[x * HW + ctzb(m)]), wmax) : 1u;
+                    const uint32_t t = pol.draw_index ? (uint32_t)pol.draw_index[i] : 0u;
+                    const unsigned long long gid = pol.game_ids ? pol.game_ids[i] : pol.game_id0 + i;
+                    uint32_t r4[4];
+                    philox_hd((uint32_t)gid, (uint32_t)(gid >> 32), t >> 2, DOMAIN_BOUNCE, pol.seed_lo, pol.seed_hi, r4);
+                    const uint32_t r = (t & 3u) == 0 ? r4[0] : ((t & 3u) == 1 ? r4[1] : ((t & 3u) == 2 ? r4[2] : r4[3]));
+                    const uint64_t thresh = (uint64_t)r * total;
+                    uint64_t cum = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int x = 0; x < MAXSRC; ++x)
+                        for (B m = A[x]; m && !found; m &= m - (B)1) {
+                            const int cell = ctzb(m);
+                            cum += wmax > 0.0f ? quantize_weight(sane_weight(pw[x * HW + cell]), wmax) : 1u;
+                            if ((cum << 32) > thresh) {
+                                found = true;
+                                sx = x; sy = pl ? g.H - 1 - row_rel : row_rel;
+                                tx = cell % g.W; ty = cell / g.W;
+                            }
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mg.b[k] = keep[k];
+            }
+            if (pol.move_out) {
+                pol.move_out[4 * i + 0] = sx; pol.move_out[4 * i + 1] = sy;
+                pol.move_out[4 * i + 2] = tx; pol.move_out[4 * i + 3] = ty;
+            }
+        } else {
+            sx = move[4 * i + 0]; sy = move[4 * i + 1]; tx = move[4 * i + 2]; ty = move[4 * i + 3];
+        }
         bool legal = ok && !over && sx >= 0 && sx < g.W && sy >= 0 && sy < g.H && tx >= 0 && tx < g.W && ty >= 0 && ty < g.H;
         int win = winner ? (int)winner[i] : -1;
         bool end_new = over;
@@ -611,12 +698,12 @@ extern "C" int bgs_bounce_moves(int H, int W, int rules, uint64_t n, const int8_
     return BGS_OK;
 }
 
-extern "C" int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
-                               const int8_t* winner, const uint8_t* ended, const int32_t* move, int8_t* grid_out, int8_t* player_out,
-                               int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status,
-                               void* stream_) {
+static int bounce_step_impl(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
+                            const int8_t* winner, const uint8_t* ended, const int32_t* move, int8_t* grid_out, int8_t* player_out,
+                            int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status,
+                            void* stream_, const SamplePolicy& pol) {
     if (!supported(H, W, 0)) return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d", H, W);
-    if (!grid || !player || !move || !grid_out || !player_out || !winner_out)
+    if (!grid || !player || !grid_out || !player_out || !winner_out)
         return set_error(BGS_EINVAL, "bounce_step: null required pointer");
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
@@ -625,13 +712,36 @@ extern "C" int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t
     if (wide_board(H, W))
         bounce_step_kernel<u128><<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
             make_geo_rt_b<u128>(H, W, rules, /*guard=*/false), n, grid, player, winner, ended, move, grid_out, player_out,
-            winner_out, ended_out, reward_out, status, vec);
+            winner_out, ended_out, reward_out, status, vec, pol);
     else
         bounce_step_kernel<uint64_t><<<(unsigned)blocks, STEP_THREADS, 0, (cudaStream_t)stream_>>>(
             make_geo_rt(H, W, rules, /*guard=*/false), n, grid, player, winner, ended, move, grid_out, player_out,
-            winner_out, ended_out, reward_out, status, vec);
+            winner_out, ended_out, reward_out, status, vec, pol);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
+}
+
+extern "C" int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
+                               const int8_t* winner, const uint8_t* ended, const int32_t* move, int8_t* grid_out, int8_t* player_out,
+                               int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status,
+                               void* stream_) {
+    if (!move) return set_error(BGS_EINVAL, "bounce_step: null required pointer");
+    SamplePolicy pol{};
+    return bounce_step_impl(H, W, rules, n, grid, player, winner, ended, move, grid_out, player_out, winner_out, ended_out,
+                            reward_out, status, stream_, pol);
+}
+
+extern "C" int bgs_bounce_sample_step(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
+                                      const int8_t* winner, const uint8_t* ended, const float* probs, uint64_t seed,
+                                      uint64_t game_id0, const uint64_t* game_ids, const int32_t* draw_index,
+                                      int8_t* grid_out, int8_t* player_out, int8_t* winner_out, uint8_t* ended_out,
+                                      float* reward_out, int32_t* move_out, int32_t* status, void* stream_) {
+    if (!probs) return set_error(BGS_EINVAL, "bounce_sample_step: null `probs`");
+    SamplePolicy pol{};
+    pol.probs = probs; pol.game_ids = game_ids; pol.draw_index = draw_index; pol.game_id0 = game_id0;
+    pol.seed_lo = (uint32_t)seed; pol.seed_hi = (uint32_t)(seed >> 32); pol.move_out = move_out;
+    return bounce_step_impl(H, W, rules, n, grid, player, winner, ended, nullptr, grid_out, player_out, winner_out,
+                            ended_out, reward_out, status, stream_, pol);
 }
 
 template <class K>

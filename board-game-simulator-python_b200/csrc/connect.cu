@@ -1597,12 +1597,34 @@ __device__ __forceinline__ BoardBits load_grid(const uint8_t* g, int H, int W) {
 // state g0+l out of shared memory.
 constexpr int STEP_THREADS = 256;
 
+// Weighted action choice (bgs_connect_sample_step): the caller's `random.choices(actions, weights)` of the
+// reference's agent loop (textual/examples/arena.py:64-68, agent.py:58-67) inside the transition kernel.
+//   weights  w_c = probs[i, c] on the playable columns (NaN / negative / zero -> 0, +inf -> FLT_MAX)
+//   integers q_c = (uint32)(w_c / max_c w_c * 65535 + 0.5)  (IEEE single, no contraction); all w_c zero -> q_c = 1
+//   draw     r = Philox4x32-10(key = seed, ctr = (id_lo, id_hi, t >> 2, 0))[t & 3],  t = draw_index[i] or, if
+//            that is NULL, the number of stones on the board (= plies played from the empty board)
+//   choice   the first playable column j (ascending) with  (q_0 + .. + q_j) * 2^32 > r * sum(q)
+// With equal weights this is exactly the uniform rule of the rollout kernels, column mulhi32(r, n_legal).
+struct StepPolicy {
+    const float* probs;           // [n, W] or null (actions come from `action`)
+    const uint64_t* game_ids;     // [n] or null (global id = game_id0 + i)
+    const int32_t* draw_index;    // [n] or null
+    unsigned long long game_id0;
+    uint32_t seed_lo, seed_hi;
+    int32_t* action_out;          // [n] the chosen column (-1: the state had ended), or null
+};
+
+__device__ __forceinline__ uint32_t quantize_weight(float w, float wmax) {
+    return (uint32_t)__fadd_rn(__fmul_rn(__fdiv_rn(w, wmax), 65535.0f), 0.5f);
+}
+__device__ __forceinline__ float sane_weight(float w) { return w > 0.0f ? fminf(w, 3.402823466e+38f) : 0.0f; }
+
 __global__ void __launch_bounds__(STEP_THREADS)
 connect_step_kernel(const DynGeo g, unsigned long long n, const int8_t* __restrict__ grid,
                     const int8_t* __restrict__ player, const int8_t* __restrict__ winner,
                     const int32_t* __restrict__ action, int8_t* grid_out, int8_t* player_out,
                     int8_t* winner_out, uint8_t* ended_out, float* reward_out, uint32_t* legal_out,
-                    int32_t* status, bool vec) {
+                    int32_t* status, bool vec, const StepPolicy pol) {
     extern __shared__ __align__(16) uint8_t s_stage[];
     const int H = g.H(), W = g.W(), HW = H * W;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1625,11 +1647,43 @@ connect_step_kernel(const DynGeo g, unsigned long long n, const int8_t* __restri
             // instruction-bound (4 Mi 6x7 states: 0.41 ms against 0.07 ms of HBM time).
             int pl = player[i];
             int win = winner[i];
-            const int col = action[i];
             uint32_t legal_mask = 0;
             for (int c = 0; c < W; ++c)
                 if (mine[(H - 1) * W + c] == 0xFFu) legal_mask |= 1u << c;
             const bool ended = win >= 0 || legal_mask == 0;
+            int col = -1;
+            if (pol.probs) {
+                if (!ended) {
+                    const float* pw = pol.probs + i * (unsigned)W;
+                    float wmax = 0.0f;
+                    for (int c = 0; c < W; ++c)
+                        if ((legal_mask >> c) & 1u) wmax = fmaxf(wmax, sane_weight(pw[c]));
+                    uint64_t total = 0;
+                    for (int c = 0; c < W; ++c)
+                        if ((legal_mask >> c) & 1u) total += wmax > 0.0f ? quantize_weight(sane_weight(pw[c]), wmax) : 1u;
+                    uint32_t t;
+                    if (pol.draw_index) {
+                        t = (uint32_t)pol.draw_index[i];
+                    } else {
+                        t = 0;
+                        for (int c = 0; c < HW; ++c) t += mine[c] != 0xFFu;
+                    }
+                    const unsigned long long gid = pol.game_ids ? pol.game_ids[i] : pol.game_id0 + i;
+                    uint32_t r4[4];
+                    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), t >> 2, DOMAIN_CONNECT, pol.seed_lo, pol.seed_hi, r4);
+                    const uint32_t r = (t & 3u) == 0 ? r4[0] : ((t & 3u) == 1 ? r4[1] : ((t & 3u) == 2 ? r4[2] : r4[3]));
+                    const uint64_t thresh = (uint64_t)r * total;
+                    uint64_t cum = 0;
+                    for (int c = 0; c < W; ++c)
+                        if ((legal_mask >> c) & 1u) {
+                            cum += wmax > 0.0f ? quantize_weight(sane_weight(pw[c]), wmax) : 1u;
+                            if ((cum << 32) > thresh) { col = c; break; }
+                        }
+                }
+                if (pol.action_out) pol.action_out[i] = col;
+            } else {
+                col = action[i];
+            }
             const bool legal = !ended && col >= 0 && col < W && ((legal_mask >> col) & 1u) && (pl == 0 || pl == 1);
             if (legal) {
                 int row = 0;  // lowest empty cell of the column
@@ -1699,6 +1753,83 @@ connect_import_kernel(int H, int W, unsigned long long n, const int8_t* __restri
             }
         }
         __syncwarp();
+    }
+}
+
+// Reference-layout states -> packed positions: the two bitboards in the public packed-board format
+// (bgs_connect_packed_words) + one meta byte (bit 0 = side to move, bits 1..2 = winner + 1).  17 bytes per
+// 6x7 position instead of 44: what a host sends over PCIe for rollouts from positions.
+__global__ void __launch_bounds__(STEP_THREADS)
+connect_pack_kernel(int H, int W, unsigned long long n, const int8_t* __restrict__ grid,
+                    const int8_t* __restrict__ player, const int8_t* __restrict__ winner, uint64_t* packed,
+                    uint8_t* meta, bool vec) {
+    extern __shared__ __align__(16) uint8_t s_stage[];
+    const int HW = H * W;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* st_ = s_stage + (size_t)warp * 32 * HW;
+    const uint8_t* mine = st_ + lane * HW;
+    const unsigned long long ngroups = (n + 31ull) / 32ull;
+    constexpr int WARPS = STEP_THREADS / 32;
+    for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
+         group += (unsigned long long)gridDim.x * WARPS) {
+        const unsigned long long g0 = group * 32ull;
+        const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
+        warp_copy(st_, reinterpret_cast<const uint8_t*>(grid) + g0 * (unsigned)HW, rows * (unsigned)HW, lane, vec);
+        __syncwarp();
+        const unsigned long long i = g0 + lane;
+        if (i < n) {
+            const BoardBits b = load_grid(mine, H, W);
+            if (HW <= 64) {
+                *reinterpret_cast<ulonglong2*>(packed + i * 2) = make_ulonglong2((uint64_t)b.p[0], (uint64_t)b.p[1]);
+            } else {
+                ulonglong2* dst = reinterpret_cast<ulonglong2*>(packed + i * 4);
+                dst[0] = make_ulonglong2((uint64_t)b.p[0], (uint64_t)(b.p[0] >> 64));
+                dst[1] = make_ulonglong2((uint64_t)b.p[1], (uint64_t)(b.p[1] >> 64));
+            }
+            const int w_in = winner ? (int)winner[i] : -1;
+            meta[i] = (uint8_t)((player[i] & 1) | (((w_in + 1) & 3) << 1));
+        }
+        __syncwarp();
+    }
+}
+
+// Packed positions -> start records of the START rollout (column heights = stones per column).
+__global__ void __launch_bounds__(256)
+connect_import_packed_kernel(int H, int W, unsigned long long n, const uint64_t* __restrict__ packed,
+                             const uint8_t* __restrict__ meta, uint64_t* rec) {
+    const int HW = H * W;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        u128 b0, b1;
+        if (HW <= 64) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(packed + i * 2);
+            b0 = v.x; b1 = v.y;
+        } else {
+            const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(packed + i * 4);
+            const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(packed + i * 4 + 2);
+            b0 = ((u128)v0.y << 64) | v0.x; b1 = ((u128)v1.y << 64) | v1.x;
+        }
+        const u128 board = HW >= 128 ? ~(u128)0 : (((u128)1 << HW) - 1);
+        b0 &= board; b1 &= board & ~b0;  // a cell holds at most one stone
+        const u128 occ = b0 | b1;
+        uint64_t hts = 0;
+        for (int c = 0; c < W; ++c) {  // stones in column c = occupied cells (H-1-row)*W + c over all rows
+            int cnt = 0;
+            for (int r = 0; r < H; ++r) cnt += (int)((occ >> (r * W + c)) & 1);
+            hts |= (uint64_t)cnt << (4 * c);
+        }
+        const unsigned mb = meta[i];
+        const int w_in = (int)((mb >> 1) & 3u) - 1;
+        const uint64_t m = (uint64_t)(mb & 1u) | (w_in >= 0 ? 2ull : 0ull) | ((uint64_t)((w_in + 1) & 0xFF) << 8);
+        uint64_t* out = rec + i * start_words(HW);
+        if (HW <= 64) {
+            reinterpret_cast<ulonglong2*>(out)[0] = make_ulonglong2((uint64_t)b0, (uint64_t)b1);
+            reinterpret_cast<ulonglong2*>(out)[1] = make_ulonglong2(hts, m);
+        } else {
+            reinterpret_cast<ulonglong2*>(out)[0] = make_ulonglong2((uint64_t)b0, (uint64_t)(b0 >> 64));
+            reinterpret_cast<ulonglong2*>(out)[1] = make_ulonglong2((uint64_t)b1, (uint64_t)(b1 >> 64));
+            reinterpret_cast<ulonglong2*>(out)[2] = make_ulonglong2(hts, m);
+        }
     }
 }
 
@@ -2003,6 +2134,42 @@ extern "C" int bgs_connect_rollout_from(int H, int W, int K, uint64_t n_games, u
     return rollout_impl(H, W, K, n_games, game_id0, seed, workspace, actions, length, winner, final_packed, stats, stream_);
 }
 
+extern "C" int bgs_connect_pack(int H, int W, uint64_t n, const int8_t* grid, const int8_t* player,
+                                const int8_t* winner, uint64_t* packed, uint8_t* meta, void* stream_) {
+    if (!bitboard_supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
+    if (!grid || !player || !packed || !meta) return set_error(BGS_EINVAL, "connect_pack: null required pointer");
+    if (((uintptr_t)packed & 15u) != 0) return set_error(BGS_EINVAL, "connect_pack: `packed` must be 16-byte aligned");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    const size_t smem = (size_t)(STEP_THREADS / 32) * 32 * H * W;
+    unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    connect_pack_kernel<<<(unsigned)blocks, STEP_THREADS, smem, (cudaStream_t)stream_>>>(
+        H, W, n, grid, player, winner, packed, meta, ((uintptr_t)grid & 15u) == 0);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
+}
+
+extern "C" int bgs_connect_rollout_from_packed(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                                               const uint64_t* packed, const uint8_t* meta, uint64_t* workspace,
+                                               uint8_t* actions, uint8_t* length, int8_t* winner,
+                                               uint64_t* final_packed, int64_t* stats, void* stream_) {
+    if (!bitboard_supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
+    if (!packed || !meta || !workspace) return set_error(BGS_EINVAL, "connect_rollout_from_packed: null required pointer");
+    if (((uintptr_t)packed & 15u) != 0) return set_error(BGS_EINVAL, "connect_rollout_from_packed: `packed` must be 16-byte aligned");
+    if (int rc = require_device()) return rc;
+    if (n_games == 0) return BGS_OK;
+    {
+        unsigned long long blocks = (n_games + 255) / 256;
+        const unsigned long long cap = (unsigned long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        connect_import_packed_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(H, W, n_games, packed, meta, workspace);
+        BGS_CUDA_TRY(cudaGetLastError());
+    }
+    return rollout_impl(H, W, K, n_games, game_id0, seed, workspace, actions, length, winner, final_packed, stats, stream_);
+}
+
 extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,
                                   int8_t* grid, float* reward, void* stream_) {
     if (!supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
@@ -2071,12 +2238,12 @@ extern "C" int bgs_connect_pack_results(uint64_t n, const uint8_t* length, const
     return BGS_OK;
 }
 
-extern "C" int bgs_connect_step(int H, int W, int K, uint64_t n, const int8_t* grid, const int8_t* player,
-                                const int8_t* winner, const int32_t* action, int8_t* grid_out,
-                                int8_t* player_out, int8_t* winner_out, uint8_t* ended_out,
-                                float* reward_out, uint32_t* legal_out, int32_t* status, void* stream_) {
+static int step_impl(int H, int W, int K, uint64_t n, const int8_t* grid, const int8_t* player,
+                     const int8_t* winner, const int32_t* action, int8_t* grid_out,
+                     int8_t* player_out, int8_t* winner_out, uint8_t* ended_out,
+                     float* reward_out, uint32_t* legal_out, int32_t* status, void* stream_, const StepPolicy& pol) {
     if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
-    if (!grid || !player || !winner || !action || !grid_out || !player_out || !winner_out)
+    if (!grid || !player || !winner || !grid_out || !player_out || !winner_out)
         return set_error(BGS_EINVAL, "connect_step: null required pointer");
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
@@ -2089,9 +2256,32 @@ extern "C" int bgs_connect_step(int H, int W, int K, uint64_t n, const int8_t* g
     if (blocks > cap) blocks = cap;
     connect_step_kernel<<<(unsigned)blocks, STEP_THREADS, smem, (cudaStream_t)stream_>>>(
         g, n, grid, player, winner, action, grid_out, player_out, winner_out, ended_out, reward_out,
-        legal_out, status, (((uintptr_t)grid | (uintptr_t)grid_out) & 15u) == 0);
+        legal_out, status, (((uintptr_t)grid | (uintptr_t)grid_out) & 15u) == 0, pol);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
+}
+
+extern "C" int bgs_connect_step(int H, int W, int K, uint64_t n, const int8_t* grid, const int8_t* player,
+                                const int8_t* winner, const int32_t* action, int8_t* grid_out,
+                                int8_t* player_out, int8_t* winner_out, uint8_t* ended_out,
+                                float* reward_out, uint32_t* legal_out, int32_t* status, void* stream_) {
+    if (!action) return set_error(BGS_EINVAL, "connect_step: null required pointer");
+    StepPolicy pol{};
+    return step_impl(H, W, K, n, grid, player, winner, action, grid_out, player_out, winner_out, ended_out, reward_out,
+                     legal_out, status, stream_, pol);
+}
+
+extern "C" int bgs_connect_sample_step(int H, int W, int K, uint64_t n, const int8_t* grid, const int8_t* player,
+                                       const int8_t* winner, const float* probs, uint64_t seed, uint64_t game_id0,
+                                       const uint64_t* game_ids, const int32_t* draw_index, int8_t* grid_out,
+                                       int8_t* player_out, int8_t* winner_out, uint8_t* ended_out, float* reward_out,
+                                       uint32_t* legal_out, int32_t* action_out, int32_t* status, void* stream_) {
+    if (!probs) return set_error(BGS_EINVAL, "connect_sample_step: null `probs`");
+    StepPolicy pol{};
+    pol.probs = probs; pol.game_ids = game_ids; pol.draw_index = draw_index; pol.game_id0 = game_id0;
+    pol.seed_lo = (uint32_t)seed; pol.seed_hi = (uint32_t)(seed >> 32); pol.action_out = action_out;
+    return step_impl(H, W, K, n, grid, player, winner, nullptr, grid_out, player_out, winner_out, ended_out, reward_out,
+                     legal_out, status, stream_, pol);
 }
 
 extern "C" int bgs_connect_query(int H, int W, uint64_t n, const int8_t* grid, const int8_t* winner,

@@ -31,6 +31,12 @@ _SIGNATURES = {
     "bgs_connect_rollout_export": (C.c_int, [_i32, _i32, _i32, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bgs_connect_start_words": (C.c_int, [_i32, _i32]),
     "bgs_connect_rollout_from": (C.c_int, [_i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 10),
+    "bgs_connect_pack": (C.c_int, [_i32, _i32, _u64] + [_vp] * 6),
+    "bgs_connect_rollout_from_packed": (C.c_int, [_i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 9),
+    "bgs_connect_sample_step": (C.c_int, [_i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _u64, _u64] + [_vp] * 11),
+    "bgs_connect_keys": (C.c_int, [_i32, _i32, _u64] + [_vp] * 5),
+    "bgs_bounce_sample_step": (C.c_int, [_i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _u64] + [_vp] * 10),
+    "bgs_bounce_keys": (C.c_int, [_i32, _i32, _u64] + [_vp] * 5),
     "bgs_connect_export": (C.c_int, [_i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "bgs_connect_trajectory_grids": (C.c_int, [_i32, _i32, _u64, _vp, _vp, _vp, _vp]),
     "bgs_connect_pack_results": (C.c_int, [_u64, _vp, _vp, _vp, _vp]),

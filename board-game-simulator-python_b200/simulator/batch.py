@@ -58,6 +58,39 @@ class RolloutResult:
     def length_histogram(self):
         return self.stats[N.STAT_HIST0:].clone()
 
+    def to_json(self, config) -> list[dict]:
+        """One dict per game in the reference's wire format (tests/test_connect.py:123-145,
+        tests/test_bounce.py:365-410): ``{"state": State.to_json() of the final position (needs
+        ``final_grid``), "actions": [Action.to_json() per ply played]}`` -- what
+        ``[a.to_json() for a in trajectory]`` / ``state.to_json()`` give through the object API."""
+        n = self.n_games
+        length = self.length.cpu().numpy().astype("int64")
+        winner = self.winner.cpu().numpy()
+        out = []
+        if self.actions is not None and self.actions.dim() == 3:  # Bounce: (source cell, target cell) per ply
+            W = int(self.final_grid.shape[2]) if self.final_grid is not None else int(_bounce_grid(config).shape[1])
+            mv = self.actions.cpu().numpy()
+            acts = [[{"source": [int(s % W), int(s // W)], "target": [int(t % W), int(t // W)]} for s, t in mv[i, : length[i]]]
+                    for i in range(n)]
+        elif self.actions is not None:
+            a = self.actions.cpu().numpy()
+            acts = [[{"column": int(c)} for c in a[i, : length[i]]] for i in range(n)]
+        else:
+            acts = [None] * n
+        grids = self.final_grid.cpu().numpy() if self.final_grid is not None else None
+        first = self.extra.get("first_player")
+        first = None if first is None else first.cpu().numpy().astype("int64")
+        for i in range(n):
+            d = {}
+            if grids is not None:
+                w = int(winner[i])
+                d["state"] = {"grid": grids[i].tolist(),
+                              "player": int((length[i] + (0 if first is None else first[i])) & 1), "winner": w if w >= 0 else -1}
+            if acts[i] is not None:
+                d["actions"] = acts[i]
+            out.append(d)
+        return out
+
 
 def all_reduce_stats(stats):
     """Sum the statistics vector over all ranks (NCCL over NVLink; the path's only collective)."""
@@ -90,11 +123,11 @@ def connect_rollout(
     reward: bool = False,
     stats=None,
     out: RolloutResult | None = None,
-    start: "ConnectBatch | None" = None,
+    start: "ConnectBatch | ConnectPacked | None" = None,
 ) -> RolloutResult:
     """Play ``n_games`` uniform-random Connect-k games to the end on the current CUDA device.
 
-    With ``start`` (a :class:`ConnectBatch` of ``n_games`` positions) the games continue from those
+    With ``start`` (a :class:`ConnectBatch`, or its 17-bytes-per-position :class:`ConnectPacked` form, of ``n_games`` positions) the games continue from those
     positions instead of the empty board -- the leaf evaluation of a tree search: ``length`` and
     ``actions`` then cover only the plies played by the rollout, and game ``i`` draws from the stream of
     global id ``game_id0 + i`` starting at draw 0.
@@ -142,7 +175,7 @@ def connect_rollout(
             )
         )
         return res
-    if start.n != n or tuple(start.grid.shape[1:]) != (H, W):
+    if start.n != n or (not isinstance(start, ConnectPacked) and tuple(start.grid.shape[1:]) != (H, W)):
         raise ValueError("start must hold n_games positions of this configuration")
     packed = None
     if final_grid:
@@ -151,15 +184,26 @@ def connect_rollout(
         if packed is None or tuple(packed.shape) != (n, pw) or packed.device != dev:
             packed = torch.empty((n, pw), dtype=torch.int64, device=dev)
         res.extra["packed"] = packed
-    work = torch.empty((n, L.bgs_connect_start_words(H, W)), dtype=torch.int64, device=dev)
-    grid0 = start.grid.contiguous()
-    N.check(
-        L.bgs_connect_rollout_from(
-            H, W, K, n, int(game_id0), seed64,
-            N.ptr(grid0), N.ptr(start.player.contiguous()), N.ptr(start.winner.contiguous()), N.ptr(work),
-            N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
+    work = out.extra.get("workspace") if out is not None else None
+    sw = L.bgs_connect_start_words(H, W)
+    if work is None or tuple(work.shape) != (n, sw) or work.device != dev:
+        work = torch.empty((n, sw), dtype=torch.int64, device=dev)
+    if isinstance(start, ConnectPacked):  # 17 / 33 bytes per position instead of H*W + 2
+        N.check(
+            L.bgs_connect_rollout_from_packed(
+                H, W, K, n, int(game_id0), seed64, N.ptr(start.packed), N.ptr(start.meta), N.ptr(work),
+                N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
+            )
         )
-    )
+    else:
+        grid0 = start.grid.contiguous()
+        N.check(
+            L.bgs_connect_rollout_from(
+                H, W, K, n, int(game_id0), seed64,
+                N.ptr(grid0), N.ptr(start.player.contiguous()), N.ptr(start.winner.contiguous()), N.ptr(work),
+                N.ptr(res.actions), N.ptr(res.length), N.ptr(res.winner), N.ptr(packed), N.ptr(stats), st,
+            )
+        )
     res.extra["workspace"] = work
     if final_grid or reward:
         N.check(
@@ -288,6 +332,34 @@ class HostRollout:
             yield self._out(done)
 
 
+@dataclass
+class ConnectPacked:
+    """n Connect-k positions as two bitboards + one meta byte each (``ConnectBatch.pack()``): ``packed``
+    int64[n, 2 or 4] in the packed-board format of ``include/bgs_b200.h``, ``meta`` uint8[n] (bit 0 = side to
+    move, bits 1..2 = winner + 1).  ``connect_rollout(start=...)`` accepts it; 17 bytes per 6x7 position cross
+    PCIe instead of 44."""
+
+    config: Any
+    packed: Any
+    meta: Any
+
+    @property
+    def n(self) -> int:
+        return int(self.meta.shape[0])
+
+
+def _keys_unique(keys):
+    """(unique keys int64[m,2], index of the first state with each key int64[m], inverse int64[n]) -- the rows
+    in ascending (signed) lexicographic order of the two key words."""
+    import torch
+
+    uniq, inverse = torch.unique(keys, dim=0, return_inverse=True)
+    n = keys.shape[0]
+    first = torch.full((uniq.shape[0],), n, dtype=torch.int64, device=keys.device)
+    first.scatter_reduce_(0, inverse, torch.arange(n, device=keys.device), reduce="amin")
+    return uniq, first, inverse
+
+
 class ConnectBatch:
     """n Connect-k states as tensors: the batched equivalent of the reference's State objects.
 
@@ -329,6 +401,102 @@ class ConnectBatch:
                 N.ptr(self.reward), N.stream_ptr(torch),
             )
         )
+
+    # -- equality / ordering / hashing of whole batches (reference helper.hpp:10-25) ----------------------
+    def key(self):
+        """int64[n, 2]: one canonical 128-bit key per state, equal iff the reference's ``==`` holds (same
+        grid, player, winner).  Exact and invertible for boards of at most 62 cells, a hash beyond."""
+        torch = N.require_cuda()
+        H, W, _ = _hwk(self.config)
+        keys = torch.empty((self.n, 2), dtype=torch.int64, device=self.grid.device)
+        N.check(N.lib().bgs_connect_keys(H, W, self.n, N.ptr(self.grid.contiguous()), N.ptr(self.player.contiguous()),
+                                         N.ptr(self.winner.contiguous()), N.ptr(keys), N.stream_ptr(torch)))
+        return keys
+
+    def equal(self, other: "ConnectBatch"):
+        """bool[n]: ``state_i == other_i`` for every i (also ``batch == other``)."""
+        if _hwk(self.config) != _hwk(other.config) or self.n != other.n:
+            raise ValueError("batches of different configurations / sizes")
+        return (self.key() == other.key()).all(dim=1)
+
+    __eq__ = equal
+    __hash__ = None
+
+    def unique(self):
+        """Deduplicate: ``(batch of the distinct states, first int64[m], inverse int64[n])`` with
+        ``batch[inverse[i]] == self[i]`` -- the set a transposition table would hold."""
+        _, first, inverse = _keys_unique(self.key())
+        return self.select(first), first, inverse
+
+    def select(self, index) -> "ConnectBatch":
+        """The states at ``index`` (an int64 tensor) as a new batch."""
+        pick = lambda t: None if t is None else t.index_select(0, index)
+        return ConnectBatch(self.config, pick(self.grid), pick(self.player), pick(self.winner), pick(self.has_ended),
+                            pick(self.legal), pick(self.reward))
+
+    def pack(self) -> ConnectPacked:
+        """Two bitboards + a meta byte per state (17 bytes for 6x7 instead of 44)."""
+        torch = N.require_cuda()
+        L = N.lib()
+        H, W, _ = _hwk(self.config)
+        packed = torch.empty((self.n, L.bgs_connect_packed_words(H, W)), dtype=torch.int64, device=self.grid.device)
+        meta = torch.empty(self.n, dtype=torch.uint8, device=self.grid.device)
+        N.check(L.bgs_connect_pack(H, W, self.n, N.ptr(self.grid.contiguous()), N.ptr(self.player.contiguous()),
+                                   N.ptr(self.winner.contiguous()), N.ptr(packed), N.ptr(meta), N.stream_ptr(torch)))
+        return ConnectPacked(self.config, packed, meta)
+
+    # -- the reference's JSON wire format for a whole batch (tests/test_connect.py:130-139) ----------------
+    def to_json(self) -> list[dict]:
+        """``[state.to_json() for state in batch]``: ``{"grid": rows bottom-up, "player", "winner"}``."""
+        g = self.grid.cpu().numpy().tolist()
+        p = self.player.cpu().numpy().tolist()
+        w = self.winner.cpu().numpy().tolist()
+        return [{"grid": g[i], "player": int(p[i]), "winner": int(w[i])} for i in range(self.n)]
+
+    @staticmethod
+    def from_json(values: list[dict], config) -> "ConnectBatch":
+        """``[State.from_json(v, config) for v in values]`` as one batch on the current CUDA device."""
+        import numpy as np
+
+        torch = N.require_cuda()
+        H, W, _ = _hwk(config)
+        grid = np.array([v["grid"] for v in values], dtype=np.int8).reshape(len(values), H, W)
+        player = np.array([v["player"] for v in values], dtype=np.int8)
+        winner = np.array([v["winner"] for v in values], dtype=np.int8)
+        return ConnectBatch(config, torch.from_numpy(grid).cuda(), torch.from_numpy(player).cuda(),
+                            torch.from_numpy(winner).cuda())
+
+    def sample_step(self, probs, seed: int, game_id0: int = 0, game_ids=None, draw_index=None):
+        """``random.choices(state.actions, weights)`` then ``sample_next_state()`` for every state in ONE kernel
+        (reference textual/examples/arena.py:64-68): ``probs`` float32[n, W] are per-column weights (columns
+        that are not playable are ignored); the draw is the Philox draw of global game id ``game_id0 + i`` (or
+        ``game_ids[i]``) at index ``draw_index[i]`` (default: the number of stones on the board), so equal weights
+        replay ``connect_rollout``'s games ply by ply.  Returns ``(next_batch, action int32[n], status)``;
+        ``action`` is -1 and ``status`` 1 where the game had already ended."""
+        torch = N.require_cuda()
+        H, W, K = _hwk(self.config)
+        n, dev = self.n, self.grid.device
+        probs = probs.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(probs.shape) != (n, W):
+            raise ValueError("probs must be float32[n, W]")
+        gids = None if game_ids is None else game_ids.to(device=dev, dtype=torch.int64).contiguous()
+        didx = None if draw_index is None else draw_index.to(device=dev, dtype=torch.int32).contiguous()
+        grid = torch.empty_like(self.grid)
+        player = torch.empty_like(self.player)
+        winner = torch.empty_like(self.winner)
+        ended = torch.empty(n, dtype=torch.uint8, device=dev)
+        legal = torch.empty(n, dtype=torch.int32, device=dev)
+        reward = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        action = torch.empty(n, dtype=torch.int32, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        N.check(
+            N.lib().bgs_connect_sample_step(
+                H, W, K, n, N.ptr(self.grid), N.ptr(self.player), N.ptr(self.winner), N.ptr(probs),
+                int(seed) & 0xFFFFFFFFFFFFFFFF, int(game_id0), N.ptr(gids), N.ptr(didx), N.ptr(grid), N.ptr(player),
+                N.ptr(winner), N.ptr(ended), N.ptr(reward), N.ptr(legal), N.ptr(action), N.ptr(status), N.stream_ptr(torch),
+            )
+        )
+        return ConnectBatch(self.config, grid, player, winner, ended, legal, reward), action, status
 
     def legal_mask(self):
         """bool[n, W]: which columns ``state.actions`` would list (reference connect.cpp:43)."""
@@ -410,6 +578,8 @@ def bounce_rollout(
     torch = N.require_cuda()
     L = N.lib()
     n = int(n_games)
+    if not 0 <= int(max_plies) <= 32767:
+        raise ValueError("max_plies must be in 0..32767 (lengths are returned as int16)")
     if start is None:
         g = _bounce_grid(config)
         _bounce_check(L, g)
@@ -419,7 +589,7 @@ def bounce_rollout(
             raise ValueError("start must hold n_games positions")
         H, W = int(start.grid.shape[1]), int(start.grid.shape[2])
         if not L.bgs_bounce_supported(H, W, 0):
-            raise RuntimeError(f"Bounce {H}x{W} is not supported by the CUDA kernels (need H*W <= 64, W <= 8)")
+            raise RuntimeError(f"Bounce {H}x{W} is not supported by the CUDA kernels (need H*W <= 128, W <= 16)")
     dev = torch.device("cuda", torch.cuda.current_device())
     res = RolloutResult(n_games=n, game_id0=int(game_id0), seed=int(seed), stats=None)
     res.length = torch.empty(n, dtype=torch.int16, device=dev) if per_game else None
@@ -455,10 +625,94 @@ class BounceBatch:
     """n Bounce states as tensors: ``grid`` int8[n,H,W], ``player`` int8[n], ``winner`` int8[n],
     ``has_ended`` uint8[n].  ``moves()`` gives the legal actions, ``step()`` the transition."""
 
-    def __init__(self, grid, player, winner, has_ended, rules: int = 0, reward=None):
+    def __init__(self, grid, player, winner, has_ended, rules: int = 0, reward=None, ply=None):
         self.grid, self.player, self.winner, self.has_ended = grid, player, winner, has_ended
         self.rules = int(rules)
         self.reward = reward
+        #: int32[n] plies played so far (the draw index of ``sample_step``); None = 0 everywhere
+        self.ply = ply
+
+    def key(self):
+        """int64[n, 2]: a 128-bit hash key per state, equal iff grid, player and winner are equal
+        (reference helper.hpp:10-25; values unpinned)."""
+        torch = N.require_cuda()
+        n, H, W = self.grid.shape
+        keys = torch.empty((n, 2), dtype=torch.int64, device=self.grid.device)
+        N.check(N.lib().bgs_bounce_keys(H, W, n, N.ptr(self.grid.contiguous()), N.ptr(self.player.contiguous()),
+                                        N.ptr(self.winner.contiguous()), N.ptr(keys), N.stream_ptr(torch)))
+        return keys
+
+    def equal(self, other: "BounceBatch"):
+        if tuple(self.grid.shape) != tuple(other.grid.shape):
+            raise ValueError("batches of different shapes")
+        return (self.key() == other.key()).all(dim=1)
+
+    __eq__ = equal
+    __hash__ = None
+
+    def select(self, index) -> "BounceBatch":
+        pick = lambda t: None if t is None else t.index_select(0, index)
+        return BounceBatch(pick(self.grid), pick(self.player), pick(self.winner), pick(self.has_ended), self.rules,
+                           pick(self.reward), pick(self.ply))
+
+    def unique(self):
+        """``(batch of the distinct states, first int64[m], inverse int64[n])``."""
+        _, first, inverse = _keys_unique(self.key())
+        return self.select(first), first, inverse
+
+    def to_json(self) -> list[dict]:
+        """``[state.to_json() for state in batch]`` (tests/test_bounce.py:385-399)."""
+        g = self.grid.cpu().numpy().tolist()
+        p = self.player.cpu().numpy().tolist()
+        w = self.winner.cpu().numpy().tolist()
+        return [{"grid": g[i], "player": int(p[i]), "winner": int(w[i])} for i in range(self.n)]
+
+    @staticmethod
+    def from_json(values: list[dict], config=None, rules: int = 0) -> "BounceBatch":
+        """``[State.from_json(v, config) for v in values]`` as one batch.  ``has_ended`` is recovered as the
+        object API does: a winner, or (for a drawn game, winner -1) a side to move without any action."""
+        import numpy as np
+
+        torch = N.require_cuda()
+        grid = torch.from_numpy(np.array([v["grid"] for v in values], dtype=np.int8)).cuda()
+        player = torch.from_numpy(np.array([v["player"] for v in values], dtype=np.int8)).cuda()
+        winner = torch.from_numpy(np.array([v["winner"] for v in values], dtype=np.int8)).cuda()
+        b = BounceBatch(grid, player, winner, (winner >= 0).to(torch.uint8), rules)
+        _, _, count = b.moves()
+        b.has_ended = ((winner >= 0) | (count == 0)).to(torch.uint8)
+        return b
+
+    def sample_step(self, probs, seed: int, game_id0: int = 0, game_ids=None, draw_index=None):
+        """``random.choices(state.actions, weights)`` + ``sample_next_state()`` in one kernel (reference
+        textual/examples/arena.py:64-68).  ``probs`` float32[n, W, H*W]: ``probs[i, sx, ty*W + tx]`` is the weight of
+        moving the piece in column ``sx`` of the mover's source row to ``(tx, ty)``.  Draw index = ``draw_index``
+        or ``self.ply`` (0 if neither): equal weights replay ``bounce_rollout``.  Returns ``(next_batch,
+        move int32[n,4], status)``."""
+        torch = N.require_cuda()
+        n, H, W = self.grid.shape
+        dev = self.grid.device
+        probs = probs.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(probs.shape) != (n, W, H * W):
+            raise ValueError("probs must be float32[n, W, H*W]")
+        didx = draw_index if draw_index is not None else self.ply
+        didx = None if didx is None else didx.to(device=dev, dtype=torch.int32).contiguous()
+        gids = None if game_ids is None else game_ids.to(device=dev, dtype=torch.int64).contiguous()
+        grid = torch.empty_like(self.grid)
+        player = torch.empty_like(self.player)
+        winner = torch.empty_like(self.winner)
+        ended = torch.empty(n, dtype=torch.uint8, device=dev)
+        reward = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        move = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        N.check(
+            N.lib().bgs_bounce_sample_step(
+                H, W, self.rules, n, N.ptr(self.grid), N.ptr(self.player), N.ptr(self.winner), N.ptr(self.has_ended),
+                N.ptr(probs), int(seed) & 0xFFFFFFFFFFFFFFFF, int(game_id0), N.ptr(gids), N.ptr(didx), N.ptr(grid),
+                N.ptr(player), N.ptr(winner), N.ptr(ended), N.ptr(reward), N.ptr(move), N.ptr(status), N.stream_ptr(torch),
+            )
+        )
+        base = didx if didx is not None else torch.zeros(n, dtype=torch.int32, device=dev)
+        return BounceBatch(grid, player, winner, ended, self.rules, reward, base + (status == 0).to(torch.int32)), move, status
 
     @property
     def n(self) -> int:
@@ -514,4 +768,5 @@ class BounceBatch:
                 N.stream_ptr(torch),
             )
         )
-        return BounceBatch(grid, player, winner, ended, self.rules, reward), status
+        ply = None if self.ply is None else self.ply + (status == 0).to(torch.int32)
+        return BounceBatch(grid, player, winner, ended, self.rules, reward, ply), status

@@ -123,6 +123,20 @@ int bgs_connect_rollout_from(int H, int W, int K, uint64_t n_games, uint64_t gam
                              uint64_t* workspace, uint8_t* actions, uint8_t* length, int8_t* winner,
                              uint64_t* final_packed, int64_t* stats, void* stream);
 
+/* Packed positions: the State objects of connect.cpp:36-46 in 17 bytes (H*W <= 64) or 33 bytes each instead
+ * of H*W + 2 -- what a host sends over PCIe for rollouts from positions (State::from_json, connect.cpp:45-46).
+ *   packed uint64[n, bgs_connect_packed_words(H, W)]  the two bitboards in the packed-board format above
+ *   meta   uint8[n]   bit 0 = side to move, bits 1..2 = winner + 1 (0 = nobody has won)
+ * bgs_connect_pack writes them from reference-layout states (grid int8[n,H,W], player int8[n], winner optional
+ * int8[n]); bgs_connect_rollout_from_packed is bgs_connect_rollout_from on such positions (same draws, same
+ * outputs).  Boards of the bit-word kernels only (H*W <= 128, W <= 16, H <= 15); `packed` 16-byte aligned. */
+int bgs_connect_pack(int H, int W, uint64_t n, const int8_t* grid, const int8_t* player, const int8_t* winner,
+                     uint64_t* packed, uint8_t* meta, void* stream);
+int bgs_connect_rollout_from_packed(int H, int W, int K, uint64_t n_games, uint64_t game_id0, uint64_t seed,
+                                    const uint64_t* packed, const uint8_t* meta, uint64_t* workspace,
+                                    uint8_t* actions, uint8_t* length, int8_t* winner, uint64_t* final_packed,
+                                    int64_t* stats, void* stream);
+
 /* State::get_grid (connect.cpp:42) and State::get_reward (connect.cpp:41) for n packed boards:
  * grid optional int8[n,H,W] (-1 / 0 / 1); reward optional float[n,2] from winner int8[n]. */
 int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,
@@ -153,6 +167,30 @@ int bgs_connect_step(int H, int W, int K, uint64_t n, const int8_t* grid, const 
                      const int8_t* winner, const int32_t* action, int8_t* grid_out,
                      int8_t* player_out, int8_t* winner_out, uint8_t* ended_out, float* reward_out,
                      uint32_t* legal_out, int32_t* status, void* stream);
+
+/* bgs_connect_step with the action CHOSEN in the kernel from per-state weights: the agent loop of
+ * textual/examples/arena.py:64-68 (`random.choices(actions, weights)` then `sample_next_state`) for n states.
+ *   probs float[n, W]: weight of each column; columns that are not playable are ignored.  NaN / negative /
+ *   zero count as 0, +inf as FLT_MAX; if every playable column has weight 0 the choice is uniform.
+ *   q_c = (uint32)(w_c / max_c w_c * 65535 + 0.5) in IEEE single; r = the Philox draw of DESIGN.md 2 for
+ *   global id (game_ids ? game_ids[i] : game_id0 + i) and draw index t = draw_index ? draw_index[i] : number of
+ *   stones on the board; the action is the first playable column j with (q_0 + .. + q_j) * 2^32 > r * sum q.
+ *   Equal weights give exactly the uniform choice of bgs_connect_rollout (column mulhi32(r, n_legal)), so
+ *   stepping n boards from empty with constant probs replays the rollout kernel's games ply by ply.
+ * action_out optional int32[n] = chosen column (-1 where the state had ended; status[i] = 1 there). */
+int bgs_connect_sample_step(int H, int W, int K, uint64_t n, const int8_t* grid, const int8_t* player,
+                            const int8_t* winner, const float* probs, uint64_t seed, uint64_t game_id0,
+                            const uint64_t* game_ids, const int32_t* draw_index, int8_t* grid_out,
+                            int8_t* player_out, int8_t* winner_out, uint8_t* ended_out, float* reward_out,
+                            uint32_t* legal_out, int32_t* action_out, int32_t* status, void* stream);
+
+/* ==, <, hash of n states at once (helper.hpp:10-25 gives every reference object == != < <= > >= and
+ * __hash__; their values are not pinned): keys uint64[n, 2] (16-byte aligned), equal for two states of one
+ * configuration iff grid, player and winner are equal.  H*W <= 62: an exact, invertible packing
+ *   b0 | b1 << HW | player << 2HW | (winner + 1) << (2HW + 1),  bit r*W + c of b0 / b1 = stone of player 0 / 1
+ * on row r (from the bottom), column c.  Larger boards: a 128-bit hash (csrc/keys.cu states the function). */
+int bgs_connect_keys(int H, int W, uint64_t n, const int8_t* grid, const int8_t* player, const int8_t* winner,
+                     uint64_t* keys, void* stream);
 
 /* State::has_ended / get_actions / get_reward (connect.cpp:39,41,43) of n existing states. */
 int bgs_connect_query(int H, int W, uint64_t n, const int8_t* grid, const int8_t* winner,
@@ -191,6 +229,22 @@ int bgs_bounce_step(int H, int W, int rules, uint64_t n, const int8_t* grid, con
                     int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status,
                     void* stream);
 
+/* bgs_bounce_step with the move chosen in the kernel from per-state weights (arena.py:64-68):
+ * probs float[n, W, H*W], probs[i, sx, ty*W + tx] = weight of moving the piece in column sx of the mover's
+ * source row to (tx, ty); quantisation, draw and choice as bgs_connect_sample_step over the legal actions in
+ * canonical order (ascending sx, then target cell), RNG domain 1, t = draw_index ? draw_index[i] : 0.
+ * Equal weights give the uniform choice of bgs_bounce_rollout.  move_out optional int32[n,4] (-1s when the
+ * state had ended or the mover is blocked; status[i] = 1 there). */
+int bgs_bounce_sample_step(int H, int W, int rules, uint64_t n, const int8_t* grid, const int8_t* player,
+                           const int8_t* winner, const uint8_t* ended, const float* probs, uint64_t seed,
+                           uint64_t game_id0, const uint64_t* game_ids, const int32_t* draw_index,
+                           int8_t* grid_out, int8_t* player_out, int8_t* winner_out, uint8_t* ended_out,
+                           float* reward_out, int32_t* move_out, int32_t* status, void* stream);
+
+/* 128-bit hash keys of n Bounce states (see bgs_connect_keys; always the hash form). */
+int bgs_bounce_keys(int H, int W, uint64_t n, const int8_t* grid, const int8_t* player, const int8_t* winner,
+                    uint64_t* keys, void* stream);
+
 /* Uniform-random rollouts from grid0 (HOST pointer, int8[H,W]; it is the Config, bounce.cpp:26).
  * Action order for the uniform choice: ascending (sy, sx, ty, tx); RNG as for Connect with ctr[3]=1.
  * moves       optional uint8[n, max_plies, 2] (source cell, target cell), cell = y*W+x, 0xFF padded
@@ -203,7 +257,11 @@ int bgs_bounce_rollout(const int8_t* grid0_host, int H, int W, int rules, int ma
 
 /* The same loop from per-game positions (BounceBatch tensors): grid int8[n,H,W] (values 0..15), player
  * int8[n], winner_in optional int8[n] (-1 none), ended_in optional uint8[n]; all DEVICE pointers.  Draws
- * and `length` count the plies played in this rollout. */
+ * and `length` count the plies played in this rollout.
+ * A start position whose side to move has no action but is not flagged (winner_in / ended_in) ends at
+ * once with length 0 and NO winner (README.md:60 promises an action whenever has_ended is false; the
+ * blocked rule of Action::sample_next_state needs the move that led here).  Callers that want the blocked
+ * rule applied pass ended_in / winner_in from bgs_bounce_step, which evaluates it when the move is made. */
 int bgs_bounce_rollout_from(int H, int W, int rules, int max_plies, uint64_t n_games, uint64_t game_id0,
                             uint64_t seed, const int8_t* grid, const int8_t* player, const int8_t* winner_in,
                             const uint8_t* ended_in, uint8_t* moves, uint16_t* length, int8_t* winner,

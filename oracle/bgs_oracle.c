@@ -475,3 +475,99 @@ int64_t bgso_bounce_replay(const int8_t* grid0, int H, int W, int rules, int max
     free(g);
     return bad;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Weighted action choice and state keys: conventions of the B200 build itself (include/bgs_b200.h,
+ * bgs_connect_sample_step / bgs_bounce_sample_step / bgs_*_keys), restated independently so that the
+ * tests can check the kernels.  The reference's counterpart of the first is the caller's
+ * random.choices(actions, weights) (textual/examples/arena.py:64-68), of the second helper.hpp:10-25
+ * (== / < / hash on every object; values unpinned).
+ * ---------------------------------------------------------------------------------------------- */
+#pragma STDC FP_CONTRACT OFF
+static float sane_weight(float w) { return w > 0.0f ? (w < 3.402823466e+38f ? w : 3.402823466e+38f) : 0.0f; }
+static uint32_t quantize_weight(float w, float wmax) {
+    volatile float t = w / wmax;       /* volatile: separate IEEE single operations, no contraction */
+    volatile float u = t * 65535.0f;
+    volatile float v = u + 0.5f;
+    return (uint32_t)v;
+}
+
+/* index (into the `count` candidate weights) chosen by draw r: first j with (q_0+..+q_j)*2^32 > r*sum q */
+static int weighted_pick(const float* w, int count, uint32_t r) {
+    float wmax = 0.0f;
+    for (int j = 0; j < count; ++j) { const float s = sane_weight(w[j]); if (s > wmax) wmax = s; }
+    uint64_t total = 0;
+    for (int j = 0; j < count; ++j) total += wmax > 0.0f ? quantize_weight(sane_weight(w[j]), wmax) : 1u;
+    const uint64_t thresh = (uint64_t)r * total;
+    uint64_t cum = 0;
+    for (int j = 0; j < count; ++j) {
+        cum += wmax > 0.0f ? quantize_weight(sane_weight(w[j]), wmax) : 1u;
+        if ((cum << 32) > thresh) return j;
+    }
+    return -1;
+}
+
+/* Column chosen for one state from probs[W] (weights of the columns; illegal ones ignored), draw index t;
+ * -1 if the state has ended. */
+int bgso_connect_sample(const int8_t* grid, int H, int W, int winner, const float* probs, uint64_t seed,
+                        uint64_t gid, uint32_t t) {
+    int32_t cols[64];
+    float w[64];
+    const int n = bgso_connect_actions(grid, H, W, winner, cols);
+    if (n == 0) return -1;
+    for (int j = 0; j < n; ++j) w[j] = probs[cols[j]];
+    const int j = weighted_pick(w, n, bgso_draw(seed, gid, t, BGSO_DOMAIN_CONNECT));
+    return j < 0 ? -1 : cols[j];
+}
+
+/* Move chosen for one Bounce state from probs[W][H*W]; returns 0 and (sx,sy,tx,ty) in move4, or -1. */
+int bgso_bounce_sample(const int8_t* grid, int H, int W, int player, int ended, int rules, const float* probs,
+                       uint64_t seed, uint64_t gid, uint32_t t, int32_t* move4) {
+    const int cap = W * H * W;
+    int32_t* acts = (int32_t*)malloc(sizeof(int32_t) * 4 * (size_t)cap);
+    float* w = (float*)malloc(sizeof(float) * (size_t)cap);
+    const int n = bgso_bounce_actions(grid, H, W, player, ended, rules, acts, cap);
+    int rc = -1;
+    if (n > 0) {
+        for (int j = 0; j < n; ++j) w[j] = probs[acts[4 * j] * (H * W) + acts[4 * j + 3] * W + acts[4 * j + 2]];
+        const int j = weighted_pick(w, n, bgso_draw(seed, gid, t, BGSO_DOMAIN_BOUNCE));
+        if (j >= 0) { for (int k = 0; k < 4; ++k) move4[k] = acts[4 * j + k]; rc = 0; }
+    }
+    free(acts);
+    free(w);
+    return rc;
+}
+
+static uint64_t mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+
+/* key[2] of one state; game 1 = Connect (exact packing when H*W <= 62), 2 = Bounce (hash). */
+void bgso_state_key(int game, const int8_t* grid, int H, int W, int player, int winner, uint64_t* key) {
+    const int HW = H * W;
+    if (game == 1 && HW <= 62) {
+        unsigned __int128 k = 0;
+        for (int c = 0; c < HW; ++c) {
+            if (grid[c] == 0) k |= (unsigned __int128)1 << c;
+            else if (grid[c] == 1) k |= (unsigned __int128)1 << (HW + c);
+        }
+        k |= (unsigned __int128)(player & 1) << (2 * HW);
+        k |= (unsigned __int128)((winner + 1) & 3) << (2 * HW + 1);
+        key[0] = (uint64_t)k; key[1] = (uint64_t)(k >> 64);
+        return;
+    }
+    uint64_t h0 = 0x9E3779B97F4A7C15ull, h1 = 0xC2B2AE3D27D4EB4Full;
+    for (int c0 = 0; c0 < HW; c0 += 8) {
+        uint64_t w = 0;
+        for (int j = 0; j < 8 && c0 + j < HW; ++j) w |= (uint64_t)(uint8_t)grid[c0 + j] << (8 * j);
+        h0 = mix64(h0 ^ w);
+        h1 = mix64(h1 + w + 0x632BE59BD9B4E019ull);
+    }
+    const uint64_t tail = (uint64_t)(uint8_t)player | ((uint64_t)(uint8_t)winner << 8) | ((uint64_t)H << 16) |
+                          ((uint64_t)W << 24) | ((uint64_t)game << 32);
+    key[0] = mix64(h0 ^ tail);
+    key[1] = mix64(h1 + tail + 0x632BE59BD9B4E019ull);
+}

@@ -113,6 +113,15 @@ int64_t bgso_bounce_replay(const int8_t* grid0, int H, int W, int rules, int max
                            const uint8_t* moves, const uint16_t* length, const int8_t* winner,
                            const int8_t* final_grid, const float* reward, int64_t* first_bad);
 
+/* ---- conventions of the B200 build's own additions (include/bgs_b200.h), restated for the tests ---- */
+/* weighted action choice (bgs_connect_sample_step / bgs_bounce_sample_step) */
+int bgso_connect_sample(const int8_t* grid, int H, int W, int winner, const float* probs, uint64_t seed,
+                        uint64_t gid, uint32_t t);
+int bgso_bounce_sample(const int8_t* grid, int H, int W, int player, int ended, int rules, const float* probs,
+                       uint64_t seed, uint64_t gid, uint32_t t, int32_t* move4);
+/* 128-bit state keys (bgs_connect_keys: game 1, bgs_bounce_keys: game 2) */
+void bgso_state_key(int game, const int8_t* grid, int H, int W, int player, int winner, uint64_t* key);
+
 #ifdef __cplusplus
 }
 #endif

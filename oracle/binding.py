@@ -282,3 +282,30 @@ def bounce_replay(grid0, moves, length, winner=None, final_grid=None, reward=Non
         _p(reward, C.c_float), C.byref(first),
     )
     return int(bad), int(first.value)
+
+
+# ------------------------------------------------------- weighted choice / keys (B200-build conventions)
+def connect_sample(grid, winner: int, probs, seed: int, gid: int, t: int) -> int:
+    g = _grid8(grid)
+    pr = np.ascontiguousarray(probs, dtype=np.float32)
+    return int(lib().bgso_connect_sample(_p(g, C.c_int8), g.shape[0], g.shape[1], C.c_int(winner), _p(pr, C.c_float),
+                                         C.c_uint64(seed), C.c_uint64(gid), C.c_uint32(t)))
+
+
+def bounce_sample(grid, player: int, ended: bool, probs, seed: int, gid: int, t: int, rules: int = 0):
+    """(sx, sy, tx, ty) or None."""
+    g = _grid8(grid)
+    pr = np.ascontiguousarray(probs, dtype=np.float32)
+    mv = np.zeros(4, dtype=np.int32)
+    rc = lib().bgso_bounce_sample(_p(g, C.c_int8), g.shape[0], g.shape[1], C.c_int(player), C.c_int(int(ended)),
+                                  C.c_int(rules), _p(pr, C.c_float), C.c_uint64(seed), C.c_uint64(gid), C.c_uint32(t),
+                                  _p(mv, C.c_int32))
+    return None if rc != 0 else tuple(int(x) for x in mv)
+
+
+def state_key(game: int, grid, player: int, winner: int) -> tuple[int, int]:
+    g = _grid8(grid)
+    key = np.zeros(2, dtype=np.uint64)
+    lib().bgso_state_key(C.c_int(game), _p(g, C.c_int8), g.shape[0], g.shape[1], C.c_int(player), C.c_int(winner),
+                         _p(key, C.c_uint64))
+    return int(key[0]), int(key[1])

@@ -324,3 +324,34 @@ def test_small_and_ragged_batches_equal_oracle(oracle, n):
         np.testing.assert_array_equal(res.winner.cpu().numpy(), ref["winner"])
         np.testing.assert_array_equal(res.final_grid.cpu().numpy(), ref["final_grid"])
         np.testing.assert_array_equal(res.stats.cpu().numpy(), ref["stats"])
+
+
+def test_replay_one_million_default_games_at_512_plies(oracle):
+    """BASELINE.json configs[2] (default 9x6 board, max_plies 512): 1 Mi games of the rollout kernel, every
+    recorded move replayed through the oracle's transition on all host threads; the truncated games (cycles)
+    must be exactly the ones the oracle still finds running at 512 plies."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    from simulator import batch
+
+    n, cap = 2**20, 512
+    res = batch.bounce_rollout(GRID, n, 20261018, 0, max_plies=cap, moves=True, final_grid=True, reward=True)
+    torch.cuda.synchronize()
+    moves, length, winner = res.actions.cpu().numpy(), res.length.cpu().numpy().astype(np.uint16), res.winner.cpu().numpy()
+    fgrid, reward = res.final_grid.cpu().numpy(), res.reward.cpu().numpy()
+    oracle.lib()
+    workers = os.cpu_count() or 1
+    chunks = np.array_split(np.arange(n), workers * 8)
+
+    def check(ix):
+        lo, hi = int(ix[0]), int(ix[-1]) + 1
+        return oracle.bounce_replay(GRID, moves[lo:hi], length[lo:hi], winner[lo:hi], fgrid[lo:hi], reward[lo:hi])
+
+    with ThreadPoolExecutor(workers) as ex:
+        results = list(ex.map(check, chunks))
+    assert sum(r[0] for r in results) == 0, results
+    s = res.stats_dict()
+    assert s["games"] == n and s["wins0"] + s["wins1"] + s["draws"] + s["truncated"] == n
+    assert s["steps"] == int(length.astype(np.int64).sum()) and s["truncated"] == int((winner == -2).sum())
+    assert 27.0 < s["steps"] / n < 30.0

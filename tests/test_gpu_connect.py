@@ -570,3 +570,32 @@ def test_single_pass_export_stays_inside_its_buffers(oracle, cfg, misalign):
     np.testing.assert_array_equal(host[off["reward"]: off["reward"] + n * 8].view(np.float32).reshape(n, 2), ref["reward"])
     np.testing.assert_array_equal(host[off["length"]: off["length"] + n], ref["length"])
     np.testing.assert_array_equal(stats.cpu().numpy(), ref["stats"])
+
+
+def test_full_size_launch_equals_oracle(oracle):
+    """BASELINE.json configs[1] at full size: the statistics of the 16 Mi-game <6,7,4> launch (no trajectory)
+    equal the oracle's over the same global ids (all host threads; ctypes releases the GIL), and a 1 Mi-game
+    slice of length / winner is identical byte for byte."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    from simulator import batch
+
+    n, seed, gid0 = 16 * 2**20, 20261018, 3 * 2**33
+    res = batch.connect_rollout((6, 7, 4), n, seed, gid0, per_game=True)
+    torch.cuda.synchronize()
+    chunk = 2**18
+    oracle.lib()
+
+    def part(k):
+        return oracle.connect_rollout(6, 7, 4, chunk, gid0=gid0 + k * chunk, seed=seed, want_actions=False, want_grid=False)
+
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        parts = list(ex.map(part, range(n // chunk)))
+    want = np.sum([p["stats"] for p in parts], axis=0)
+    np.testing.assert_array_equal(res.stats.cpu().numpy(), want)
+    lo = 5 * 2**20  # a 1 Mi slice in the middle of the batch
+    length, winner = res.length.cpu().numpy(), res.winner.cpu().numpy()
+    for k in range(lo // chunk, (lo + 2**20) // chunk):
+        np.testing.assert_array_equal(length[k * chunk:(k + 1) * chunk], parts[k]["length"])
+        np.testing.assert_array_equal(winner[k * chunk:(k + 1) * chunk], parts[k]["winner"])

@@ -37,7 +37,9 @@ for _p in (ROOT, PRODUCT):
 
 CONFIG = (6, 7, 4)
 GAMES_PER_GPU = 16 * 2**20
+STRONG_GAMES = 64 * 2**20  # strong-scaling pass: this many games in total, whatever the number of GPUs
 OPS_PER_STEP = 100  # algorithmic thread-level 32-bit integer instructions per env-step
+BOUNCE_OPS_PER_STEP = 1400  # the Bounce budget fixed in round 1, kept for comparability
 SM_MAX_MHZ_FALLBACK = 1965.0
 METRIC = "connect4_6x7x4_random_rollout_env_steps_per_sec"
 UNIT = "env-steps/s"
@@ -296,12 +298,37 @@ def other_configs(torch, batch, N, dev):
     grid[1] = grid[7] = [1, 2, 3, 3, 2, 1]  # reference src/simulator/textual/bounce.py:66-78
     n = 4 * 2**20
     ms, steps = timed(lambda i: batch.bounce_rollout(grid, n, SEED, i * n, max_plies=512, stats=stats), stats)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak_g = sms * 128 * SM_MAX_MHZ_FALLBACK * 1e6 / 1e9
     out["bounce_default_9x6"] = {
         "games": n, "max_plies": 512, "ms_per_launch": ms, "env_steps_per_s": steps / ms * 1e3,
         "kernel": "bounce_rollout_slots_kernel<2, GeoCT<9,6>, 0, 64>",
-        "frac_of_int_issue_peak_at_1400_ops_per_step":
-            steps / ms * 1e3 * 1400 / (torch.cuda.get_device_properties(dev).multi_processor_count * 128 * SM_MAX_MHZ_FALLBACK * 1e6),
+        "roofline": {
+            "bound": "int_issue", "algorithmic_ops_per_env_step": BOUNCE_OPS_PER_STEP,
+            "achieved": steps / ms * 1e3 * BOUNCE_OPS_PER_STEP / 1e9, "peak": peak_g, "unit": "G thread-instr/s",
+            "frac": steps / ms * 1e3 * BOUNCE_OPS_PER_STEP / 1e9 / peak_g,
+            "peak_def": f"{sms} SMs x 4 schedulers x 32 lanes x {SM_MAX_MHZ_FALLBACK:.0f} MHz; budget of 1400 thread-level "
+                        "integer instructions per env-step fixed in round 1 (DESIGN.md 4)",
+            **bounce_counters(),
+        },
     }
+    try:  # configs[2] end to end: per-game results (2 bytes, packed) + statistics to pinned host memory, pipelined
+        bh = batch.HostRollout(grid, n, depth=2, packed=True, game="bounce", max_plies=512)
+        for _ in bh.stream(SEED, 0, 2):
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bsteps = 0
+        for st, _ in bh.stream(SEED, 100 * n, 4):
+            bsteps += int(st[N.STAT_STEPS])
+        dt = time.perf_counter() - t0
+        out["bounce_default_9x6"]["e2e"] = {
+            "value": bsteps / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": bh.d2h_bytes,
+            "ms_per_step": 1e3 * dt / 4, "api": "simulator.batch.HostRollout(game='bounce', packed=True).stream",
+        }
+        del bh
+    except Exception as e:
+        out["bounce_default_9x6"]["e2e"] = {"error": repr(e)}
     for cfg, bytes_per_game in (((8, 9, 5), 154), ((10, 12, 6), 250)):
         res = [None]
 
@@ -327,6 +354,49 @@ def other_configs(torch, batch, N, dev):
         res[0] = None
         torch.cuda.empty_cache()
     return out
+
+
+def bounce_counters():
+    path = os.path.join(ROOT, "profiles", "bounce_kernel_counters.json")
+    try:
+        d = json.load(open(path))
+        return {k: d[k] for k in ("measured_inst_per_step", "issue_active", "alu_pipe", "active_lanes", "source") if k in d}
+    except Exception:
+        return {}
+
+
+def headline_counters():
+    """Measured instruction mix of the dominant kernel from the committed ncu capture (profiles/): thread-level
+    instructions executed per env-step, issue-slot and ALU-pipe utilisation.  The 100-ops budget of the roofline is
+    an ALGORITHMIC figure; these say what the kernel physically executes."""
+    path = os.path.join(ROOT, "profiles", "headline_kernel_counters.json")
+    try:
+        d = json.load(open(path))
+        return {k: d[k] for k in ("measured_inst_per_step", "measured_thread_inst_per_step", "issue_active",
+                                  "alu_pipe", "active_lanes", "source") if k in d}
+    except Exception:
+        return {"measured_inst_per_step": None, "issue_active": None, "alu_pipe": None}
+
+
+def object_api_throughput(n_games: int = 12):
+    """The README loop (README.md:52-69) through the PRODUCT's object API: every property is a CUDA kernel with
+    a batch of one plus a synchronisation.  This is the drop-in's single-game cost -- far below the CPU
+    reference it replaces on this path; the batched entry points are the product."""
+    import random
+
+    from simulator.game import connect
+
+    random.seed(0)
+    config = connect.Config(*CONFIG)
+    steps = 0
+    t0 = time.perf_counter()
+    for _ in range(n_games):
+        state = config.sample_initial_state()
+        while not state.has_ended:
+            state = random.choice(state.actions).sample_next_state()
+            steps += 1
+        _ = state.reward
+    return steps / (time.perf_counter() - t0)
 
 
 def run_b200(args):
@@ -413,24 +483,25 @@ def run_b200(args):
     stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
 
     # ---- dominant kernel alone (rank-local, no collective): roofline -----------------------------
+    # K launches back to back inside ONE event bracket on the launching stream (no host synchronisation between
+    # them, so launch latency is hidden behind the previous kernel exactly as in the timed region above).
     barrier()
-    kms, ksteps = [], 0
+    stats.zero_()
+    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ka.record()
     for i in range(args.steps):
-        stats.zero_()
-        a, b = kev[i]
-        a.record()
         results[i % ROT] = batch.connect_rollout(CONFIG, n, SEED, (10_000 + i) * total + rank * n, per_game=True,
                                                  stats=stats, out=results[i % ROT])
-        b.record()
-        torch.cuda.synchronize()
-        kms.append(a.elapsed_time(b))
-        ksteps += int(stats[N.STAT_STEPS])
-    kernel_s = sum(kms) / 1e3
+    kb.record()
+    torch.cuda.synchronize()
+    kernel_s = ka.elapsed_time(kb) / 1e3
+    ksteps = int(stats[N.STAT_STEPS])
 
     # ---- end to end through the public API, pinned host results --------------------------------
     # simulator.batch.HostRollout.stream: every batch's per-game results and statistics are copied
-    # device->host into pinned memory inside the timed region (the copy of batch i overlaps the kernel
-    # of batch i+1); the loop consumes the host statistics of every batch.
+    # device->host into pinned memory inside the timed region as ONE copy per batch (the copy of batch i overlaps
+    # the kernel of batch i+1); the loop consumes the host statistics of every batch.  The pinned buffers are
+    # allocated on CPUs local to this rank's GPU.
     host = batch.HostRollout(CONFIG, n, depth=3, packed=True)  # one byte per game: length | (winner + 1) << 6
     for i in range(min(args.warmup, 3)):
         host.run(SEED, (20_000 + i) * total + rank * n)
@@ -455,26 +526,71 @@ def run_b200(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_n, op=dist.ReduceOp.SUM)
     e2e_value = int(e2e_n) / float(e2e_t)
+    d2h_gbps_rank = host.d2h_bytes * args.steps / e2e_reps[1][0] / 1e9
     # the same path with separate length / winner arrays (2 bytes per game), pipelined and synchronous
     host2 = batch.HostRollout(CONFIG, n, depth=3)
     host2.run(SEED, 39_000 * total + rank * n)
     for _ in host2.stream(SEED, 39_500 * total + rank * n * 4, 4):  # touch every buffer set before timing
         pass
+    barrier()
     t0 = time.perf_counter()
     un_steps = 0
     for st, _, _ in host2.stream(SEED, 40_000 * total + rank * n * args.steps, args.steps):
         un_steps += int(st[N.STAT_STEPS])
     e2e_unpacked_value = un_steps / (time.perf_counter() - t0)
+    barrier()
     t0 = time.perf_counter()
     sync_steps = 0
     for i in range(args.steps):
         st, _, _ = host2.run(SEED, (45_000 + i) * total + rank * n)
         sync_steps += int(st[N.STAT_STEPS])
     e2e_sync_value = sync_steps / (time.perf_counter() - t0)
+    aux = torch.tensor([e2e_unpacked_value, e2e_sync_value], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(aux, op=dist.ReduceOp.MIN)  # the slowest rank bounds the job
+    e2e_unpacked_value, e2e_sync_value = float(aux[0]), float(aux[1])
+    del host2
+
+    # ---- strong scaling + cross-rank determinism: a FIXED global id range is split
+    # over the ranks (shard_range), the statistics are all-reduced, and rank 0 replays the whole range alone
+    # (untimed) to check that N ranks give the single-rank answer for the same global ids.
+    strong_total = STRONG_GAMES
+    s_start, s_count = batch.shard_range(strong_total, rank, world)
+    sres = None
+    sstats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
+    sres = batch.connect_rollout(CONFIG, s_count, SEED, 60_000 * GAMES_PER_GPU + s_start, per_game=True, stats=sstats, out=sres)
+    barrier()
+    strong_reps = []
+    for rep in range(3):
+        sstats.zero_()
+        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sa.record()
+        sres = batch.connect_rollout(CONFIG, s_count, SEED, 60_000 * GAMES_PER_GPU + s_start, per_game=True, stats=sstats,
+                                     out=sres)
+        if world > 1:
+            dist.all_reduce(sstats, op=dist.ReduceOp.SUM)
+        sb.record()
+        torch.cuda.synchronize()
+        st_ = torch.tensor(sa.elapsed_time(sb) / 1e3, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(st_, op=dist.ReduceOp.MAX)
+        strong_reps.append(float(st_))
+    strong_s = sorted(strong_reps)[1]
+    strong_steps = int(sstats[N.STAT_STEPS])
+    stats_equal = None
+    if rank == 0:
+        single = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
+        del sres
+        batch.connect_rollout(CONFIG, strong_total, SEED, 60_000 * GAMES_PER_GPU, per_game=False, stats=single)
+        torch.cuda.synchronize()
+        stats_equal = bool(torch.equal(single, sstats))
 
     # ---- end to end with REAL tensor inputs: rollouts that continue from caller-supplied positions
-    # (leaf evaluation of a tree search).  Every step copies 4 Mi positions host->device from pinned
-    # memory (grid int8[n,6,7] + player + winner = 44 B each) and the results device->host.
+    # (leaf evaluation of a tree search), simulator.batch.HostLeafRollout.  Every step copies 4 Mi positions
+    # host->device from pinned memory as packed records (two bitboards + a meta byte = 17 B each, instead of the
+    # 44 B of an int8 grid + player + winner) and the packed results (1 B per game) + statistics device->host;
+    # three batches are in flight (H2D of batch i+1, kernel of batch i, D2H of batch i-1 overlap).
     fp = None
     if world == 1:
         try:
@@ -483,38 +599,40 @@ def run_b200(args):
             gen = torch.Generator(device="cuda").manual_seed(1)
             for _ in range(10):  # 10 random plies: mid-game positions
                 b0, _ = b0.step(torch.randint(0, CONFIG[1], (n_pos,), device="cuda", generator=gen))
-            h_grid, h_player, h_winner = (t.cpu().pin_memory() for t in (b0.grid, b0.player, b0.winner))
-            d_grid, d_player, d_winner = torch.empty_like(b0.grid), torch.empty_like(b0.player), torch.empty_like(b0.winner)
-            o_len = torch.empty(n_pos, dtype=torch.uint8).pin_memory()
-            o_win = torch.empty(n_pos, dtype=torch.int8).pin_memory()
-            o_stats = torch.zeros(N.STATS_LEN, dtype=torch.int64).pin_memory()
-            fstats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device=dev)
-            fres, fsteps = None, 0
-            reps = max(3, min(args.steps, 10))
-            for i in range(reps + 2):
-                if i == 2:
+            pk = b0.pack()
+            leaf = batch.HostLeafRollout(CONFIG, n_pos, depth=3)
+            for slot in range(leaf.depth):
+                hp, hm = leaf.host_inputs(slot)
+                hp.copy_(pk.packed.cpu())
+                hm.copy_(pk.meta.cpu())
+            del b0, pk
+            reps = max(6, min(args.steps, 20))
+            fsteps, t0, tickets = 0, None, []
+            for i in range(reps + 3):
+                if i == 3:
+                    for tk in tickets:
+                        leaf.result(tk)
+                    tickets = []
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
                     fsteps = 0
-                d_grid.copy_(h_grid, non_blocking=True)
-                d_player.copy_(h_player, non_blocking=True)
-                d_winner.copy_(h_winner, non_blocking=True)
-                fstats.zero_()
-                start = batch.ConnectBatch(CONFIG, d_grid, d_player, d_winner, has_ended=False)
-                fres = batch.connect_rollout(CONFIG, n_pos, SEED, 50_000 * total + i * n_pos, per_game=True,
-                                             stats=fstats, out=fres, start=start)
-                o_len.copy_(fres.length, non_blocking=True)
-                o_win.copy_(fres.winner, non_blocking=True)
-                o_stats.copy_(fstats, non_blocking=True)
-                torch.cuda.synchronize()
-                fsteps += int(o_stats[N.STAT_STEPS])
+                if len(tickets) == leaf.depth:
+                    st, _ = leaf.result(tickets.pop(0))
+                    fsteps += int(st[N.STAT_STEPS])
+                tickets.append(leaf.submit(SEED, 50_000 * total + i * n_pos))
+            for tk in tickets:
+                st, _ = leaf.result(tk)
+                fsteps += int(st[N.STAT_STEPS])
             dt = time.perf_counter() - t0
             fp = {
                 "value": fsteps / dt, "unit": UNIT, "positions_per_step": n_pos,
-                "h2d_bytes_per_step": n_pos * (CONFIG[0] * CONFIG[1] + 2), "d2h_bytes_per_step": n_pos * 2 + N.STATS_LEN * 8,
-                "ms_per_step": 1e3 * dt / reps,
-                "api": "simulator.batch.connect_rollout(start=ConnectBatch) -> bgs_connect_rollout_from, synchronous",
+                "h2d_bytes_per_step": leaf.h2d_bytes, "d2h_bytes_per_step": leaf.d2h_bytes,
+                "ms_per_step": 1e3 * dt / reps, "h2d_GBps": leaf.h2d_bytes * reps / dt / 1e9,
+                "api": "simulator.batch.HostLeafRollout.submit/result -> bgs_connect_rollout_from_packed + "
+                       "bgs_connect_pack_results, 3 batches in flight; positions as ConnectBatch.pack() records "
+                       "(17 B each; round 1 sent int8 grids, 44 B each: 1.16e10)",
             }
+            del leaf
         except Exception as e:  # an auxiliary figure must never break the bench line
             fp = {"error": repr(e)}
 
@@ -546,13 +664,26 @@ def run_b200(args):
                 "d2h_bytes_per_step": host.d2h_bytes * world,
                 "api": "simulator.batch.HostRollout(packed=True).stream -> bgs_connect_rollout + bgs_connect_pack_results; "
                        "every batch's per-game results (1 byte: length | (winner+1)<<6) and statistics copied to pinned "
-                       "host memory, copy of batch i overlapping the kernels of the next batches; median of 3 repetitions "
-                       "of K steps (wall clock, max over ranks)",
+                       "host memory as ONE copy per batch (pinned pages allocated on CPUs local to the GPU), the copy of "
+                       "batch i overlapping the kernels of the next batches; median of 3 repetitions of K steps (wall "
+                       "clock, max over ranks)",
                 "repetitions_this_rank": [st_ / t_ for t_, st_ in e2e_reps],
+                "d2h_GBps_this_rank": d2h_gbps_rank,
+                "pinned_memory_numa_local_cpus": host.numa_cpus,
                 "two_arrays_value": e2e_unpacked_value * world,
                 "synchronous_call_value": e2e_sync_value * world,
                 "from_positions": fp,
             },
+            "strong_scaling": {
+                "global_games": strong_total, "games_this_rank": s_count, "seconds": strong_s,
+                "strong_scaling_value": strong_steps / strong_s, "unit": UNIT,
+                "stats_equal_to_single_rank": stats_equal,
+                "note": "a fixed range of global game ids split over the ranks (contiguous shards), statistics "
+                        "all-reduced inside the timed bracket; rank 0 then replays the whole range alone and compares "
+                        "the 256 statistics words (SURVEY.md 8d C5, 4.5 T4); median of 3, max over ranks",
+            },
+            "strong_scaling_value": strong_steps / strong_s,
+            "stats_equal_to_single_rank": stats_equal,
             "gpu_launches": args.steps,
             "gpu_launches_note": "1 connect_rollout_lut_kernel per step in each timed region (value, kernel-only, e2e; "
                              "the e2e region adds 1 pack_results_kernel per step)",
@@ -565,6 +696,8 @@ def run_b200(args):
                 "algorithmic_ops_per_env_step": OPS_PER_STEP,
                 "peak_def": f"{sms} SMs x 4 schedulers x 32 lanes x {f_mhz:.0f} MHz (median SM clock sampled by NVML "
                             "during the timed region); the path is register-resident, HBM is not the bound",
+                "timing": "K launches back to back in one CUDA-event bracket on the launching stream",
+                **headline_counters(),
                 "hbm_write_GBps": (2 * n + 2048) * args.steps / kernel_s / 1e9,
                 "hbm_peak_GBps_measured": (json.load(open(peaks_path)).get("hbm_gbs") if os.path.exists(peaks_path) else 6650.0),
             },
@@ -572,6 +705,12 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             cb = cpu_rollout_throughput(args.cpu_seconds)
             cb.pop("seconds"), cb.pop("steps")
+            try:
+                cb["object_api_steps_per_s"] = object_api_throughput()
+                cb["object_api_note"] = ("README.md:52-69 loop through simulator.game.connect ON THE GPU (one kernel + one "
+                                         "synchronisation per property, batch of one): the drop-in's single-game cost")
+            except Exception as e:
+                cb["object_api_error"] = repr(e)
             try:
                 cb["python_api_1thread_steps_per_s"] = python_api_throughput(200)
                 v, procs = python_api_all_cores(150)

@@ -664,6 +664,16 @@ bounce_step_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __rest
     warp_copy_bytes(reinterpret_cast<uint8_t*>(grid_out) + g0 * (unsigned)HW, s_stage[warp], span, lane, vec);
 }
 
+// length (< 16384) and winner of every game in one 16-bit word: bits 0..13 length, bits 14..15 winner + 2
+// (0 truncated, 1 draw, 2 player 0, 3 player 1): 2 instead of 3 bytes per game over PCIe.
+__global__ void __launch_bounds__(256)
+bounce_pack_results_kernel(unsigned long long n, const uint16_t* __restrict__ length, const int8_t* __restrict__ winner,
+                           uint16_t* __restrict__ packed) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        packed[i] = (uint16_t)((length[i] & 0x3FFFu) | (((unsigned)(winner[i] + 2) & 3u) << 14));
+}
+
 // boards that need 128-bit words
 static bool wide_board(int H, int W) { return W > 8 || H * W > 64; }
 
@@ -858,6 +868,19 @@ extern "C" int bgs_bounce_rollout_from(int H, int W, int rules, int max_plies, u
     if (!grid || !player) return set_error(BGS_EINVAL, "bounce_rollout_from: null required pointer");
     return bounce_rollout_impl(nullptr, grid, player, winner_in, ended_in, H, W, rules, max_plies, n_games, game_id0,
                                seed, moves, length, winner, final_grid, reward, stats, stream_);
+}
+
+extern "C" int bgs_bounce_pack_results(uint64_t n, const uint16_t* length, const int8_t* winner, uint16_t* packed,
+                                       void* stream_) {
+    if (!length || !winner || !packed) return set_error(BGS_EINVAL, "bounce_pack_results: null pointer");
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    unsigned long long blocks = (n + 255ull) / 256ull;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    bounce_pack_results_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(n, length, winner, packed);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
 }
 
 extern "C" int bgs_bounce_rollout_host(int device, const int8_t* grid0, int H, int W, int rules, int max_plies,

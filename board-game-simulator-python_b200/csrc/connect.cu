@@ -1538,6 +1538,9 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
 
 // length (<= 63) and winner of every game in one byte: bits 0..5 length, bits 6..7 winner + 1.
 // Halves the device->host traffic of the per-game results (16 bytes per thread in, 16 out).
+// WIDE (boards of 64..127 cells, games from the empty board): bits 0..6 length, bit 7 = draw; the winner of a
+// decided game follows from the parity of its length (odd = player 0).
+template <bool WIDE>
 __global__ void __launch_bounds__(256)
 pack_results_kernel(unsigned long long n, const uint8_t* __restrict__ length, const int8_t* __restrict__ winner,
                     uint8_t* __restrict__ packed) {
@@ -1549,13 +1552,15 @@ pack_results_kernel(unsigned long long n, const uint8_t* __restrict__ length, co
         // per byte: (winner + 1) << 6 | length
         // (a winner byte of -1 is 0xFF: reduce it to 2 bits BEFORE adding 1, or the carry crosses into the next byte)
         auto f = [](uint32_t lw, uint32_t ww) {
+            if (WIDE) return (ww & 0x80808080u) | (lw & 0x7F7F7F7Fu);  // winner -1 = 0xFF: its sign bit is the draw flag
             return ((((ww & 0x03030303u) + 0x01010101u) & 0x03030303u) << 6) | (lw & 0x3F3F3F3Fu);
         };
         reinterpret_cast<uint4*>(packed)[v] = make_uint4(f(l.x, w.x), f(l.y, w.y), f(l.z, w.z), f(l.w, w.w));
     }
     if (blockIdx.x == 0)
         for (unsigned long long i = nvec * 16ull + threadIdx.x; i < n; i += blockDim.x)
-            packed[i] = (uint8_t)((((uint32_t)(winner[i] + 1) & 3u) << 6) | (length[i] & 63u));
+            packed[i] = WIDE ? (uint8_t)(((uint8_t)winner[i] & 0x80u) | (length[i] & 0x7Fu))
+                             : (uint8_t)((((uint32_t)(winner[i] + 1) & 3u) << 6) | (length[i] & 63u));
 }
 
 __global__ void __launch_bounds__(256)
@@ -2222,8 +2227,19 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
                                          reinterpret_cast<uint8_t*>(grids), (cudaStream_t)stream_, actions);
 }
 
+static int pack_results_impl(bool wide, uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed, void* stream_);
+
 extern "C" int bgs_connect_pack_results(uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed,
                                         void* stream_) {
+    return pack_results_impl(false, n, length, winner, packed, stream_);
+}
+
+extern "C" int bgs_connect_pack_results_wide(uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed,
+                                             void* stream_) {
+    return pack_results_impl(true, n, length, winner, packed, stream_);
+}
+
+static int pack_results_impl(bool wide, uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed, void* stream_) {
     if (!length || !winner || !packed) return set_error(BGS_EINVAL, "connect_pack_results: null pointer");
     if ((((uintptr_t)length | (uintptr_t)winner | (uintptr_t)packed) & 15u) != 0)
         return set_error(BGS_EINVAL, "connect_pack_results: pointers must be 16-byte aligned");
@@ -2233,7 +2249,8 @@ extern "C" int bgs_connect_pack_results(uint64_t n, const uint8_t* length, const
     const unsigned long long cap = (unsigned long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    pack_results_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(n, length, winner, packed);
+    if (wide) pack_results_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(n, length, winner, packed);
+    else pack_results_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(n, length, winner, packed);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "bgs_connect_export": (C.c_int, [_i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "bgs_connect_trajectory_grids": (C.c_int, [_i32, _i32, _u64, _vp, _vp, _vp, _vp]),
     "bgs_connect_pack_results": (C.c_int, [_u64, _vp, _vp, _vp, _vp]),
+    "bgs_connect_pack_results_wide": (C.c_int, [_u64, _vp, _vp, _vp, _vp]),
+    "bgs_bounce_pack_results": (C.c_int, [_u64, _vp, _vp, _vp, _vp]),
     "bgs_connect_step": (C.c_int, [_i32, _i32, _i32, _u64] + [_vp] * 12),
     "bgs_connect_query": (C.c_int, [_i32, _i32, _u64] + [_vp] * 6),
     "bgs_connect_rollout_host": (C.c_int, [_i32, _i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 6),

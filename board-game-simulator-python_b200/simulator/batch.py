@@ -15,6 +15,7 @@ The loop being replaced is the reference's README.md:49-72::
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Any
 
@@ -231,90 +232,206 @@ def connect_trajectory_grids(config, actions, length, out=None):
     return out
 
 
+def gpu_local_cpus(device_index: int):
+    """The CPUs NVML reports as local to GPU ``device_index`` (same NUMA node / PCIe root), or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus or None
+    except Exception:
+        return None
+
+
+class _numa_local:
+    """Context manager: run the enclosed allocations on CPUs local to the GPU, so that pinned host pages
+    (allocated where the calling thread runs) land on the GPU's NUMA node; the caller's affinity is restored."""
+
+    def __init__(self, device_index: int, enabled: bool = True):
+        self.cpus = gpu_local_cpus(device_index) if enabled else None
+        self.saved = None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except OSError:
+                self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except OSError:
+                pass
+        return False
+
+
 class HostRollout:
     """End-to-end rollouts with results in pinned host memory (what bench.py's ``e2e`` times).
 
     A rollout from the empty board has no tensor input -- its inputs are the scalars (config, n_games,
     seed, game_id0), which travel in the kernel launch parameters -- so the host->device side is 0
-    bytes; per-game ``length`` / ``winner`` and the statistics vector come back device->host into
-    pinned memory for EVERY batch.
+    bytes; the per-game results and the statistics vector come back device->host into pinned memory for
+    EVERY batch, as ONE copy: the device-side record of a batch is ``[per-game results | int64[256]
+    statistics]`` in one buffer (the rollout kernel accumulates its statistics straight into the tail).
+
+    ``game="connect"`` (``config`` = (H, W, K) or a Config) or ``game="bounce"`` (``config`` = the start grid).
+    ``packed=True`` shrinks the per-game results on the device before they cross PCIe:
+      Connect, at most 63 cells: 1 byte ``length | (winner + 1) << 6``; 64..127 cells: 1 byte
+      ``length | draw << 7`` (a decided game's winner is the parity of its length); Bounce: 2 bytes
+      ``length | (winner + 2) << 14``.  ``HostRollout.unpack`` / ``unpack_results`` recover (length, winner).
+    ``packed=False``: length and winner arrays as they are (Connect 2, Bounce 3 bytes per game).
 
     ``run`` is the synchronous call (kernel, then copy).  ``stream`` is the pipelined iterator: the
     device->host copy of batch i runs on a copy stream while the kernel of batch i+1 runs on the
-    compute stream (two buffer sets), which hides the PCIe time behind the kernel.
+    compute stream (``depth`` buffer sets), which hides the PCIe time behind the kernel.  The pinned
+    buffers are allocated on CPUs local to the GPU (NUMA node of its PCIe root; ``numa_local=False`` disables).
     """
 
-    def __init__(self, config, n_games: int, depth: int = 2, packed: bool = False):
+    def __init__(self, config, n_games: int, depth: int = 2, packed: bool = False, game: str = "connect",
+                 max_plies: int = 512, rules: int = 0, numa_local: bool = True):
         torch = N.require_cuda()
         self.torch = torch
         self.config = config
-        self.n = int(n_games)
+        self.game = game
+        self.n = n = int(n_games)
         self.depth = int(depth)
-        H, W, _ = _hwk(config)
-        if packed and H * W > 63:
-            raise ValueError("packed per-game results need a board of at most 63 cells")
-        #: packed=True: ONE byte per game crosses PCIe (length | (winner + 1) << 6, packed on the device by
-        #: bgs_connect_pack_results); run() / stream() then yield (stats, result) and HostRollout.unpack
-        #: recovers (length, winner) on the host
         self.packed = bool(packed)
+        self.max_plies, self.rules = int(max_plies), int(rules)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if game == "connect":
+            H, W, _ = _hwk(config)
+            if packed and H * W > 127:
+                raise ValueError("packed per-game results need a board of at most 127 cells")
+            self.mode = ("u8" if H * W <= 63 else "u8wide") if packed else "connect2"
+        elif game == "bounce":
+            if packed and self.max_plies > 16383:
+                raise ValueError("packed Bounce results need max_plies < 16384")
+            self.mode = "u16" if packed else "bounce3"
+        else:
+            raise ValueError("game must be 'connect' or 'bounce'")
+        n16 = (n + 15) // 16 * 16
+        #: byte offsets of the pieces of one batch record
+        if self.mode in ("u8", "u8wide"):
+            self.off = {"result": 0}
+            body = n16
+        elif self.mode == "connect2":
+            self.off = {"length": 0, "winner": n16}
+            body = 2 * n16
+        elif self.mode == "u16":
+            self.off = {"result": 0}
+            body = 2 * n16
+        else:
+            self.off = {"length": 0, "winner": 2 * n16}
+            body = 3 * n16
+        self.off["stats"] = body
+        self.nbytes = body + N.STATS_LEN * 8
         self.sets = []
-        for _ in range(self.depth):
-            self.sets.append({
-                "length_host": None if packed else torch.empty(self.n, dtype=torch.uint8).pin_memory(),
-                "winner_host": None if packed else torch.empty(self.n, dtype=torch.int8).pin_memory(),
-                "result_host": torch.empty(self.n, dtype=torch.uint8).pin_memory() if packed else None,
-                "result_dev": torch.empty(self.n, dtype=torch.uint8, device="cuda") if packed else None,
-                "stats_host": torch.zeros(N.STATS_LEN, dtype=torch.int64).pin_memory(),
-                "stats_dev": torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda"),
-                "res": None,
-                "computed": torch.cuda.Event(),
-                "copied": torch.cuda.Event(),
-            })
+        with _numa_local(dev.index, numa_local) as pin:
+            self.numa_cpus = len(pin.cpus) if pin.cpus else None
+            for _ in range(self.depth):
+                rec_dev = torch.zeros(self.nbytes, dtype=torch.uint8, device=dev)
+                rec_host = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
+                self.sets.append({
+                    "rec_dev": rec_dev, "rec_host": rec_host,
+                    "stats_dev": rec_dev[body:].view(torch.int64),
+                    "res": None,
+                    "computed": torch.cuda.Event(),
+                    "copied": torch.cuda.Event(),
+                })
         self.copy_stream = torch.cuda.Stream()
         self.h2d_bytes = 0
-        self.d2h_bytes = self.n * (1 if packed else 2) + N.STATS_LEN * 8
+        self.d2h_bytes = self.nbytes
+
+    # -- views of one record ---------------------------------------------------------------------------------
+    def _view(self, rec, name, dtype, count):
+        torch = self.torch
+        o = self.off[name]
+        return rec[o: o + count * torch.empty(0, dtype=dtype).element_size()].view(dtype)
 
     @staticmethod
     def unpack(result):
-        """(length uint8, winner int8) from packed per-game results (host or device tensor)."""
+        """(length uint8, winner int8) from 1-byte packed Connect results of a board of at most 63 cells."""
         import torch
 
         return result & 63, (result >> 6).to(torch.int8) - 1
 
+    def unpack_results(self, result):
+        """(length, winner) from this object's packed per-game results (host or device tensor)."""
+        torch = self.torch
+        if self.mode == "u8":
+            return self.unpack(result)
+        if self.mode == "u8wide":
+            length = result & 127
+            decided = torch.where((length & 1) == 1, 0, 1).to(torch.int8)
+            return length, torch.where(result >= 128, torch.full_like(decided, -1), decided)
+        if self.mode == "u16":
+            r = result.to(torch.int32) & 0xFFFF
+            return (r & 0x3FFF).to(torch.int16), ((r >> 14) - 2).to(torch.int8)
+        raise ValueError("results are not packed")
+
     def _launch(self, s, seed, game_id0):
         torch = self.torch
+        n = self.n
         s["stats_dev"].zero_()
-        s["res"] = connect_rollout(self.config, self.n, seed, game_id0, per_game=True, stats=s["stats_dev"], out=s["res"])
-        if self.packed:
-            N.check(N.lib().bgs_connect_pack_results(self.n, N.ptr(s["res"].length), N.ptr(s["res"].winner),
-                                                      N.ptr(s["result_dev"]), N.stream_ptr(torch)))
+        rec = s["rec_dev"]
+        L = N.lib()
+        if self.game == "connect":
+            out = s["res"]
+            if out is None and self.mode == "connect2":  # the kernel writes straight into the record
+                out = RolloutResult(n_games=n, game_id0=0, seed=0, stats=None,
+                                    length=self._view(rec, "length", torch.uint8, n),
+                                    winner=self._view(rec, "winner", torch.int8, n))
+            s["res"] = connect_rollout(self.config, n, seed, game_id0, per_game=True, stats=s["stats_dev"], out=out)
+            if self.mode in ("u8", "u8wide"):
+                fn = L.bgs_connect_pack_results if self.mode == "u8" else L.bgs_connect_pack_results_wide
+                N.check(fn(n, N.ptr(s["res"].length), N.ptr(s["res"].winner), N.ptr(rec), N.stream_ptr(torch)))
+        else:
+            s["res"] = bounce_rollout(self.config, n, seed, game_id0, max_plies=self.max_plies, rules=self.rules,
+                                      per_game=True, stats=s["stats_dev"])
+            if self.mode == "u16":
+                N.check(L.bgs_bounce_pack_results(n, N.ptr(s["res"].length), N.ptr(s["res"].winner), N.ptr(rec),
+                                                  N.stream_ptr(torch)))
+            else:
+                self._view(rec, "length", torch.int16, n).copy_(s["res"].length)
+                self._view(rec, "winner", torch.int8, n).copy_(s["res"].winner)
         s["computed"].record()
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(s["computed"])
-            if self.packed:
-                s["result_host"].copy_(s["result_dev"], non_blocking=True)
-            else:
-                s["length_host"].copy_(s["res"].length, non_blocking=True)
-                s["winner_host"].copy_(s["res"].winner, non_blocking=True)
-            s["stats_host"].copy_(s["stats_dev"], non_blocking=True)
+            s["rec_host"].copy_(rec, non_blocking=True)  # ONE device->host copy per batch
             s["copied"].record()
 
     def _out(self, s):
-        if self.packed:
-            return s["stats_host"], s["result_host"]
-        return s["stats_host"], s["length_host"], s["winner_host"]
+        torch = self.torch
+        h = s["rec_host"]
+        stats = h[self.off["stats"]:].view(torch.int64)
+        if self.mode in ("u8", "u8wide"):
+            return stats, self._view(h, "result", torch.uint8, self.n)
+        if self.mode == "u16":
+            return stats, self._view(h, "result", torch.int16, self.n)
+        ldt = torch.uint8 if self.game == "connect" else torch.int16
+        return stats, self._view(h, "length", ldt, self.n), self._view(h, "winner", torch.int8, self.n)
 
     def run(self, seed: int, game_id0: int = 0):
-        """One end-to-end rollout; returns (stats, length, winner) as pinned host tensors (synchronised)."""
+        """One end-to-end rollout; returns ``(stats, length, winner)`` -- or ``(stats, result)`` when packed -- as
+        views of the pinned host record (synchronised)."""
         s = self.sets[0]
         self._launch(s, seed, game_id0)
         s["copied"].synchronize()
         return self._out(s)
 
     def stream(self, seed: int, game_id0: int, n_batches: int):
-        """Yields ``(stats, length, winner)`` host tensors for ``n_batches`` consecutive batches of
-        ``n_games`` games (global ids ``game_id0 + i*n_games ...``).  A yielded set is valid until the
-        next-but-one ``next()``."""
+        """Yields the host tensors of ``run`` for ``n_batches`` consecutive batches of ``n_games`` games (global
+        ids ``game_id0 + i*n_games ...``).  A yielded set is valid until the next-but-one ``next()``."""
         torch = self.torch
         pending = []
         for i in range(n_batches):
@@ -330,6 +447,90 @@ class HostRollout:
         for done in pending:
             done["copied"].synchronize()
             yield self._out(done)
+
+
+class HostLeafRollout:
+    """End-to-end leaf evaluation: positions in pinned HOST memory -> rollouts -> per-game results in pinned
+    host memory, pipelined (``State.from_json`` positions + the README.md:49-72 loop, for a tree search).
+
+    Positions travel as :class:`ConnectPacked` records (two bitboards + a meta byte: 17 bytes per 6x7 position
+    instead of 44); results come back as one packed byte per game + the statistics vector.  ``submit`` enqueues
+    one batch (host->device copy, rollout, device->host copy on three streams) and returns a ticket;
+    ``result(ticket)`` waits for it.  With ``depth`` tickets in flight the H2D copy of batch i+1, the kernel of
+    batch i and the D2H copy of batch i-1 overlap."""
+
+    def __init__(self, config, n_positions: int, depth: int = 3, numa_local: bool = True):
+        torch = N.require_cuda()
+        self.torch, self.config, self.n, self.depth = torch, config, int(n_positions), int(depth)
+        H, W, _ = _hwk(config)
+        if H * W > 63:
+            raise ValueError("HostLeafRollout packs results in one byte: boards of at most 63 cells")
+        n = self.n
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pw = N.lib().bgs_connect_packed_words(H, W)
+        n16 = (n + 15) // 16 * 16
+        self.in_bytes = n * pw * 8 + n16
+        self.out_off_stats = n16
+        self.out_bytes = n16 + N.STATS_LEN * 8
+        self.sets = []
+        with _numa_local(dev.index, numa_local):
+            for _ in range(self.depth):
+                in_dev = torch.empty(self.in_bytes, dtype=torch.uint8, device=dev)
+                out_dev = torch.zeros(self.out_bytes, dtype=torch.uint8, device=dev)
+                self.sets.append({
+                    "in_host": torch.empty(self.in_bytes, dtype=torch.uint8).pin_memory(),
+                    "out_host": torch.zeros(self.out_bytes, dtype=torch.uint8).pin_memory(),
+                    "in_dev": in_dev, "out_dev": out_dev,
+                    "packed": in_dev[: n * pw * 8].view(torch.int64).view(n, pw),
+                    "meta": in_dev[n * pw * 8: n * pw * 8 + n],
+                    "stats_dev": out_dev[n16:].view(torch.int64),
+                    "res": None, "loaded": torch.cuda.Event(), "computed": torch.cuda.Event(), "copied": torch.cuda.Event(),
+                })
+        self.h2d_stream, self.d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+        self.h2d_bytes, self.d2h_bytes = self.in_bytes, self.out_bytes
+        self._next = 0
+
+    def host_inputs(self, ticket_slot: int):
+        """(packed int64[n, words], meta uint8[n]) views of the pinned INPUT record of a slot: fill them (e.g.
+        from ``ConnectBatch.pack()`` copied to the host) before ``submit``."""
+        s = self.sets[ticket_slot]
+        n = self.n
+        pw = s["packed"].shape[1]
+        h = s["in_host"]
+        return h[: n * pw * 8].view(self.torch.int64).view(n, pw), h[n * pw * 8: n * pw * 8 + n]
+
+    def submit(self, seed: int, game_id0: int, slot: int | None = None) -> int:
+        torch = self.torch
+        if slot is None:
+            slot = self._next
+            self._next = (self._next + 1) % self.depth
+        s = self.sets[slot]
+        with torch.cuda.stream(self.h2d_stream):
+            self.h2d_stream.wait_event(s["computed"])  # the previous rollout that read in_dev is done
+            s["in_dev"].copy_(s["in_host"], non_blocking=True)
+            s["loaded"].record()
+        cur = torch.cuda.current_stream()
+        cur.wait_event(s["loaded"])
+        cur.wait_event(s["copied"])  # the previous results of this slot have left out_dev
+        s["stats_dev"].zero_()
+        start = ConnectPacked(self.config, s["packed"], s["meta"])
+        s["res"] = connect_rollout(self.config, self.n, seed, game_id0, per_game=True, stats=s["stats_dev"], out=s["res"],
+                                   start=start)
+        N.check(N.lib().bgs_connect_pack_results(self.n, N.ptr(s["res"].length), N.ptr(s["res"].winner), N.ptr(s["out_dev"]),
+                                                  N.stream_ptr(torch)))
+        s["computed"].record()
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(s["computed"])
+            s["out_host"].copy_(s["out_dev"], non_blocking=True)
+            s["copied"].record()
+        return slot
+
+    def result(self, slot: int):
+        """(stats int64[256], result uint8[n]) of a submitted batch, as views of its pinned host record."""
+        s = self.sets[slot]
+        s["copied"].synchronize()
+        h = s["out_host"]
+        return h[self.out_off_stats:].view(self.torch.int64), h[: self.n]
 
 
 @dataclass

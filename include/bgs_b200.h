@@ -154,6 +154,9 @@ int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, const uint8_t* 
  * at most 63 cells (length < 64); winner + 1 is 0 (draw), 1 (player 0), 2 (player 1).  All pointers 16-byte
  * aligned device pointers. */
 int bgs_connect_pack_results(uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed, void* stream);
+/* The same for boards of 64..127 cells, games played from the empty board: packed[i] = length[i] | draw << 7;
+ * the winner of a decided game is the parity of its length (odd: player 0). */
+int bgs_connect_pack_results_wide(uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed, void* stream);
 
 /* Batched single transition on reference-layout states.  Replaces, for n states at once,
  *   State::get_action_at (connect.cpp:44)  -> status[i] = 0 ok / 1 illegal (state left unchanged)
@@ -266,6 +269,10 @@ int bgs_bounce_rollout_from(int H, int W, int rules, int max_plies, uint64_t n_g
                             uint64_t seed, const int8_t* grid, const int8_t* player, const int8_t* winner_in,
                             const uint8_t* ended_in, uint8_t* moves, uint16_t* length, int8_t* winner,
                             int8_t* final_grid, float* reward, int64_t* stats, void* stream);
+
+/* Per-game Bounce results in two bytes instead of three: packed[i] = length[i] | (winner[i] + 2) << 14
+ * (lengths below 16384; winner + 2: 0 truncated, 1 draw, 2 player 0, 3 player 1). */
+int bgs_bounce_pack_results(uint64_t n, const uint16_t* length, const int8_t* winner, uint16_t* packed, void* stream);
 
 int bgs_bounce_rollout_host(int device, const int8_t* grid0_host, int H, int W, int rules,
                             int max_plies, uint64_t n_games, uint64_t game_id0, uint64_t seed,

@@ -355,3 +355,24 @@ def test_replay_one_million_default_games_at_512_plies(oracle):
     assert s["games"] == n and s["wins0"] + s["wins1"] + s["draws"] + s["truncated"] == n
     assert s["steps"] == int(length.astype(np.int64).sum()) and s["truncated"] == int((winner == -2).sum())
     assert 27.0 < s["steps"] / n < 30.0
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_pipelined_host_stream_equals_oracle(oracle, packed):
+    """HostRollout(game="bounce"): BASELINE.json configs[2] end to end -- every batch's per-game results and
+    statistics in pinned host memory (one copy per batch; 2 bytes per game when packed) equal the oracle's."""
+    from simulator import batch
+
+    n, k, cap = 3001, 4, 96
+    host = batch.HostRollout(GRID, n, depth=2, packed=packed, game="bounce", max_plies=cap)
+    assert host.d2h_bytes == (2 if packed else 3) * ((n + 15) // 16 * 16) + 2048
+    for i, out in enumerate(host.stream(17, 40, k)):
+        ref = oracle.bounce_rollout(GRID, n, max_plies=cap, gid0=40 + i * n, seed=17, want_moves=False, want_grid=False)
+        if packed:
+            length, winner = host.unpack_results(out[1])
+        else:
+            length, winner = out[1], out[2]
+        np.testing.assert_array_equal(length.numpy().astype(np.uint16), ref["length"])
+        np.testing.assert_array_equal(winner.numpy(), ref["winner"])
+        np.testing.assert_array_equal(out[0].numpy(), ref["stats"])
+    assert (ref["winner"] == -2).sum() > 0  # some games were cut at the cap

@@ -446,7 +446,67 @@ def test_packed_host_results_equal_oracle(oracle):
         np.testing.assert_array_equal(winner.numpy(), ref["winner"])
         np.testing.assert_array_equal(st.numpy(), ref["stats"])
     with pytest.raises(ValueError):
-        batch.HostRollout((8, 9, 5), 10, packed=True)
+        batch.HostRollout((12, 12, 5), 10, packed=True)  # 144 cells: a length does not fit 7 bits
+
+
+@pytest.mark.parametrize("cfg", [(8, 9, 5), (10, 12, 6), (7, 9, 4)])
+def test_packed_host_results_on_boards_of_more_than_63_cells(oracle, cfg):
+    """64..127 cells: one byte = length | draw << 7 (a decided game's winner is the parity of its length)."""
+    from simulator import batch
+
+    n = 6001
+    host = batch.HostRollout(cfg, n, packed=True)
+    assert host.d2h_bytes == (n + 15) // 16 * 16 + 2048
+    for i, (st, result) in enumerate(host.stream(5, 100, 3)):
+        ref = oracle.connect_rollout(*cfg, n, gid0=100 + i * n, seed=5, want_actions=False, want_grid=False)
+        length, winner = host.unpack_results(result)
+        np.testing.assert_array_equal(length.numpy(), ref["length"])
+        np.testing.assert_array_equal(winner.numpy(), ref["winner"])
+        np.testing.assert_array_equal(st.numpy(), ref["stats"])
+    assert (ref["winner"] == -1).sum() > 0  # the sample holds draws
+
+
+def test_leaf_rollouts_from_host_positions_pipelined(oracle):
+    """HostLeafRollout: packed positions in pinned host memory -> rollouts -> packed results in pinned host
+    memory, three batches in flight; every batch equals the oracle's rollouts from those positions."""
+    from simulator import batch
+
+    cfg, n, k = (6, 7, 4), 7000, 5
+    g = torch.Generator(device="cuda").manual_seed(3)
+    positions = []
+    leaf = batch.HostLeafRollout(cfg, n, depth=3)
+    assert leaf.h2d_bytes == n * 16 + (n + 15) // 16 * 16 and leaf.d2h_bytes == (n + 15) // 16 * 16 + 2048
+    for j in range(k):
+        b = batch.ConnectBatch.initial(cfg, n)
+        for _ in range(4 + 3 * j):
+            b, _ = b.step(torch.randint(0, 7, (n,), device="cuda", generator=g))
+        positions.append(b)
+    tickets = []
+    for j in range(k):
+        if j >= 3:  # the slot is about to be reused: consume its previous batch first
+            stats, result = leaf.result(tickets[j - 3])
+            _check_leaf(oracle, positions[j - 3], stats, result, 50 + (j - 3))
+        slot = j % 3
+        pk = positions[j].pack()
+        hp, hm = leaf.host_inputs(slot)
+        hp.copy_(pk.packed.cpu())
+        hm.copy_(pk.meta.cpu())
+        tickets.append(leaf.submit(9, (50 + j) * n, slot))
+    for j in range(k - 3, k):
+        stats, result = leaf.result(tickets[j])
+        _check_leaf(oracle, positions[j], stats, result, 50 + j)
+
+
+def _check_leaf(oracle, b, stats, result, batch_no):
+    from simulator import batch
+
+    n = b.n
+    ref = oracle.connect_rollout_from(4, b.grid.cpu().numpy(), b.player.cpu().numpy(), b.winner.cpu().numpy(),
+                                      gid0=batch_no * n, seed=9)
+    length, winner = batch.HostRollout.unpack(result)
+    np.testing.assert_array_equal(length.numpy(), ref["length"])
+    np.testing.assert_array_equal(winner.numpy(), ref["winner"])
+    np.testing.assert_array_equal(stats.numpy(), ref["stats"])
 
 
 def test_dlpack_export():

@@ -463,7 +463,8 @@ def test_packed_host_results_on_boards_of_more_than_63_cells(oracle, cfg):
         np.testing.assert_array_equal(length.numpy(), ref["length"])
         np.testing.assert_array_equal(winner.numpy(), ref["winner"])
         np.testing.assert_array_equal(st.numpy(), ref["stats"])
-    assert (ref["winner"] == -1).sum() > 0  # the sample holds draws
+    if cfg[2] > 4:
+        assert (ref["winner"] == -1).sum() > 0  # the sample holds draws (the bit-7 flag is exercised)
 
 
 def test_leaf_rollouts_from_host_positions_pipelined(oracle):

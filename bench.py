@@ -502,7 +502,9 @@ def run_b200(args):
     # device->host into pinned memory inside the timed region as ONE copy per batch (the copy of batch i overlaps
     # the kernel of batch i+1); the loop consumes the host statistics of every batch.  The pinned buffers are
     # allocated on CPUs local to this rank's GPU.
-    host = batch.HostRollout(CONFIG, n, depth=3, packed=True)  # one byte per game: length | (winner + 1) << 6
+    # per-game results in the dense code: 3 games per 16-bit word (37 outcomes each: 36 lengths with the winner
+    # given by the parity, or a draw) = 5.33 bits per game
+    host = batch.HostRollout(CONFIG, n, depth=3, packed="dense")
     for i in range(min(args.warmup, 3)):
         host.run(SEED, (20_000 + i) * total + rank * n)
     # the pipelined path is timed 3 times over K steps each (after one untimed pass that touches every
@@ -662,9 +664,9 @@ def run_b200(args):
             "e2e": {
                 "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes * world,
                 "d2h_bytes_per_step": host.d2h_bytes * world,
-                "api": "simulator.batch.HostRollout(packed=True).stream -> bgs_connect_rollout + bgs_connect_pack_results; "
-                       "every batch's per-game results (1 byte: length | (winner+1)<<6) and statistics copied to pinned "
-                       "host memory as ONE copy per batch (pinned pages allocated on CPUs local to the GPU), the copy of "
+                "api": "simulator.batch.HostRollout(packed='dense').stream -> bgs_connect_rollout + bgs_connect_pack_results_dense; "
+                       "every batch's per-game results (length and winner of every game, 3 games per 16-bit word in base 37) "
+                       "and statistics copied to pinned host memory as ONE copy per batch (pinned pages allocated on CPUs local to the GPU), the copy of "
                        "batch i overlapping the kernels of the next batches; median of 3 repetitions of K steps (wall "
                        "clock, max over ranks)",
                 "repetitions_this_rank": [st_ / t_ for t_, st_ in e2e_reps],
@@ -686,7 +688,7 @@ def run_b200(args):
             "stats_equal_to_single_rank": stats_equal,
             "gpu_launches": args.steps,
             "gpu_launches_note": "1 connect_rollout_lut_kernel per step in each timed region (value, kernel-only, e2e; "
-                             "the e2e region adds 1 pack_results_kernel per step)",
+                             "the e2e region adds 1 pack_results_dense_kernel per step)",
             "roofline": {
                 "bound": "int_issue", "achieved": achieved, "peak": peak, "unit": "G thread-instr/s",
                 "frac": achieved / peak, "traffic": traffic,

@@ -1563,6 +1563,27 @@ pack_results_kernel(unsigned long long n, const uint8_t* __restrict__ length, co
                              : (uint8_t)((((uint32_t)(winner[i] + 1) & 3u) << 6) | (length[i] & 63u));
 }
 
+// Dense per-game results: a game from the empty board ends after Lmin = 2K-1 .. H*W plies with a winner given
+// by the parity of its length, or in a draw -- S = H*W - Lmin + 2 symbols.  G = floor(16 / log2 S) games share
+// one 16-bit word, word = s0 + S*s1 + S^2*s2 + ..  (6x7x4: S = 37, G = 3: 5.33 bits per game instead of 8).
+__global__ void __launch_bounds__(256)
+pack_results_dense_kernel(unsigned long long n, const uint8_t* __restrict__ length, const int8_t* __restrict__ winner,
+                          uint16_t* __restrict__ packed, int lmin, int S, int G) {
+    const unsigned long long nwords = (n + (unsigned)G - 1ull) / (unsigned)G;
+    for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < nwords;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t code = 0, mul = 1;
+        for (int j = 0; j < G; ++j) {
+            const unsigned long long i = w * (unsigned)G + j;
+            uint32_t sym = 0;
+            if (i < n) sym = winner[i] < 0 ? (uint32_t)(S - 1) : (uint32_t)((int)length[i] - lmin);
+            code += sym * mul;
+            mul *= (uint32_t)S;
+        }
+        packed[w] = (uint16_t)code;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 reward_kernel(unsigned long long n, const int8_t* __restrict__ winner, float2* __restrict__ reward) {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
@@ -2225,6 +2246,41 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
     }
     return launch_export_rows<MODE_TRAJ>(H, W, n_games * (unsigned long long)(H * W + 1), nullptr, length,
                                          reinterpret_cast<uint8_t*>(grids), (cudaStream_t)stream_, actions);
+}
+
+// (Lmin, S, G) of the dense result code of a board; G = 0: no gain over one byte per game
+static void dense_code(int H, int W, int K, int* lmin, int* S, int* G) {
+    const int HW = H * W;
+    *lmin = 2 * K - 1 < HW ? 2 * K - 1 : HW;
+    *S = HW - *lmin + 2;
+    int g = 0;
+    for (unsigned long long p = 1; p * (unsigned)*S <= 65536ull; p *= (unsigned)*S) ++g;
+    *G = (HW <= 255 && g >= 2) ? g : 0;
+}
+
+extern "C" int bgs_connect_dense_results(int H, int W, int K, int* lmin, int* symbols) {
+    int l, s, g;
+    dense_code(H, W, K, &l, &s, &g);
+    if (lmin) *lmin = l;
+    if (symbols) *symbols = s;
+    return g;
+}
+
+extern "C" int bgs_connect_pack_results_dense(int H, int W, int K, uint64_t n, const uint8_t* length, const int8_t* winner,
+                                              uint16_t* packed, void* stream_) {
+    if (!length || !winner || !packed) return set_error(BGS_EINVAL, "connect_pack_results_dense: null pointer");
+    int lmin, S, G;
+    dense_code(H, W, K, &lmin, &S, &G);
+    if (!supported(H, W, K) || G == 0) return set_error(BGS_EUNSUPPORTED, "connect_pack_results_dense: no dense code for %dx%d k=%d", H, W, K);
+    if (int rc = require_device()) return rc;
+    if (n == 0) return BGS_OK;
+    const unsigned long long nwords = (n + G - 1) / G;
+    unsigned long long blocks = (nwords + 255ull) / 256ull;
+    const unsigned long long cap = (unsigned long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    pack_results_dense_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(n, length, winner, packed, lmin, S, G);
+    BGS_CUDA_TRY(cudaGetLastError());
+    return BGS_OK;
 }
 
 static int pack_results_impl(bool wide, uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed, void* stream_);

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "bgs_connect_pack_results": (C.c_int, [_u64, _vp, _vp, _vp, _vp]),
     "bgs_connect_pack_results_wide": (C.c_int, [_u64, _vp, _vp, _vp, _vp]),
     "bgs_bounce_pack_results": (C.c_int, [_u64, _vp, _vp, _vp, _vp]),
+    "bgs_connect_dense_results": (C.c_int, [_i32, _i32, _i32, _vp, _vp]),
+    "bgs_connect_pack_results_dense": (C.c_int, [_i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp]),
     "bgs_connect_step": (C.c_int, [_i32, _i32, _i32, _u64] + [_vp] * 12),
     "bgs_connect_query": (C.c_int, [_i32, _i32, _u64] + [_vp] * 6),
     "bgs_connect_rollout_host": (C.c_int, [_i32, _i32, _i32, _i32, _u64, _u64, _u64] + [_vp] * 6),

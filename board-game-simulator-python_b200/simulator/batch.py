@@ -289,6 +289,8 @@ class HostRollout:
       Connect, at most 63 cells: 1 byte ``length | (winner + 1) << 6``; 64..127 cells: 1 byte
       ``length | draw << 7`` (a decided game's winner is the parity of its length); Bounce: 2 bytes
       ``length | (winner + 2) << 14``.  ``HostRollout.unpack`` / ``unpack_results`` recover (length, winner).
+    ``packed="dense"`` (Connect): several games per 16-bit word in base S = number of possible outcomes
+      (6x7x4: 3 games per word, 5.33 bits per game) -- for hosts whose D2H bandwidth is the limit.
     ``packed=False``: length and winner arrays as they are (Connect 2, Bounce 3 bytes per game).
 
     ``run`` is the synchronous call (kernel, then copy).  ``stream`` is the pipelined iterator: the
@@ -309,10 +311,19 @@ class HostRollout:
         self.max_plies, self.rules = int(max_plies), int(rules)
         dev = torch.device("cuda", torch.cuda.current_device())
         if game == "connect":
-            H, W, _ = _hwk(config)
-            if packed and H * W > 127:
-                raise ValueError("packed per-game results need a board of at most 127 cells")
-            self.mode = ("u8" if H * W <= 63 else "u8wide") if packed else "connect2"
+            H, W, K = _hwk(config)
+            if packed == "dense":
+                import ctypes as C
+
+                lmin, sym = C.c_int(0), C.c_int(0)
+                self.dense = (N.lib().bgs_connect_dense_results(H, W, K, C.byref(lmin), C.byref(sym)), lmin.value, sym.value)
+                if self.dense[0] == 0:
+                    raise ValueError("no dense result code for this board")
+                self.mode = "dense"
+            else:
+                if packed and H * W > 127:
+                    raise ValueError("packed per-game results need a board of at most 127 cells")
+                self.mode = ("u8" if H * W <= 63 else "u8wide") if packed else "connect2"
         elif game == "bounce":
             if packed and self.max_plies > 16383:
                 raise ValueError("packed Bounce results need max_plies < 16384")
@@ -324,6 +335,10 @@ class HostRollout:
         if self.mode in ("u8", "u8wide"):
             self.off = {"result": 0}
             body = n16
+        elif self.mode == "dense":
+            self.off = {"result": 0}
+            self.nwords = (n + self.dense[0] - 1) // self.dense[0]
+            body = (2 * self.nwords + 15) // 16 * 16
         elif self.mode == "connect2":
             self.off = {"length": 0, "winner": n16}
             body = 2 * n16
@@ -377,6 +392,18 @@ class HostRollout:
         if self.mode == "u16":
             r = result.to(torch.int32) & 0xFFFF
             return (r & 0x3FFF).to(torch.int16), ((r >> 14) - 2).to(torch.int8)
+        if self.mode == "dense":
+            G, lmin, S = self.dense
+            r = result.to(torch.int32) & 0xFFFF
+            syms = []
+            for _ in range(G):
+                syms.append(r % S)
+                r = r // S
+            sym = torch.stack(syms, dim=1).reshape(-1)[: self.n]
+            draw = sym == S - 1
+            length = torch.where(draw, torch.full_like(sym, _hwk(self.config)[0] * _hwk(self.config)[1]), sym + lmin)
+            winner = torch.where(draw, torch.full_like(sym, -1), 1 - (length & 1))
+            return length.to(torch.uint8), winner.to(torch.int8)
         raise ValueError("results are not packed")
 
     def _launch(self, s, seed, game_id0):
@@ -395,6 +422,10 @@ class HostRollout:
             if self.mode in ("u8", "u8wide"):
                 fn = L.bgs_connect_pack_results if self.mode == "u8" else L.bgs_connect_pack_results_wide
                 N.check(fn(n, N.ptr(s["res"].length), N.ptr(s["res"].winner), N.ptr(rec), N.stream_ptr(torch)))
+            elif self.mode == "dense":
+                H, W, K = _hwk(self.config)
+                N.check(L.bgs_connect_pack_results_dense(H, W, K, n, N.ptr(s["res"].length), N.ptr(s["res"].winner),
+                                                         N.ptr(rec), N.stream_ptr(torch)))
         else:
             s["res"] = bounce_rollout(self.config, n, seed, game_id0, max_plies=self.max_plies, rules=self.rules,
                                       per_game=True, stats=s["stats_dev"])
@@ -418,6 +449,8 @@ class HostRollout:
             return stats, self._view(h, "result", torch.uint8, self.n)
         if self.mode == "u16":
             return stats, self._view(h, "result", torch.int16, self.n)
+        if self.mode == "dense":
+            return stats, self._view(h, "result", torch.int16, self.nwords)
         ldt = torch.uint8 if self.game == "connect" else torch.int16
         return stats, self._view(h, "length", ldt, self.n), self._view(h, "winner", torch.int8, self.n)
 

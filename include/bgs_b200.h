@@ -158,6 +158,16 @@ int bgs_connect_pack_results(uint64_t n, const uint8_t* length, const int8_t* wi
  * the winner of a decided game is the parity of its length (odd: player 0). */
 int bgs_connect_pack_results_wide(uint64_t n, const uint8_t* length, const int8_t* winner, uint8_t* packed, void* stream);
 
+/* Dense per-game results for games played from the empty board: such a game ends after Lmin = min(2K-1, H*W) ..
+ * H*W plies with the winner given by the parity of its length (odd: player 0), or in a draw, so there are
+ * S = H*W - Lmin + 2 symbols (length - Lmin, or S-1 for a draw) and G = floor(16 / log2 S) games fit one
+ * uint16: packed[w] = sym[G*w] + S*sym[G*w+1] + S^2*sym[G*w+2] + ...   (6x7x4: S = 37, G = 3, 5.33 bits per game).
+ * bgs_connect_dense_results returns G (0: no gain for this board) and Lmin / S through the pointers;
+ * packed holds (n + G - 1) / G words. */
+int bgs_connect_dense_results(int H, int W, int K, int* lmin, int* symbols);
+int bgs_connect_pack_results_dense(int H, int W, int K, uint64_t n, const uint8_t* length, const int8_t* winner,
+                                   uint16_t* packed, void* stream);
+
 /* Batched single transition on reference-layout states.  Replaces, for n states at once,
  *   State::get_action_at (connect.cpp:44)  -> status[i] = 0 ok / 1 illegal (state left unchanged)
  *   Action::sample_next_state (connect.cpp:52) -> grid_out, player_out, winner_out

@@ -660,3 +660,23 @@ def test_full_size_launch_equals_oracle(oracle):
     for k in range(lo // chunk, (lo + 2**20) // chunk):
         np.testing.assert_array_equal(length[k * chunk:(k + 1) * chunk], parts[k]["length"])
         np.testing.assert_array_equal(winner[k * chunk:(k + 1) * chunk], parts[k]["winner"])
+
+
+@pytest.mark.parametrize("cfg", [(6, 7, 4), (4, 5, 3), (8, 9, 5)])
+def test_dense_host_results_equal_oracle(oracle, cfg):
+    """HostRollout(packed="dense"): several games per 16-bit word in base S (6x7x4: 3 games, 5.33 bits each)."""
+    from simulator import batch
+
+    n = 10007
+    host = batch.HostRollout(cfg, n, packed="dense")
+    G, lmin, S = host.dense
+    assert S ** G <= 65536 < S ** (G + 1) and lmin == 2 * cfg[2] - 1
+    assert host.d2h_bytes == (2 * ((n + G - 1) // G) + 15) // 16 * 16 + 2048
+    if cfg == (6, 7, 4):
+        assert (G, S) == (3, 37)
+    for i, (st, result) in enumerate(host.stream(5, 100, 3)):
+        ref = oracle.connect_rollout(*cfg, n, gid0=100 + i * n, seed=5, want_actions=False, want_grid=False)
+        length, winner = host.unpack_results(result)
+        np.testing.assert_array_equal(length.numpy(), ref["length"])
+        np.testing.assert_array_equal(winner.numpy(), ref["winner"])
+        np.testing.assert_array_equal(st.numpy(), ref["stats"])

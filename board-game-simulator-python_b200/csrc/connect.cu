@@ -1570,7 +1570,41 @@ __global__ void __launch_bounds__(256)
 pack_results_dense_kernel(unsigned long long n, const uint8_t* __restrict__ length, const int8_t* __restrict__ winner,
                           uint16_t* __restrict__ packed, int lmin, int S, int G) {
     const unsigned long long nwords = (n + (unsigned)G - 1ull) / (unsigned)G;
-    for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < nwords;
+    unsigned long long w0 = 0;
+    if (G == 3 && (((uintptr_t)length | (uintptr_t)winner | (uintptr_t)packed) & 15u) == 0) {
+        // 48 games -> 16 words per thread: three 128-bit loads of each input, two 128-bit stores
+        const unsigned long long nblk = n / 48ull;
+        for (unsigned long long b = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; b < nblk;
+             b += (unsigned long long)gridDim.x * blockDim.x) {
+            uint32_t lw[12], ww[12];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint4 l = reinterpret_cast<const uint4*>(length)[3 * b + q];
+                const uint4 w = reinterpret_cast<const uint4*>(winner)[3 * b + q];
+                lw[4 * q] = l.x; lw[4 * q + 1] = l.y; lw[4 * q + 2] = l.z; lw[4 * q + 3] = l.w;
+                ww[4 * q] = w.x; ww[4 * q + 1] = w.y; ww[4 * q + 2] = w.z; ww[4 * q + 3] = w.w;
+            }
+            uint32_t out[8];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {  // word k = games 3k .. 3k+2 of the block
+                uint32_t code = 0, mul = 1;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int g = 3 * k + j;
+                    const uint32_t len = (lw[g >> 2] >> (8 * (g & 3))) & 0xFFu;
+                    const bool draw = ((ww[g >> 2] >> (8 * (g & 3))) & 0x80u) != 0u;
+                    code += (draw ? (uint32_t)(S - 1) : len - (uint32_t)lmin) * mul;
+                    mul *= (uint32_t)S;
+                }
+                if (k & 1) out[k >> 1] |= code << 16; else out[k >> 1] = code;
+            }
+            uint4* dst = reinterpret_cast<uint4*>(packed) + 2 * b;
+            dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+            dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        }
+        w0 = nblk * 16ull;  // the remaining words go through the generic loop below
+    }
+    for (unsigned long long w = w0 + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < nwords;
          w += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t code = 0, mul = 1;
         for (int j = 0; j < G; ++j) {
@@ -2275,7 +2309,7 @@ extern "C" int bgs_connect_pack_results_dense(int H, int W, int K, uint64_t n, c
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
     const unsigned long long nwords = (n + G - 1) / G;
-    unsigned long long blocks = (nwords + 255ull) / 256ull;
+    unsigned long long blocks = (nwords / 16ull + 255ull) / 256ull + 1ull;
     const unsigned long long cap = (unsigned long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     pack_results_dense_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(n, length, winner, packed, lmin, S, G);

@@ -49,18 +49,25 @@ SEED = 20261018
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_rollout_throughput(budget_s: float, threads: int | None = None, chunk: int = 1 << 15):
-    """Times oracle/bgs_oracle.c (bgso_connect_rollout) on `threads` host threads for ~budget_s.
+def cpu_rollout_throughput(budget_s: float, threads: int | None = None, chunk: int = 1 << 15, engine: str = "bitboard"):
+    """Times the CPU port of the hot path on `threads` host threads for ~budget_s.
 
+    engine "bitboard": oracle/fast_connect.c -- the same loop written the way a CPU engine would (single-word
+    bitboards, shift-and-AND run test, -O3), checked game by game against the oracle; the "best CPU" figure of
+    SURVEY.md 8d (iii).  engine "naive": oracle/bgs_oracle.c (bgso_connect_rollout), the brute-force checker.
     ctypes releases the GIL during the call, so plain threads scale across cores."""
-    import numpy as np
-
     from oracle import binding as o  # the checker, used here only as the timed CPU baseline
 
     threads = threads or os.cpu_count() or 1
     o.lib()
     H, W, K = CONFIG
-    o.connect_rollout(H, W, K, 256, want_actions=False, want_grid=False)  # warm up
+    if engine == "bitboard":
+        run = lambda gid0: o.fast_connect_rollout(H, W, K, chunk, gid0=gid0, seed=SEED, per_game=False)
+        what = "oracle/fast_connect.c (C bitboards, -O3; verified against oracle/bgs_oracle.c)"
+    else:
+        run = lambda gid0: o.connect_rollout(H, W, K, chunk, gid0=gid0, seed=SEED, want_actions=False, want_grid=False)
+        what = "oracle/bgs_oracle.c (C, brute force, -O2)"
+    run(0)  # warm up
     done = [0] * threads
     games = [0] * threads
     t_end = time.perf_counter() + budget_s
@@ -68,8 +75,7 @@ def cpu_rollout_throughput(budget_s: float, threads: int | None = None, chunk: i
     def work(tid):
         i = 0
         while time.perf_counter() < t_end:
-            gid0 = (tid * 1_000_003 + i) * chunk
-            res = o.connect_rollout(H, W, K, chunk, gid0=gid0, seed=SEED, want_actions=False, want_grid=False)
+            res = run((tid * 1_000_003 + i) * chunk)
             done[tid] += int(res["stats"][o.STAT_STEPS])
             games[tid] += chunk
             i += 1
@@ -87,7 +93,7 @@ def cpu_rollout_throughput(budget_s: float, threads: int | None = None, chunk: i
         "cores": threads,
         "kind": "port",
         "sample": f"{sum(games)} games ({sum(done)} env-steps) of the same Connect(6,7,4) workload in {dt:.1f} s "
-                  f"on {threads} threads, oracle/bgs_oracle.c (C, -O2)",
+                  f"on {threads} threads, {what}",
         "seconds": dt,
         "steps": sum(done),
     }
@@ -183,8 +189,9 @@ def run_reference(args):
         "cpu_baseline": {
             "value": value, "unit": UNIT, "cores": last["cores"], "kind": "port",
             "sample": f"each step = a {per_step:.0f} s bounded sample of the workload on {last['cores']} host threads; "
-                      "oracle/bgs_oracle.c -- the reference's own engine (jojolebarjos/board-game-simulator@c8f8a07) "
-                      "is not in the reference tree and cannot be built offline",
+                      "oracle/fast_connect.c (bitboard C loop, -O3, verified against the oracle) -- the reference's own "
+                      "engine (jojolebarjos/board-game-simulator@c8f8a07) is not in the reference tree and cannot be "
+                      "built offline",
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -707,6 +714,11 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             cb = cpu_rollout_throughput(args.cpu_seconds)
             cb.pop("seconds"), cb.pop("steps")
+            try:
+                cb["naive_oracle_value"] = cpu_rollout_throughput(min(4.0, args.cpu_seconds), engine="naive")["value"]
+                cb["naive_oracle_note"] = "oracle/bgs_oracle.c (brute-force checker), same threads -- round 1's yardstick"
+            except Exception as e:
+                cb["naive_oracle_error"] = repr(e)
             try:
                 cb["object_api_steps_per_s"] = object_api_throughput()
                 cb["object_api_note"] = ("README.md:52-69 loop through simulator.game.connect ON THE GPU (one kernel + one "

@@ -113,6 +113,11 @@ int64_t bgso_bounce_replay(const int8_t* grid0, int H, int W, int rules, int max
                            const uint8_t* moves, const uint16_t* length, const int8_t* winner,
                            const int8_t* final_grid, const float* reward, int64_t* first_bad);
 
+/* ---- fast_connect.c: the same Connect rollout loop on single-word bitboards (the "best CPU" baseline) ---- */
+int bgso_fast_connect_supported(int H, int W, int K);
+int bgso_fast_connect_rollout(int H, int W, int K, uint64_t n, uint64_t gid0, uint64_t seed, uint8_t* length,
+                              int8_t* winner, int64_t* stats);
+
 /* ---- conventions of the B200 build's own additions (include/bgs_b200.h), restated for the tests ---- */
 /* weighted action choice (bgs_connect_sample_step / bgs_bounce_sample_step) */
 int bgso_connect_sample(const int8_t* grid, int H, int W, int winner, const float* probs, uint64_t seed,

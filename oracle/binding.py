@@ -28,19 +28,14 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc if the shared library is missing or stale."""
-    src = os.path.join(_HERE, "bgs_oracle.c")
-    hdr = os.path.join(_HERE, "bgs_oracle.h")
+    srcs = [os.path.join(_HERE, f) for f in ("bgs_oracle.c", "fast_connect.c", "bgs_oracle.h", "Makefile")]
     stale = (
         force
         or not os.path.exists(_LIB_PATH)
-        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     )
     if stale:
-        subprocess.run(
-            ["gcc", "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", _LIB_PATH, src],
-            check=True,
-            cwd=_HERE,
-        )
+        subprocess.run(["make", "-C", _HERE, "-B", "libbgs_oracle.so"], check=True, capture_output=True)
     return _LIB_PATH
 
 
@@ -132,6 +127,22 @@ def connect_rollout(H, W, K, n, gid0=0, seed=0, want_actions=True, want_grid=Tru
     )
     if rc != 0:
         raise ValueError("oracle: unsupported Connect configuration")
+    return res
+
+
+def fast_connect_rollout(H, W, K, n, gid0=0, seed=0, per_game=True):
+    """fast_connect.c: the bitboard loop (same draws, same results as connect_rollout without trajectories)."""
+    res = {
+        "length": np.empty(n, dtype=np.uint8) if per_game else None,
+        "winner": np.empty(n, dtype=np.int8) if per_game else None,
+        "stats": np.zeros(STATS_LEN, dtype=np.int64),
+    }
+    rc = lib().bgso_fast_connect_rollout(
+        C.c_int(H), C.c_int(W), C.c_int(K), C.c_uint64(n), C.c_uint64(gid0), C.c_uint64(seed),
+        _p(res["length"], C.c_uint8), _p(res["winner"], C.c_int8), _p(res["stats"], C.c_int64),
+    )
+    if rc != 0:
+        raise ValueError("fast_connect: unsupported board")
     return res
 
 

@@ -215,3 +215,12 @@ def test_bounce_rollout_statistics(oracle):
     assert set(np.unique(rt["winner"])) <= {-2, -1, 0, 1}
     assert oracle.bounce_replay(grid0, rt["moves"], rt["length"], rt["winner"], rt["final_grid"], rt["reward"]) == (0, -1)
     np.testing.assert_array_equal(rt["moves"][:, :5], r["moves"][:200, :5])
+
+
+def test_bitboard_cpu_baseline_equals_the_oracle(oracle):
+    """oracle/fast_connect.c (the "best CPU" loop timed by bench.py) plays exactly the oracle's games."""
+    for (H, W, K), n in (((6, 7, 4), 20000), ((4, 5, 3), 5000), ((7, 8, 5), 3000), ((2, 3, 2), 500), ((6, 7, 1), 100), ((3, 3, 4), 300)):
+        a = oracle.connect_rollout(H, W, K, n, gid0=77, seed=9, want_actions=False, want_grid=False)
+        b = oracle.fast_connect_rollout(H, W, K, n, gid0=77, seed=9)
+        for k in ("length", "winner", "stats"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=f"{k} {(H, W, K)}")

@@ -396,8 +396,10 @@ def object_api_throughput(n_games: int = 12):
     random.seed(0)
     config = connect.Config(*CONFIG)
     steps = 0
-    t0 = time.perf_counter()
-    for _ in range(n_games):
+    t0 = None
+    for game in range(n_games + 1):
+        if game == 1:  # the first game is a warm-up (CUDA context, module load, staging buffers)
+            steps, t0 = 0, time.perf_counter()
         state = config.sample_initial_state()
         while not state.has_ended:
             state = random.choice(state.actions).sample_next_state()

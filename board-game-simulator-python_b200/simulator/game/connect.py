@@ -12,12 +12,71 @@ machine without a GPU, constructors / JSON / equality work and anything that nee
 """
 from __future__ import annotations
 
+import threading
 from typing import Any
 
 import numpy as np
 
 from .. import _native as N
 from .. import batch as _batch
+
+
+class _OneState:
+    """Staging for the single-object API: ONE pinned host record in, ONE out, per call.
+
+    Every property of the reference's objects is computed by the CUDA kernels with a batch of one.  A naive
+    wrapper pays a small host<->device copy and a synchronisation per field (grid, player, winner, column in;
+    grid, player, winner, ended, legal, reward, status out: ~10 of them, ~230 us per ply); here the inputs of a
+    call travel as one pinned record, the outputs come back as one, and the C ABI gets raw pointers into the two
+    device records.  Layout (bytes): grid[HW] | player | winner | pad -> 16-byte aligned int32 action;
+    outputs: grid[HW] | player | winner | ended | pad -> aligned legal u32 | status i32 | reward f32[2]."""
+
+    _cache: dict = {}
+
+    def __init__(self, H: int, W: int):
+        torch = N.require_cuda()
+        self.torch = torch
+        HW = H * W
+        self.HW = HW
+        self.o_act = (HW + 2 + 15) // 16 * 16
+        self.in_bytes = self.o_act + 16
+        self.o_words = (HW + 3 + 15) // 16 * 16
+        self.out_bytes = self.o_words + 16
+        self.in_host = torch.zeros(self.in_bytes, dtype=torch.uint8).pin_memory()
+        self.out_host = torch.zeros(self.out_bytes, dtype=torch.uint8).pin_memory()
+        self.in_dev = torch.zeros(self.in_bytes, dtype=torch.uint8, device="cuda")
+        self.out_dev = torch.zeros(self.out_bytes, dtype=torch.uint8, device="cuda")
+        self.in_np = self.in_host.numpy()
+        self.out_np = self.out_host.numpy()
+        #: the staging records are shared by every object of this board size: one call at a time (the
+        #: reference's example apps call state.actions from pool threads, textual/examples/agent.py:61)
+        self.lock = threading.Lock()
+
+    @classmethod
+    def get(cls, H: int, W: int) -> "_OneState":
+        torch = N.require_cuda()
+        key = (H, W, torch.cuda.current_device())
+        if key not in cls._cache:
+            cls._cache[key] = cls(H, W)
+        return cls._cache[key]
+
+    def load(self, grid, player, winner, column=0):
+        HW = self.HW
+        self.in_np[:HW] = grid.reshape(-1).view(np.uint8)
+        self.in_np[HW] = player & 0xFF
+        self.in_np[HW + 1] = winner & 0xFF
+        self.in_np[self.o_act: self.o_act + 4].view(np.int32)[0] = column
+        self.in_dev.copy_(self.in_host, non_blocking=True)
+
+    def fetch(self):
+        """(grid bytes, player, winner, ended, legal, status, reward) of the last call (synchronises once)."""
+        self.out_host.copy_(self.out_dev, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        o, HW, w = self.out_np, self.HW, self.o_words
+        words = o[w: w + 16]
+        return (o[:HW].view(np.int8).copy(), int(o[HW:HW + 1].view(np.int8)[0]), int(o[HW + 1:HW + 2].view(np.int8)[0]),
+                bool(o[HW + 2]), int(words[0:4].view(np.uint32)[0]), int(words[4:8].view(np.int32)[0]),
+                words[8:16].view(np.float32).copy())
 
 
 class Config:
@@ -93,14 +152,18 @@ class State:
     # -- GPU-computed facts about this state -----------------------------------------------------
     def _facts(self):
         if self._info is None:
-            torch = N.require_cuda()
-            b = _batch.ConnectBatch(
-                self.config,
-                torch.from_numpy(self._grid[None]).cuda(),
-                torch.tensor([self._player], dtype=torch.int8, device="cuda"),
-                torch.tensor([self._winner], dtype=torch.int8, device="cuda"),
-            )
-            self._info = (bool(b.has_ended.item()), int(b.legal.item()) & 0xFFFFFFFF, b.reward[0].cpu().numpy())
+            cfg = self.config
+            H, W = cfg.height, cfg.width
+            if not N.lib().bgs_connect_supported(H, W, cfg.count):
+                raise RuntimeError(f"Connect {H}x{W} k={cfg.count} is not supported by the CUDA kernels")
+            st = _OneState.get(H, W)
+            with st.lock:
+                st.load(self._grid, self._player, self._winner)
+                i, o, HW = st.in_dev.data_ptr(), st.out_dev.data_ptr(), st.HW
+                N.check(N.lib().bgs_connect_query(H, W, 1, i, i + HW + 1, o + HW + 2, o + st.o_words, o + st.o_words + 8,
+                                                  N.stream_ptr(st.torch)))
+                _, _, _, ended, legal, _, reward = st.fetch()
+            self._info = (ended, legal, reward)
         return self._info
 
     @property
@@ -173,20 +236,22 @@ class Action:
         return (self.state._key(), self.column)
 
     def sample_next_state(self) -> State:
-        torch = N.require_cuda()
         s = self.state
-        b = _batch.ConnectBatch(
-            s.config,
-            torch.from_numpy(s._grid[None]).cuda(),
-            torch.tensor([s._player], dtype=torch.int8, device="cuda"),
-            torch.tensor([s._winner], dtype=torch.int8, device="cuda"),
-            has_ended=False,  # facts of the OLD state are not needed for the transition
-        )
-        nxt, status = b.step(torch.tensor([self.column], dtype=torch.int32, device="cuda"))
-        if int(status.item()) != 0:
+        cfg = s.config
+        H, W, K = cfg.height, cfg.width, cfg.count
+        if not N.lib().bgs_connect_supported(H, W, K):
+            raise RuntimeError(f"Connect {H}x{W} k={K} is not supported by the CUDA kernels")
+        st = _OneState.get(H, W)
+        with st.lock:
+            st.load(s._grid, s._player, s._winner, self.column)
+            i, o, HW = st.in_dev.data_ptr(), st.out_dev.data_ptr(), st.HW
+            ow = o + st.o_words
+            N.check(N.lib().bgs_connect_step(H, W, K, 1, i, i + HW, i + HW + 1, i + st.o_act, o, o + HW, o + HW + 1,
+                                             o + HW + 2, ow + 8, ow, ow + 4, N.stream_ptr(st.torch)))
+            grid, player, winner, ended, legal, status, reward = st.fetch()
+        if status != 0:
             raise RuntimeError(f"illegal action: column {self.column}")
-        info = (bool(nxt.has_ended.item()), int(nxt.legal.item()) & 0xFFFFFFFF, nxt.reward[0].cpu().numpy())
-        return State(s.config, nxt.grid[0].cpu().numpy(), int(nxt.player.item()), int(nxt.winner.item()), info)
+        return State(cfg, grid.reshape(H, W), player, winner, (ended, legal, reward))
 
     def to_json(self) -> dict[str, Any]:
         return {"column": self.column}

@@ -930,15 +930,18 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     const uint32_t warp_lines = lines - lane * 4u;  // line 0 of lane 0
     uint2* list = s_list[GRID ? (threadIdx.x >> 5) : 0];
 
-    // Grid flush geometry, fixed per lane: a pass serves GPP finished games with LPG lanes each; lane
-    // (fg, fu) writes the 8-byte unit fu (cells 8*fu .. 8*fu+7, at most two board rows) of the pass's game fg.
-    constexpr unsigned UPG = HW / 8;                                          // 8-byte units per game
-    constexpr unsigned LPG = UPG <= 8 ? 8u : (UPG <= 10 ? 10u : 16u);         // 8x9: 10 lanes (3 games a pass), 10x12: 16 (2)
+    // Grid flush geometry, fixed per lane: a pass serves GPP finished games with LPG lanes each.
+    //   W % 4 != 0 (8x9): lane (fg, fu) writes the 8-byte unit fu (cells 8*fu .. 8*fu+7, at most two board rows).
+    //   W % 4 == 0 (10x12): lane (fg, fu) writes board ROW fu -- one line word in, W/4 table look-ups, W/4 32-bit
+    //   stores out; no second row, and H lanes per game instead of H*W/8 (10x12: 3 games a pass instead of 2).
+    constexpr bool ROWS = W % 4 == 0;
+    constexpr unsigned UPG = ROWS ? (unsigned)H : (unsigned)HW / 8u;         // lane-units per game
+    constexpr unsigned LPG = UPG <= 8 ? 8u : (UPG <= 10 ? 10u : 16u);         // 8x9: 10 lanes (3 games a pass), 10x12: 10 (3)
     constexpr unsigned GPP = 32u / LPG;
-    static_assert(!GRID || UPG <= 16, "fused grids: at most 128 cells");
+    static_assert(!GRID || UPG <= 16, "fused grids: at most 16 lane-units per game");
     const unsigned fg = lane / LPG, fu = lane - fg * LPG;
     const bool f_on = fg < GPP && fu < UPG;
-    const unsigned fr0 = (8u * fu) / (unsigned)W, fc0 = 8u * fu - fr0 * (unsigned)W;
+    const unsigned fr0 = ROWS ? fu : (8u * fu) / (unsigned)W, fc0 = ROWS ? 0u : 8u * fu - fr0 * (unsigned)W;
     const uint32_t f_x0 = fr0 * (LINES_THREADS * 4), f_x1 = (fr0 + 1u < (unsigned)H ? fr0 + 1u : fr0) * (LINES_THREADS * 4);
 
     uint32_t toprow = 0, t = 0;
@@ -983,12 +986,22 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                         const uint2 e = list[gi];
                         const uint32_t gidx = e.y;
                         const uint32_t src = warp_lines + e.x * 4u;
-                        const uint32_t x0 = lds_u32(src + f_x0), x1 = lds_u32(src + f_x1);
-                        const uint32_t a = ((x0 & MW) | ((x1 & MW) << W)) >> fc0;    // player 0's stones on cells 8*fu ..
-                        const uint32_t b = ((x0 >> 16) | ((x1 >> 16) << W)) >> fc0;  // player 1's
-                        const uint32_t lo = lds_u32(cell4 + 4u * ((a & 0xFu) | ((b & 0xFu) << 4)));
-                        const uint32_t hi = lds_u32(cell4 + 4u * (((a >> 4) & 0xFu) | (b & 0xF0u)));
-                        *reinterpret_cast<uint2*>(p.final_grid + ((size_t)gidx * HW + 8u * fu)) = make_uint2(lo, hi);
+                        if (ROWS) {
+                            const uint32_t x = lds_u32(src + f_x0);  // row fu: player 0 in bits 0..W-1, player 1 in 16..16+W-1
+                            uint8_t* dst = reinterpret_cast<uint8_t*>(p.final_grid) + ((size_t)gidx * HW + (unsigned)W * fu);
+#pragma unroll
+                            for (int q = 0; q < W / 4; ++q) {
+                                const uint32_t y = x >> (4 * q);
+                                *reinterpret_cast<uint32_t*>(dst + 4 * q) = lds_u32(cell4 + 4u * ((y & 0xFu) | ((y >> 12) & 0xF0u)));
+                            }
+                        } else {
+                            const uint32_t x0 = lds_u32(src + f_x0), x1 = lds_u32(src + f_x1);
+                            const uint32_t a = ((x0 & MW) | ((x1 & MW) << W)) >> fc0;    // player 0's stones on cells 8*fu ..
+                            const uint32_t b = ((x0 >> 16) | ((x1 >> 16) << W)) >> fc0;  // player 1's
+                            const uint32_t lo = lds_u32(cell4 + 4u * ((a & 0xFu) | ((b & 0xFu) << 4)));
+                            const uint32_t hi = lds_u32(cell4 + 4u * (((a >> 4) & 0xFu) | (b & 0xF0u)));
+                            *reinterpret_cast<uint2*>(p.final_grid + ((size_t)gidx * HW + 8u * fu)) = make_uint2(lo, hi);
+                        }
                     }
                     g0 += GPP;
                 } while (g0 < nfin);

@@ -1549,6 +1549,130 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
     }
 }
 
+// MODE_TRAJ for boards whose cell count is even but not a multiple of 8 (6x7): word-stationary.
+// Two consecutive positions of a game are 2*H*W bytes = NW = H*W/2 32-bit words, and position t+2 differs from
+// position t in the bytes of (at most) two cells, so a lane owns fixed WORDS of that double row: the 4 cells of
+// its word, the ply at which each is filled (minus the byte's position parity) and by whom sit in registers,
+// and the word of double position s is  (ow & m) | ~m  with  m = sign_bytes((0x80 | 2s) - tm)  -- five
+// instructions per 4 output bytes instead of ~5 per byte for expanding every position from bitboards.
+// GPW = 3 games share a warp (3 * 21 = 63 words on 2 * 32 lane slots); their T*H*W contiguous bytes are staged
+// in shared memory (16-bit stores: a game is only 2-byte aligned) and leave as 128-bit stores.  tm / ow come from
+// the ply-parallel scatter of the cell kernel above.
+constexpr int TRAJW_THREADS = 128;
+template <int H, int W>
+__global__ void __launch_bounds__(TRAJW_THREADS)
+connect_traj_words_kernel(unsigned long long n_games, const uint8_t* __restrict__ actions,
+                          const uint8_t* __restrict__ length, uint8_t* out) {
+    constexpr int HW = H * W, T = HW + 1, NW = HW / 2, GPW = 3, WARPS = TRAJW_THREADS / 32;
+    constexpr int GB = T * HW;                // bytes of one game
+    constexpr int NS = (T + 1) / 2;           // double positions (the last one holds a single position: T is odd)
+    static_assert(HW % 2 == 0 && HW <= 126 && W <= 16 && GPW * NW <= 64, "even cell count, two word slots per lane");
+    constexpr int STAGE = (GPW * GB + 15 + 15) & ~15;
+    __shared__ __align__(16) uint8_t s_stage[WARPS][STAGE];
+    __shared__ uint8_t s_tm[WARPS][GPW * HW];
+    __shared__ uint8_t s_ow[WARPS][GPW * HW];
+    __shared__ uint8_t s_act[WARPS][GPW * HW];
+    __shared__ uint8_t s_cnt[WARPS][GPW * 16];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    uint8_t* tm = s_tm[warp];
+    uint8_t* ow = s_ow[warp];
+    uint8_t* act = s_act[warp];
+    uint8_t* cnt = s_cnt[warp];
+    uint8_t* stg = s_stage[warp];
+    // this lane's two word slots: (game of the group, word of the double row); fixed for the whole kernel
+    unsigned sj[2], sw[2], last_halves[2];
+    bool son[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const unsigned q = lane + 32u * k;
+        son[k] = q < (unsigned)(GPW * NW);
+        sj[k] = son[k] ? q / NW : 0u;
+        sw[k] = q - sj[k] * NW;
+        const int valid = HW - 4 * (int)sw[k];  // bytes of the word that belong to the FIRST position of a pair
+        last_halves[k] = valid >= 4 ? 2u : (valid > 0 ? (unsigned)valid / 2u : 0u);
+    }
+    const unsigned long long ngroups = (n_games + GPW - 1ull) / GPW;
+    for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
+         group += (unsigned long long)gridDim.x * WARPS) {
+        const unsigned long long g0 = group * GPW;
+        const unsigned ng = (unsigned)((n_games - g0) < (unsigned long long)GPW ? (n_games - g0) : GPW);
+        for (unsigned i = lane; i < GPW * HW; i += 32) {
+            tm[i] = 0x7F;
+            ow[i] = 0xFF;
+            act[i] = i < ng * HW ? actions[g0 * HW + i] : (uint8_t)0;
+        }
+        for (unsigned i = lane; i < GPW * 16; i += 32) cnt[i] = 0;
+        const unsigned len_mine = lane < ng ? length[g0 + lane] : 0u;
+        __syncwarp();
+        // ---- scatter: ply p of game j fills the lowest empty cell of its column
+        for (unsigned q0 = 0; q0 < GPW * HW; q0 += 32) {
+            const unsigned q = q0 + lane;
+            const unsigned j = q / HW, pl = q - j * HW;
+            const unsigned lenj = __shfl_sync(0xffffffffu, len_mine, j < GPW ? j : 0);
+            const bool valid = q < GPW * HW && pl < lenj;
+            const unsigned col = valid ? act[q] : 0u;
+            const unsigned mm = __match_any_sync(0xffffffffu, valid ? (j * 16u + col) : (0x100u + lane));
+            const unsigned below = valid ? cnt[j * 16 + col] : 0u;  // stones already in the column
+            __syncwarp();
+            if (valid) {
+                if ((mm >> lane) == 1u) cnt[j * 16 + col] = (uint8_t)(below + __popc(mm));  // last ply of the column
+                const unsigned cell = (below + __popc(mm & lt)) * W + col;
+                tm[j * HW + cell] = (uint8_t)(pl + 1);
+                ow[j * HW + cell] = (uint8_t)(pl & 1);
+            }
+            __syncwarp();
+        }
+        // ---- this lane's words: 4 cells each, fill ply (minus the byte's position parity) and owner
+        uint32_t tm4[2], ow4[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            tm4[k] = 0x7F7F7F7Fu; ow4[k] = 0u;
+            if (son[k] && sj[k] < ng) {
+                uint32_t tv = 0, ov = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned b = 4u * sw[k] + i, par = b >= (unsigned)HW ? 1u : 0u, cell = b - par * HW;
+                    const unsigned t0 = tm[sj[k] * HW + cell];
+                    tv |= (t0 == 0x7Fu ? 0x7Fu : t0 - par) << (8 * i);  // shown from position t0: double position s shows it iff t0 - par <= 2s
+                    ov |= (uint32_t)ow[sj[k] * HW + cell] << (8 * i);
+                }
+                tm4[k] = tv; ow4[k] = ov;
+            }
+        }
+        // ---- all positions, two at a time
+        const unsigned long long G0 = g0 * (unsigned long long)GB;
+        const unsigned pad = (unsigned)(G0 & 15ull);
+        uint32_t tb = 0x80808080u;
+        for (int s2 = 0; s2 < NS; ++s2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (son[k] && sj[k] < ng) {
+                    const uint32_t m = sign_bytes(tb - tm4[k]);
+                    const uint32_t v = (ow4[k] & m) | ~m;
+                    uint8_t* dst = stg + pad + sj[k] * GB + s2 * (2 * HW) + 4 * sw[k];
+                    const unsigned halves = s2 == NS - 1 ? last_halves[k] : 2u;
+                    if (halves >= 1u) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)v;
+                    if (halves >= 2u) *reinterpret_cast<uint16_t*>(dst + 2) = (uint16_t)(v >> 16);
+                }
+            }
+            tb += 0x02020202u;
+        }
+        __syncwarp();
+        // ---- stage -> global: head (2-byte stores up to the first 16-byte boundary), 128-bit body, tail
+        const unsigned L = ng * (unsigned)GB;
+        uint8_t* gdst = out + G0;
+        const unsigned head = (16u - pad) & 15u;  // pad is even
+        for (unsigned i = 2u * lane; i < head; i += 64)
+            *reinterpret_cast<uint16_t*>(gdst + i) = *reinterpret_cast<const uint16_t*>(stg + pad + i);
+        const unsigned nvec = (L - head) >> 4;
+        for (unsigned q = lane; q < nvec; q += 32)
+            *reinterpret_cast<uint4*>(gdst + head + 16u * q) = *reinterpret_cast<const uint4*>(stg + pad + head + 16u * q);
+        for (unsigned i = head + (nvec << 4) + 2u * lane; i < L; i += 64)
+            *reinterpret_cast<uint16_t*>(gdst + i) = *reinterpret_cast<const uint16_t*>(stg + pad + i);
+        __syncwarp();
+    }
+}
+
 // length (<= 63) and winner of every game in one byte: bits 0..5 length, bits 6..7 winner + 1.
 // Halves the device->host traffic of the per-game results (16 bytes per thread in, 16 out).
 // WIDE (boards of 64..127 cells, games from the empty board): bits 0..6 length, bit 7 = draw; the winner of a
@@ -2290,6 +2414,18 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
         };
         if (H == 8) return launch(connect_traj_cells_kernel<8, 9>, 3);
         return launch(connect_traj_cells_kernel<10, 12>, 2);
+    }
+    if (((uintptr_t)grids & 15u) == 0 && H == 6 && W == 7) {  // the headline board: word-stationary kernel
+        auto kern = connect_traj_words_kernel<6, 7>;
+        int per_sm = 0;
+        BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRAJW_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        unsigned long long blocks = (n_games + 3ull * (TRAJW_THREADS / 32) - 1ull) / (3ull * (TRAJW_THREADS / 32));
+        const unsigned long long cap = (unsigned long long)sm_count() * per_sm;
+        if (blocks > cap) blocks = cap;
+        kern<<<(unsigned)blocks, TRAJW_THREADS, 0, (cudaStream_t)stream_>>>(n_games, actions, length, reinterpret_cast<uint8_t*>(grids));
+        BGS_CUDA_TRY(cudaGetLastError());
+        return BGS_OK;
     }
     return launch_export_rows<MODE_TRAJ>(H, W, n_games * (unsigned long long)(H * W + 1), nullptr, length,
                                          reinterpret_cast<uint8_t*>(grids), (cudaStream_t)stream_, actions);

@@ -843,7 +843,7 @@ __device__ __forceinline__ uint32_t line_or(uint32_t lines, uint32_t li, uint32_
 }
 
 template <int H, int W, int K, int J, int ACT>
-__device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint64_t& hts, uint32_t r, uint32_t& t, int& res,
+__device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint32_t r, uint32_t& t, int& res,
                                           uint32_t lut8, uint32_t lines, uint8_t* act_row, uint32_t& blk) {
     typedef LineGeo<H, W> LG;
     constexpr int P = J & 1;
@@ -858,9 +858,11 @@ __device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint64_t& hts, uint3
         const bool hi = k >= nlo;
         c = lds_u8(lut8 + (hi ? (freem >> HB) : lo) * 8u + (hi ? k - nlo : k)) + (hi ? (uint32_t)HB : 0u);
     }
-    const uint32_t sh = 4u * c;
-    const uint32_t h = (uint32_t)(hts >> sh) & 15u;
-    hts += 1ull << sh;
+    // the column's line word holds its stones: their number is the row the new stone lands on (one POPC instead
+    // of 64-bit nibble arithmetic on a packed height register: 0.723 -> 0.672 ms per 4 Mi 8x9 games)
+    const uint32_t caddr = lines + (LG::COL0 + c) * (LINES_THREADS * 4);
+    const uint32_t xc0 = lds_u32(caddr);
+    const uint32_t h = (uint32_t)__popc(xc0);
     if (h == (uint32_t)(H - 1)) toprow |= 1u << c;
     if (ACT == 1) act_row[t] = (uint8_t)c;
     if (ACT == 2) blk |= c << (4 * J);
@@ -869,7 +871,8 @@ __device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint64_t& hts, uint3
     t += 1;
     const uint32_t bc = 1u << (c + 16u * P), bh = 1u << (h + 16u * P);
     const uint32_t xr = line_or(lines, h, bc);                                // row h, position c
-    const uint32_t xc = line_or(lines, LG::COL0 + c, bh);                     // column c, position h
+    const uint32_t xc = xc0 | bh;                                             // column c, position h
+    sts_u32(caddr, xc);
     const uint32_t xd = line_or(lines, LG::DIA0 + c + (uint32_t)(H - 1) - h, bc);  // diagonal (c - h const)
     const uint32_t xa = line_or(lines, LG::ANT0 + c + h, bc);                 // anti-diagonal (c + h const)
     // Two lines per run test: the mover's 16-bit halves of two line words side by side (one PRMT).  Bit 15
@@ -945,7 +948,6 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     const uint32_t f_x0 = fr0 * (LINES_THREADS * 4), f_x1 = (fr0 + 1u < (unsigned)H ? fr0 + 1u : fr0) * (LINES_THREADS * 4);
 
     uint32_t toprow = 0, t = 0;
-    uint64_t hts = 0;
     int res = BGS_WINNER_DRAW;
     bool alive = false, retired = false;
     uint32_t idx = 0, pool_next = 0, pool_cnt = 0;
@@ -1029,7 +1031,7 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                     // slower: 0.852 against 0.804 ms per 4 Mi 8x9 games; the 8-way bank conflicts stall the warp)
 #pragma unroll
                     for (int li = 0; li < LG::NL; ++li) my_lines[li * LINES_THREADS] = 0u;
-                    toprow = 0; hts = 0; res = BGS_WINNER_DRAW;
+                    toprow = 0; res = BGS_WINNER_DRAW;
                     alive = true;
                 } else {
                     retired = true;
@@ -1046,10 +1048,10 @@ connect_rollout_lines_kernel(const RolloutParams p) {
         const bool started = alive;
         const uint32_t tb = t;
         uint32_t blk = ACT == 3 ? 0xFFFFFFFFu : 0u;
-        if (alive) alive = lines_ply<H, W, K, 0, ACT>(toprow, hts, r[0], t, res, lut8, lines, act_row, blk);
-        if (alive) alive = lines_ply<H, W, K, 1, ACT>(toprow, hts, r[1], t, res, lut8, lines, act_row, blk);
-        if (alive) alive = lines_ply<H, W, K, 2, ACT>(toprow, hts, r[2], t, res, lut8, lines, act_row, blk);
-        if (alive) alive = lines_ply<H, W, K, 3, ACT>(toprow, hts, r[3], t, res, lut8, lines, act_row, blk);
+        if (alive) alive = lines_ply<H, W, K, 0, ACT>(toprow, r[0], t, res, lut8, lines, act_row, blk);
+        if (alive) alive = lines_ply<H, W, K, 1, ACT>(toprow, r[1], t, res, lut8, lines, act_row, blk);
+        if (alive) alive = lines_ply<H, W, K, 2, ACT>(toprow, r[2], t, res, lut8, lines, act_row, blk);
+        if (alive) alive = lines_ply<H, W, K, 3, ACT>(toprow, r[3], t, res, lut8, lines, act_row, blk);
         if (ACT == 2 && started) *reinterpret_cast<uint16_t*>(act_row + (tb >> 1)) = (uint16_t)blk;
         if (ACT == 3 && started) *reinterpret_cast<uint32_t*>(act_row + tb) = blk;
     }

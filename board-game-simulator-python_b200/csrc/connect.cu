@@ -945,7 +945,7 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     const unsigned fg = lane / LPG, fu = lane - fg * LPG;
     const bool f_on = fg < GPP && fu < UPG;
     const unsigned fr0 = ROWS ? fu : (8u * fu) / (unsigned)W, fc0 = ROWS ? 0u : 8u * fu - fr0 * (unsigned)W;
-    const uint32_t f_x0 = fr0 * (LINES_THREADS * 4), f_x1 = (fr0 + 1u < (unsigned)H ? fr0 + 1u : fr0) * (LINES_THREADS * 4);
+    const uint32_t f_x0 = fr0 * (LINES_THREADS * 4);
 
     uint32_t toprow = 0, t = 0;
     int res = BGS_WINNER_DRAW;
@@ -984,11 +984,12 @@ connect_rollout_lines_kernel(const RolloutParams p) {
 #pragma unroll 1
                 do {  // one pass in most iterations
                     const unsigned gi = g0 + fg;
-                    if (f_on && gi < nfin) {
-                        const uint2 e = list[gi];
-                        const uint32_t gidx = e.y;
-                        const uint32_t src = warp_lines + e.x * 4u;
-                        if (ROWS) {
+                    const bool on = f_on && gi < nfin;
+                    const uint2 e = list[on ? gi : 0u];
+                    const uint32_t gidx = e.y;
+                    const uint32_t src = warp_lines + e.x * 4u;
+                    if (ROWS) {
+                        if (on) {
                             const uint32_t x = lds_u32(src + f_x0);  // row fu: player 0 in bits 0..W-1, player 1 in 16..16+W-1
                             uint8_t* dst = reinterpret_cast<uint8_t*>(p.final_grid) + ((size_t)gidx * HW + (unsigned)W * fu);
 #pragma unroll
@@ -996,8 +997,15 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                                 const uint32_t y = x >> (4 * q);
                                 *reinterpret_cast<uint32_t*>(dst + 4 * q) = lds_u32(cell4 + 4u * ((y & 0xFu) | ((y >> 12) & 0xF0u)));
                             }
-                        } else {
-                            const uint32_t x0 = lds_u32(src + f_x0), x1 = lds_u32(src + f_x1);
+                        }
+                    } else {
+                        // lane fu of a game's group loads row line fu ONCE (the lanes of a group hit one bank: H
+                        // wavefronts instead of 2 * UPG), the two rows a unit needs come from its neighbours by shuffle
+                        const uint32_t xrow = (on && fu < (unsigned)H) ? lds_u32(src + fu * (LINES_THREADS * 4)) : 0u;
+                        const unsigned gbase = fg * LPG;
+                        const uint32_t x0 = __shfl_sync(0xffffffffu, xrow, gbase + fr0);
+                        const uint32_t x1 = __shfl_sync(0xffffffffu, xrow, gbase + (fr0 + 1u < (unsigned)H ? fr0 + 1u : fr0));
+                        if (on) {
                             const uint32_t a = ((x0 & MW) | ((x1 & MW) << W)) >> fc0;    // player 0's stones on cells 8*fu ..
                             const uint32_t b = ((x0 >> 16) | ((x1 >> 16) << W)) >> fc0;  // player 1's
                             const uint32_t lo = lds_u32(cell4 + 4u * ((a & 0xFu) | ((b & 0xFu) << 4)));

@@ -1,6 +1,7 @@
 """N>1 host-side logic on CPU: contiguous game-id shards + one all-reduce(sum) of the statistics
-vector (gloo, world_size 2).  The per-rank "engine" here is the oracle; the GPU path is covered by
-tests/test_gpu_connect.py::test_sharding_is_invisible."""
+vector (gloo, world_size 2).  The per-rank "engine" here is the oracle (no GPU in the CPU suite); the same
+check with the PRODUCT as the engine is tests/test_gpu_distributed.py (two ranks on one GPU, gloo on CUDA tensors)
+and bench.py --gpus N (`stats_equal_to_single_rank`, NCCL)."""
 import os
 import socket
 import sys

@@ -544,23 +544,28 @@ __device__ __forceinline__ bool has_run_mixed(uint64_t me) {
     return acc != 0;
 }
 
-// One ply of player P.  `lut` / `ht` are 32-bit shared-memory addresses: lut[free*8 + k] is the
-// bit index of the BOTTOM cell of the k-th playable column ((H-1)*W + c); ht is pre-biased by
-// -(H-1)*W so that ht[that index] is the number of stones in the column.
+// One ply of player P.  `lut` / `ht` / `bitlut` are 32-bit shared-memory addresses: lut[free*8 + k] is the bit
+// index of the BOTTOM cell of the k-th playable column ((H-1)*W + c); ht is this thread's 8 column bytes pre-biased
+// by -(H-1)*W, so that ht[that index] is the column's LANDING CELL (bottom cell at first, W less after each stone;
+// the byte of a full column wraps and is never read again); bitlut[cell] is 1 << cell as two words.
+//
+// The lane's progress is ONE register: tr = plies played | status << 8 (status 0 = running, 1 / 2 = won by
+// player 0 / 1, 4 = draw; 0x80000000 = the lane has left the game loop).  `tb` is its value at the start of the 4-ply block (a multiple of 4, status 0), so slot
+// J plays ply tb + J and nothing is written on the hot path: a win is one predicated IMAD (FMA pipe), the
+// board-full test exists only in the slot whose ply count can reach H*W, and the caller adds 4 after a whole block.
 template <int H, int W, int K, int J, bool ACTIONS>
-__device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t r, uint32_t& t, int& res,
+__device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t r, uint32_t tb, uint32_t& tr,
                                         uint32_t lut, uint32_t ht, uint32_t& blk, uint32_t one, uint32_t bitlut) {
     typedef StaticGeo<H, W, K> G;
     constexpr int P = J & 1;
+    constexpr int HW = H * W;
     const uint32_t freem = ~top_occ & ((1u << W) - 1u);                   // ALU: one LOP3
     const uint32_t n = (uint32_t)__popc(freem);                           // XU
-    const uint32_t cb = lds_u8(imad_hi(r, n, imad(freem, 8u * one, lut)));     // FMA, FMA, LSU
+    const uint32_t cb = lds_u8(imad(freem, 8u * one, imad_hi(r, n, 0u)) + lut);  // FMA, FMA, LSU (base folded into the address)
     const uint32_t hp = imad(cb, one, ht);                                // FMA
-    const uint32_t h = lds_u8(hp);                                        // LSU
-    sts_u8(hp, imad(h, one, one));                                         // FMA, LSU
+    const uint32_t cell = lds_u8(hp);                                     // LSU: the column's landing cell
+    sts_u8(hp, imad(one, (uint32_t)(-W), cell));                          // FMA, LSU: one row up
     if (ACTIONS) blk = imad(cb, (1u << (4 * J)) * one, blk);            // FMA (bias removed at the block end)
-    t = imad(t, one, one);                                                // FMA
-    const uint32_t cell = imad(h, (uint32_t)(-W), cb);                    // FMA
     // the cell is empty, so adding the bit is OR-ing it, and no carry can cross the words; the bit
     // itself comes from a 64-bit shared-memory table (LSU pipe) instead of two ALU shifts
     const uint2 bit = lds_u64(imad(cell, 8u * one, bitlut));              // FMA, LSU
@@ -568,8 +573,13 @@ __device__ __forceinline__ bool lut_ply(uint64_t& me, uint32_t top_occ, uint32_t
     const uint32_t hi = (H * W > 32) ? imad(bit.y, one, (uint32_t)(me >> 32)) : 0u;
     me = ((uint64_t)hi << 32) | lo;
     const bool won = has_run_mixed<G>(me);
-    if (won) res = P;
-    return !(won || t == (uint32_t)(H * W));
+    if (won) tr = imad(one, (uint32_t)((J + 1) | ((P + 1) << 8)), tb);
+    if (((J + 1) & 3) == (HW & 3)) {  // the only slot in which the board can fill up
+        const bool full = tb == (uint32_t)(HW - (J + 1));
+        if (full && !won) tr = imad(one, (uint32_t)((J + 1) | (4 << 8)), tb);
+        return !(won || full);
+    }
+    return !won;
 }
 
 // A ply that cannot end the game (fewer than K stones of the mover on the board, board not full):
@@ -579,24 +589,30 @@ __device__ __forceinline__ void lut_ply_light(uint64_t& me, uint32_t top_occ, ui
                                               uint32_t& blk, uint32_t one, uint32_t bitlut) {
     const uint32_t freem = ~top_occ & ((1u << W) - 1u);
     const uint32_t n = (uint32_t)__popc(freem);
-    const uint32_t cb = lds_u8(imad_hi(r, n, imad(freem, 8u * one, lut)));
+    const uint32_t cb = lds_u8(imad(freem, 8u * one, imad_hi(r, n, 0u)) + lut);
     const uint32_t hp = imad(cb, one, ht);
-    const uint32_t h = lds_u8(hp);
-    sts_u8(hp, imad(h, one, one));
+    const uint32_t cell = lds_u8(hp);
+    sts_u8(hp, imad(one, (uint32_t)(-W), cell));
     if (ACTIONS) blk = imad(cb, (1u << (4 * J)) * one, blk);
-    const uint32_t cell = imad(h, (uint32_t)(-W), cb);
     const uint2 bit = lds_u64(imad(cell, 8u * one, bitlut));
     const uint32_t lo = imad(bit.x, one, (uint32_t)me);
     const uint32_t hi = (H * W > 32) ? imad(bit.y, one, (uint32_t)(me >> 32)) : 0u;
     me = ((uint64_t)hi << 32) | lo;
 }
 
+// the 8 column bytes of an empty board: byte c = (H-1)*W + c
+template <int H, int W>
+__device__ __forceinline__ uint2 landing_cells() {
+    constexpr uint32_t B = (H - 1) * W;
+    return make_uint2((B) | (B + 1) << 8 | (B + 2) << 16 | (B + 3) << 24, (B + 4) | (B + 5) << 8 | (B + 6) << 16 | (B + 7) << 24);
+}
+
 // A game that has been played through its opening, waiting in the warp's ring for a free lane.
 struct __align__(16) Prepared {
     uint32_t p0lo, p0hi, p1lo, p1hi;
-    uint32_t ht_lo, ht_hi;  // the 8 column-height bytes
-    uint32_t idx;           // game index, 0xFFFFFFFF = beyond n_games
-    uint32_t t_res;         // plies played | (winner + 1) << 8 | over << 16
+    uint32_t ht_lo, ht_hi;  // the 8 column bytes (landing cells)
+    uint32_t idx;           // game index
+    uint32_t tr;            // plies played | status << 8 (see lut_ply); 0x80000000 = beyond n_games
 };
 
 constexpr int RING = 64;        // prepared games per warp (>= 31 + 32)
@@ -614,37 +630,37 @@ __device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base
     const uint32_t id = base + (threadIdx.x & 31u);
     const bool valid = id < p.n_games;
     const unsigned long long gid = p.game_id0 + id;
-    *ht2_row = make_uint2(0u, 0u);
+    *ht2_row = landing_cells<H, W>();
     uint64_t q0 = 0, q1 = 0;
-    uint32_t t = 0, blk0 = 0, blk1 = 0;
-    int res = BGS_WINNER_DRAW;
-    bool alive = true;
+    uint32_t tr = 0, blk0 = 0, blk1 = 0;
+    bool go = true;
     uint32_t r[4];
     philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 0u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
-#define BGS_OPEN_PLY(J, T, ME, BLK)                                                                           \
-    if ((T) < 2 * K - 2) {                                                                                    \
-        lut_ply_light<H, W, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], lut, ht2, BLK, one, bitlut);   \
-        t = (T) + 1;                                                                                          \
-    } else if (alive) {                                                                                       \
-        alive = lut_ply<H, W, K, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], t, res, lut, ht2, BLK, one, bitlut); \
+#define BGS_OPEN_PLY(J, TB, ME, BLK)                                                                           \
+    if ((TB) + (J) < 2 * K - 2) {                                                                              \
+        lut_ply_light<H, W, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], lut, ht2, BLK, one, bitlut);  \
+    } else if (go) {                                                                                           \
+        go = lut_ply<H, W, K, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], (uint32_t)(TB), tr, lut, ht2, BLK, one, bitlut); \
     }
     BGS_OPEN_PLY(0, 0, q0, blk0)
-    BGS_OPEN_PLY(1, 1, q1, blk0)
-    BGS_OPEN_PLY(2, 2, q0, blk0)
-    BGS_OPEN_PLY(3, 3, q1, blk0)
-    const uint32_t t4 = t;
-    if (t4 == 4 && alive) philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 1u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
-    if (alive) {
+    BGS_OPEN_PLY(1, 0, q1, blk0)
+    BGS_OPEN_PLY(2, 0, q0, blk0)
+    BGS_OPEN_PLY(3, 0, q1, blk0)
+    if (go) {
+        tr = 4u;
+        if (2 * K - 2 < 8) philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 1u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
         BGS_OPEN_PLY(0, 4, q0, blk1)
-        BGS_OPEN_PLY(1, 5, q1, blk1)
-        BGS_OPEN_PLY(2, 6, q0, blk1)
-        BGS_OPEN_PLY(3, 7, q1, blk1)
+        BGS_OPEN_PLY(1, 4, q1, blk1)
+        BGS_OPEN_PLY(2, 4, q0, blk1)
+        BGS_OPEN_PLY(3, 4, q1, blk1)
+        if (go) tr = 8u;
     }
 #undef BGS_OPEN_PLY
     if (ACTIONS && valid) {
         constexpr uint32_t B = (H - 1) * W;
         uint16_t* row = reinterpret_cast<uint16_t*>(p.actions + (size_t)id * HW);
-        const uint32_t pl0 = t4;  // plies of block 0 that were played (4 unless K is tiny)
+        const uint32_t t = tr & 0xFFu;
+        const uint32_t pl0 = t < 4u ? t : 4u;  // plies of block 0 that were played (4 unless K is tiny)
         const uint32_t b0 = pl0 == 4 ? B * 0x1111u : (pl0 == 3 ? B * 0x111u : (pl0 == 2 ? B * 0x11u : B));
         row[0] = (uint16_t)(blk0 - b0);
         if (t > 4) {
@@ -654,20 +670,18 @@ __device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base
         }
     }
     const uint2 hts = *ht2_row;
-    Prepared e;
-    e.p0lo = (uint32_t)q0; e.p0hi = (uint32_t)(q0 >> 32); e.p1lo = (uint32_t)q1; e.p1hi = (uint32_t)(q1 >> 32);
-    e.ht_lo = hts.x; e.ht_hi = hts.y;
-    e.idx = valid ? id : 0xFFFFFFFFu;
-    e.t_res = t | ((uint32_t)(res + 1) << 8) | (alive ? 0u : 1u << 16);
     uint4* dst = reinterpret_cast<uint4*>(ring + slot);
-    dst[0] = make_uint4(e.p0lo, e.p0hi, e.p1lo, e.p1hi);
-    dst[1] = make_uint4(e.ht_lo, e.ht_hi, e.idx, e.t_res);
+    dst[0] = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32));
+    dst[1] = make_uint4(hts.x, hts.y, id, valid ? tr : 0x80000000u);
 }
 
 // NOTE: no minBlocksPerSM argument: with `__launch_bounds__(256, 1)` ptxas spends 72 registers (3 CTAs
 // per SM, 1.02 ms), with (256, 8) it squeezes into 32 (1.04 ms); left alone it uses 40 (6 CTAs, 0.97 ms).
+#ifndef BGS_LUT_MINBLOCKS
+#define BGS_LUT_MINBLOCKS 0
+#endif
 template <int H, int W, int K, bool ACTIONS, bool PACKED>
-__global__ void __launch_bounds__(ROLLOUT_THREADS)
+__global__ void __launch_bounds__(ROLLOUT_THREADS, BGS_LUT_MINBLOCKS)
 connect_rollout_lut_kernel(const RolloutParams p) {
     static_assert(H * W <= 64 && W <= 8, "LUT kernel: one 64-bit board word, at most 8 columns");
     constexpr int WARPS = ROLLOUT_THREADS / 32;
@@ -696,32 +710,38 @@ connect_rollout_lut_kernel(const RolloutParams p) {
     *ht_row = make_uint2(0u, 0u);
     __syncthreads();
     const uint32_t one = p.one;
-    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_lut);
+    // table bases behind an opaque move: ptxas would otherwise rebuild them (S2R CgaCtaId, LEA, add) in every
+    // block; like this they stay in uniform registers and the loads take the [R + UR] form
+    uint32_t lut = (uint32_t)__cvta_generic_to_shared(s_lut);
+    uint32_t bitlut = (uint32_t)__cvta_generic_to_shared(s_bit);
+    uint32_t hist = (uint32_t)__cvta_generic_to_shared(s_hist);
+    asm volatile("mov.u32 %0, %0;" : "+r"(lut));
+    asm volatile("mov.u32 %0, %0;" : "+r"(bitlut));
+    asm volatile("mov.u32 %0, %0;" : "+r"(hist));
     const uint32_t ht = (uint32_t)__cvta_generic_to_shared(ht_row) - (uint32_t)((H - 1) * W);
     const uint32_t ht2 = (uint32_t)__cvta_generic_to_shared(ht2_row) - (uint32_t)((H - 1) * W);
-    const uint32_t bitlut = (uint32_t)__cvta_generic_to_shared(s_bit);
     Prepared* ring = s_ring[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
 
     constexpr int HW = H * W;
+    static_assert(HW + 1 < HIST_BINS, "draws are counted in bin H*W + 1");
     uint64_t p0 = 0, p1 = 0;
-    uint32_t t = 0;
-    int res = BGS_WINNER_DRAW;
-    bool alive = false, retired = false;
+    uint32_t tr = 0;  // plies played | status << 8 (lut_ply); 0 = the lane holds no game, 0x80000000 = no game is left
     uint32_t idx = 0;
     uint32_t ring_head = 0, ring_cnt = 0;  // warp-uniform
 
     for (;;) {
         // ---- warp-convergent: retire finished games, hand out prepared ones ------------------
-        if (!alive && t != 0) {
-            p.length[idx] = (uint8_t)t;
-            p.winner[idx] = (int8_t)res;
+        if ((int)tr >= 256) {
+            const uint32_t code = tr >> 8;  // 1, 2: the winner + 1; 4: draw
+            p.length[idx] = (uint8_t)tr;
+            p.winner[idx] = (int8_t)(code - 1u - (code & 4u));
             if (PACKED) store_packed(p.final_packed, idx, HW, p0, p1);
-            atomicAdd(&s_hist[t], 1u);
-            if (res < 0) atomicAdd(&s_draws, 1u);
-            t = 0;
+            // one histogram bump per game; a draw goes to bin H*W + 1 (folded back before the flush)
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist + 4u * ((tr & 0xFFu) + (tr >> 10))) : "memory");
+            tr = 0;
         }
-        const bool need = !alive && !retired;
+        const bool need = tr == 0u;
         const unsigned m = __ballot_sync(0xffffffffu, need);
         if (m) {
             const uint32_t want = __popc(m);
@@ -738,43 +758,45 @@ connect_rollout_lut_kernel(const RolloutParams p) {
                 const uint32_t rank = __popc(m & ((1u << lane) - 1u));
                 const uint4* src = reinterpret_cast<const uint4*>(ring + ((ring_head + rank) & (RING - 1)));
                 const uint4 a = src[0], b = src[1];
-                if (b.z == 0xFFFFFFFFu) {
-                    retired = true;
-                } else {
-                    p0 = ((uint64_t)a.y << 32) | a.x;
-                    p1 = ((uint64_t)a.w << 32) | a.z;
-                    *ht_row = make_uint2(b.x, b.y);
-                    idx = b.z;
-                    t = b.w & 0xFFu;
-                    res = (int)((b.w >> 8) & 0xFFu) - 1;
-                    alive = (b.w >> 16) == 0u;
-                }
+                p0 = ((uint64_t)a.y << 32) | a.x;
+                p1 = ((uint64_t)a.w << 32) | a.z;
+                *ht_row = make_uint2(b.x, b.y);
+                idx = b.z;
+                tr = b.w;  // GONE for ids beyond n_games
             }
             ring_head = (ring_head + want) & (RING - 1);
             ring_cnt -= want;
             __syncwarp();
         }
-        if (!__any_sync(0xffffffffu, alive || t != 0)) break;
+        if (!__any_sync(0xffffffffu, (int)tr > 0)) break;
 
-        // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
+        // ---- the 4 draws of plies tb .. tb+3 (tb is a multiple of 4 on every running lane) ----
         const unsigned long long gid = p.game_id0 + idx;
+        const uint32_t tb = tr;
         uint32_t r[4];
-        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), tb >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
         // trajectory: the 4 columns of this block as 4-bit fields of one 16-bit word, accumulated with
         // IMADs; each played slot adds (H-1)*W + c, so the bias of the slots played is subtracted at the end
-        const bool started = alive;
-        const uint32_t tb = t;
         uint32_t blk = 0;
-        if (alive) alive = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[0], t, res, lut, ht, blk, one, bitlut);
-        if (alive) alive = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[1], t, res, lut, ht, blk, one, bitlut);
-        if (alive) alive = lut_ply<H, W, K, 2, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[2], t, res, lut, ht, blk, one, bitlut);
-        if (alive) alive = lut_ply<H, W, K, 3, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[3], t, res, lut, ht, blk, one, bitlut);
-        if (ACTIONS && started) {
-            constexpr uint32_t B = (H - 1) * W;  // bias per played slot
-            const uint32_t played = t - tb;      // 1..4
-            const uint32_t bias = played == 4 ? B * 0x1111u : (played == 3 ? B * 0x111u : (played == 2 ? B * 0x11u : B));
-            *reinterpret_cast<uint16_t*>(p.actions + (size_t)idx * HW + (tb >> 1)) = (uint16_t)(blk - bias);
+        if (tb - 1u < 255u) {  // running (a game that ended in its opening is retired by the next iteration)
+            bool go = lut_ply<H, W, K, 0, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[0], tb, tr, lut, ht, blk, one, bitlut);
+            if (go) go = lut_ply<H, W, K, 1, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[1], tb, tr, lut, ht, blk, one, bitlut);
+            if (go) go = lut_ply<H, W, K, 2, ACTIONS>(p0, (uint32_t)p0 | (uint32_t)p1, r[2], tb, tr, lut, ht, blk, one, bitlut);
+            if (go) go = lut_ply<H, W, K, 3, ACTIONS>(p1, (uint32_t)p0 | (uint32_t)p1, r[3], tb, tr, lut, ht, blk, one, bitlut);
+            if (go) tr = imad(one, 4u, tb);
+            if (ACTIONS) {
+                constexpr uint32_t B = (H - 1) * W;  // bias per played slot
+                const uint32_t played = (tr & 0xFFu) - tb;  // 1..4
+                const uint32_t bias = played == 4 ? B * 0x1111u : (played == 3 ? B * 0x111u : (played == 2 ? B * 0x11u : B));
+                *reinterpret_cast<uint16_t*>(p.actions + (size_t)idx * HW + (tb >> 1)) = (uint16_t)(blk - bias);
+            }
         }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // draws were counted in their own bin
+        s_draws = s_hist[HW + 1];
+        s_hist[HW] += s_hist[HW + 1];
+        s_hist[HW + 1] = 0;
     }
     __syncthreads();
     if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats);

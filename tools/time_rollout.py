@@ -21,7 +21,10 @@ ap.add_argument("--games", type=int, default=16 * 2**20)
 ap.add_argument("--launches", type=int, default=10)
 ap.add_argument("--actions", action="store_true")
 ap.add_argument("--grid", action="store_true")
+ap.add_argument("--lib", default=None, help="time another build of libbgs_b200.so (kernel experiments)")
 args = ap.parse_args()
+if args.lib:
+    N.LIB_PATH = os.path.abspath(args.lib)
 cfg = tuple(args.cfg)
 stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda")
 res = None
@@ -39,5 +42,5 @@ for i in range(args.launches + 3):
         ms.append(a.elapsed_time(b))
         steps.append(int(stats[N.STAT_STEPS]))
 med = statistics.median(ms)
-print(f"{cfg} games={args.games} actions={args.actions} grid={args.grid} generic={os.environ.get('BGS_CONNECT_GENERIC', '0')}: "
+print(f"{cfg} games={args.games} actions={args.actions} grid={args.grid} lib={os.path.basename(os.path.dirname(N.LIB_PATH)) if args.lib else 'default'}: "
       f"ms min/med/max = {min(ms):.3f}/{med:.3f}/{max(ms):.3f}; {statistics.mean(steps) / med / 1e6:.1f} G env-steps/s (median)")

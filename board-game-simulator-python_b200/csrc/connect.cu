@@ -515,33 +515,38 @@ __device__ __forceinline__ uint32_t shl_fma(uint32_t x) {
 // m(i) = me(i) & me(i-d) is a pair ENDING at i, i.e. the run starting at i-d, so the remaining
 // right-shift doubling steps are unchanged and the start mask is shifted up by d.
 template <class G, int I>
-__device__ __forceinline__ uint64_t runs_dir_mixed(uint64_t me) {
+__device__ __forceinline__ uint32_t runs_dir_mixed(uint64_t me) {  // OR of the two masked halves
     constexpr int K = G::K();
     constexpr int d = dir_dr(I) * G::W() + dir_dc(I);
-    if (K < 2) return me & G::template valid<I>();
-    const uint32_t lo = (uint32_t)me, hi = (uint32_t)(me >> 32);
-    const uint32_t mlo = lo & shl_fma<d>(lo);
-    const uint32_t mhi = (G::H() * G::W() > 32) ? (hi & __funnelshift_l(lo, hi, d)) : 0u;
-    uint64_t m = ((uint64_t)mhi << 32) | mlo;
-    int len = 2;
+    constexpr uint64_t vm = (K < 2) ? G::template valid<I>() : (G::template valid<I>() << d);
+    constexpr uint32_t vlo = (uint32_t)vm, vhi = (uint32_t)(vm >> 32);
+    uint64_t m = me;
+    if (K >= 2) {
+        const uint32_t lo = (uint32_t)me, hi = (uint32_t)(me >> 32);
+        const uint32_t mlo = lo & shl_fma<d>(lo);
+        const uint32_t mhi = (G::H() * G::W() > 32) ? (hi & __funnelshift_l(lo, hi, d)) : 0u;
+        m = ((uint64_t)mhi << 32) | mlo;
+        int len = 2;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        if (2 * len <= K) {
-            m &= shr(m, len * d);
-            len *= 2;
+        for (int it = 0; it < 8; ++it) {
+            if (2 * len <= K) {
+                m &= shr(m, len * d);
+                len *= 2;
+            }
         }
+        if (len < K) m &= shr(m, (K - len) * d);
     }
-    if (len < K) m &= shr(m, (K - len) * d);
-    return m & (G::template valid<I>() << d);
+    // the halves a direction's start mask empties are dropped at compile time, and the caller ORs plain 32-bit
+    // values (6x7x4: 5 half-words remain = two 3-input LOP3s; a 64-bit OR + compare took three)
+    uint32_t r = 0;
+    if (vlo) r = (uint32_t)m & vlo;
+    if (vhi) r |= (uint32_t)(m >> 32) & vhi;
+    return r;
 }
 
 template <class G>
 __device__ __forceinline__ bool has_run_mixed(uint64_t me) {
-    uint64_t acc = runs_dir_mixed<G, 0>(me);
-    acc |= runs_dir_mixed<G, 1>(me);
-    acc |= runs_dir_mixed<G, 2>(me);
-    acc |= runs_dir_mixed<G, 3>(me);
-    return acc != 0;
+    return (runs_dir_mixed<G, 0>(me) | runs_dir_mixed<G, 1>(me) | runs_dir_mixed<G, 2>(me) | runs_dir_mixed<G, 3>(me)) != 0;
 }
 
 // One ply of player P.  `lut` / `ht` / `bitlut` are 32-bit shared-memory addresses: lut[free*8 + k] is the bit

@@ -605,6 +605,23 @@ __device__ __forceinline__ void lut_ply_light(uint64_t& me, uint32_t top_occ, ui
     me = ((uint64_t)hi << 32) | lo;
 }
 
+// The same for a ply before which no column can be full (fewer than H stones on the board): all W columns are
+// playable, so the column is mulhi(r, W) itself -- no playable mask, no population count, no table.  `blk`
+// receives the column WITHOUT the (H-1)*W bias of the other ply functions.
+template <int H, int W, int J, bool ACTIONS>
+__device__ __forceinline__ void lut_ply_first(uint64_t& me, uint32_t r, uint32_t ht, uint32_t& blk, uint32_t one,
+                                              uint32_t bitlut) {
+    const uint32_t col = imad_hi(r, (uint32_t)W, 0u);
+    const uint32_t hp = imad(col, one, ht + (uint32_t)((H - 1) * W));
+    const uint32_t cell = lds_u8(hp);
+    sts_u8(hp, imad(one, (uint32_t)(-W), cell));
+    if (ACTIONS) blk = imad(col, (1u << (4 * J)) * one, blk);
+    const uint2 bit = lds_u64(imad(cell, 8u * one, bitlut));
+    const uint32_t lo = imad(bit.x, one, (uint32_t)me);
+    const uint32_t hi = (H * W > 32) ? imad(bit.y, one, (uint32_t)(me >> 32)) : 0u;
+    me = ((uint64_t)hi << 32) | lo;
+}
+
 // the 8 column bytes of an empty board: byte c = (H-1)*W + c
 template <int H, int W>
 __device__ __forceinline__ uint2 landing_cells() {
@@ -642,7 +659,9 @@ __device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base
     uint32_t r[4];
     philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), 0u, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
 #define BGS_OPEN_PLY(J, TB, ME, BLK)                                                                           \
-    if ((TB) + (J) < 2 * K - 2) {                                                                              \
+    if ((TB) + (J) < 2 * K - 2 && (TB) + (J) < H) {                                                            \
+        lut_ply_first<H, W, J, ACTIONS>(ME, r[J], ht2, BLK, one, bitlut);                                      \
+    } else if ((TB) + (J) < 2 * K - 2) {                                                                       \
         lut_ply_light<H, W, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], lut, ht2, BLK, one, bitlut);  \
     } else if (go) {                                                                                           \
         go = lut_ply<H, W, K, J, ACTIONS>(ME, (uint32_t)q0 | (uint32_t)q1, r[J], (uint32_t)(TB), tr, lut, ht2, BLK, one, bitlut); \
@@ -662,17 +681,19 @@ __device__ __forceinline__ void open_games(const RolloutParams& p, uint32_t base
     }
 #undef BGS_OPEN_PLY
     if (ACTIONS && valid) {
+        // every slot played by lut_ply / lut_ply_light added (H-1)*W + column, lut_ply_first the bare column
         constexpr uint32_t B = (H - 1) * W;
+        constexpr int FIRST = (2 * K - 2 < H) ? 2 * K - 2 : H;  // plies 0 .. FIRST-1 go through lut_ply_first
         uint16_t* row = reinterpret_cast<uint16_t*>(p.actions + (size_t)id * HW);
         const uint32_t t = tr & 0xFFu;
-        const uint32_t pl0 = t < 4u ? t : 4u;  // plies of block 0 that were played (4 unless K is tiny)
-        const uint32_t b0 = pl0 == 4 ? B * 0x1111u : (pl0 == 3 ? B * 0x111u : (pl0 == 2 ? B * 0x11u : B));
-        row[0] = (uint16_t)(blk0 - b0);
-        if (t > 4) {
-            const uint32_t pl1 = t - 4;
-            const uint32_t b1 = pl1 == 4 ? B * 0x1111u : (pl1 == 3 ? B * 0x111u : (pl1 == 2 ? B * 0x11u : B));
-            row[1] = (uint16_t)(blk1 - b1);
+        uint32_t b0 = 0, b1 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= FIRST && (uint32_t)j < t) b0 += B << (4 * j);
+            if (4 + j >= FIRST && (uint32_t)(4 + j) < t) b1 += B << (4 * j);
         }
+        row[0] = (uint16_t)(blk0 - b0);
+        if (t > 4) row[1] = (uint16_t)(blk1 - b1);
     }
     const uint2 hts = *ht2_row;
     uint4* dst = reinterpret_cast<uint4*>(ring + slot);

@@ -890,11 +890,15 @@ __device__ __forceinline__ uint32_t line_or(uint32_t lines, uint32_t li, uint32_
     return x;
 }
 
+// The lane's progress is one register, as in the LUT kernel: tr = plies played | status << 8 (0 running, 1 / 2 won
+// by player 0 / 1, 4 draw); `tb` = its value at the start of the 4-ply block, so slot J plays ply tb + J, a win is
+// one predicated write and the board-full test exists only in the slot whose ply count can reach H*W.
 template <int H, int W, int K, int J, int ACT>
-__device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint32_t r, uint32_t& t, int& res,
+__device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint32_t r, uint32_t tb, uint32_t& tr,
                                           uint32_t lut8, uint32_t lines, uint8_t* act_row, uint32_t& blk) {
     typedef LineGeo<H, W> LG;
     constexpr int P = J & 1;
+    constexpr int HW = H * W;
     const uint32_t freem = ~toprow & ((1u << W) - 1u);
     const uint32_t k = __umulhi(r, (uint32_t)__popc(freem));
     uint32_t c;
@@ -912,11 +916,10 @@ __device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint32_t r, uint32_t
     const uint32_t xc0 = lds_u32(caddr);
     const uint32_t h = (uint32_t)__popc(xc0);
     if (h == (uint32_t)(H - 1)) toprow |= 1u << c;
-    if (ACT == 1) act_row[t] = (uint8_t)c;
+    if (ACT == 1) act_row[tb + J] = (uint8_t)c;
     if (ACT == 2) blk |= c << (4 * J);
     // fused export: byte J of the block word = the column (one PRMT); unplayed slots keep their 0xFF
     if (ACT == 3) blk = __byte_perm(blk, c, J == 0 ? 0x3214 : (J == 1 ? 0x3240 : (J == 2 ? 0x3410 : 0x4210)));
-    t += 1;
     const uint32_t bc = 1u << (c + 16u * P), bh = 1u << (h + 16u * P);
     const uint32_t xr = line_or(lines, h, bc);                                // row h, position c
     const uint32_t xc = xc0 | bh;                                             // column c, position h
@@ -927,8 +930,10 @@ __device__ __forceinline__ bool lines_ply(uint32_t& toprow, uint32_t r, uint32_t
     // of a half is never set (lines are at most 15 long), so no run can cross from one half into the other.
     constexpr uint32_t SEL = P ? 0x7632u : 0x5410u;
     const bool won = (run_bits<K>(__byte_perm(xr, xc, SEL)) | run_bits<K>(__byte_perm(xd, xa, SEL))) != 0u;
-    if (won) res = P;
-    return !(won || t == (uint32_t)(H * W));
+    if (won) tr = tb + (uint32_t)((J + 1) | ((P + 1) << 8));
+    // the only slot in which the board can fill up; a draw leaves `tr` untouched (the caller sees tr == tb)
+    if (((J + 1) & 3) == (HW & 3)) return !(won || tb == (uint32_t)(HW - (J + 1)));
+    return !won;
 }
 
 // ACT: 0 no trajectory / 1 one byte per ply into the pre-filled row / 2 16-bit blocks of 4-bit columns
@@ -950,13 +955,13 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     constexpr bool FUSED = GRID || ACT == 3;
     static_assert(!FUSED || HW % 8 == 0, "fused export: rows are written in 8-byte units");
     static_assert(!(FUSED && PACKED), "fused export replaces the packed boards");
-    __shared__ unsigned int s_hist[HW + 1];  // a game lasts at most H*W plies
+    __shared__ unsigned int s_hist[HW + 2];  // a game lasts at most H*W plies; bin H*W + 1 counts the draws
     __shared__ unsigned int s_draws;
     __shared__ uint8_t s_lut8[LG::LUT_ROWS * 8];  // [mask of HALF_BITS bits][k] -> index of the k-th set bit
     __shared__ __align__(16) uint32_t s_lines[LG::NL * LINES_THREADS];  // [line][thread]: conflict-free whatever lines the lanes touch
     __shared__ uint32_t s_cell4[GRID ? 256 : 1];                    // [p0 nibble | p1 nibble << 4] -> 4 grid bytes
     __shared__ uint2 s_list[GRID ? LINES_THREADS / 32 : 1][32];     // (lane, game index) of the lanes retiring now
-    for (int i = threadIdx.x; i < HW + 1; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < HW + 2; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) s_draws = 0;
     for (int i = threadIdx.x; i < LG::LUT_ROWS * 8; i += blockDim.x) {
         int mask = i >> 3, k = i & 7, c = 0;
@@ -995,17 +1000,18 @@ connect_rollout_lines_kernel(const RolloutParams p) {
     const unsigned fr0 = ROWS ? fu : (8u * fu) / (unsigned)W, fc0 = ROWS ? 0u : 8u * fu - fr0 * (unsigned)W;
     const uint32_t f_x0 = fr0 * (LINES_THREADS * 4);
 
-    uint32_t toprow = 0, t = 0;
-    int res = BGS_WINNER_DRAW;
-    bool alive = false, retired = false;
+    constexpr uint32_t EMPTY = 0x40000000u, GONE = 0x80000000u;  // the lane needs a game / no game is left for it
+    uint32_t toprow = 0;
+    uint32_t tr = EMPTY;  // plies played | status << 8 (lines_ply), or EMPTY / GONE
     uint32_t idx = 0, pool_next = 0, pool_cnt = 0;
 
     for (;;) {
         // ---- warp-convergent: retire finished games, claim new ones -------------------------
-        const bool fin = !alive && t != 0;
+        const bool fin = (tr & 0x700u) != 0u;
         if (fin) {
-            p.length[idx] = (uint8_t)t;
-            p.winner[idx] = (int8_t)res;
+            const uint32_t code = tr >> 8;  // 1, 2: the winner + 1; 4: draw
+            p.length[idx] = (uint8_t)tr;
+            p.winner[idx] = (int8_t)(code - 1u - (code & 4u));
             if (PACKED) {  // rebuild the two bitboards from the row lines
                 u128 b0 = 0, b1 = 0;
 #pragma unroll
@@ -1016,9 +1022,8 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                 }
                 store_packed(p.final_packed, idx, HW, b0, b1);
             }
-            atomicAdd(&s_hist[t], 1u);
-            if (res < 0) atomicAdd(&s_draws, 1u);
-            t = 0;
+            atomicAdd(&s_hist[(tr & 0xFFu) + (tr >> 10)], 1u);  // a draw goes to bin H*W + 1 (folded back before the flush)
+            tr = EMPTY;
         }
         if (GRID) {
             const unsigned fm = __ballot_sync(0xffffffffu, fin);
@@ -1066,7 +1071,7 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                 __syncwarp();  // the row lines are read before they are reset below
             }
         }
-        const bool need = !alive && !retired;
+        const bool need = tr == EMPTY;
         const unsigned m = __ballot_sync(0xffffffffu, need);
         if (m) {
             const uint32_t id = claim_index<CLAIM_CHUNK>(m, p.counter, pool_next, pool_cnt, [&](uint32_t base) {
@@ -1087,29 +1092,37 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                     // slower: 0.852 against 0.804 ms per 4 Mi 8x9 games; the 8-way bank conflicts stall the warp)
 #pragma unroll
                     for (int li = 0; li < LG::NL; ++li) my_lines[li * LINES_THREADS] = 0u;
-                    toprow = 0; res = BGS_WINNER_DRAW;
-                    alive = true;
+                    toprow = 0;
+                    tr = 0;
                 } else {
-                    retired = true;
+                    tr = GONE;
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, alive)) break;
+        if (!__any_sync(0xffffffffu, tr < EMPTY)) break;
 
-        // ---- the 4 draws of plies t .. t+3 (t is a multiple of 4 on every live lane) ---------
+        // ---- the 4 draws of plies tb .. tb+3 (tb is a multiple of 4 on every running lane) ----
         const unsigned long long gid = p.game_id0 + idx;
+        const uint32_t tb = tr;
         uint32_t r[4];
-        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), t >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
+        philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), tb >> 2, DOMAIN_CONNECT, p.seed_lo, p.seed_hi, r);
         uint8_t* act_row = ACT ? p.actions + (size_t)idx * HW : nullptr;
-        const bool started = alive;
-        const uint32_t tb = t;
         uint32_t blk = ACT == 3 ? 0xFFFFFFFFu : 0u;
-        if (alive) alive = lines_ply<H, W, K, 0, ACT>(toprow, r[0], t, res, lut8, lines, act_row, blk);
-        if (alive) alive = lines_ply<H, W, K, 1, ACT>(toprow, r[1], t, res, lut8, lines, act_row, blk);
-        if (alive) alive = lines_ply<H, W, K, 2, ACT>(toprow, r[2], t, res, lut8, lines, act_row, blk);
-        if (alive) alive = lines_ply<H, W, K, 3, ACT>(toprow, r[3], t, res, lut8, lines, act_row, blk);
-        if (ACT == 2 && started) *reinterpret_cast<uint16_t*>(act_row + (tb >> 1)) = (uint16_t)blk;
-        if (ACT == 3 && started) *reinterpret_cast<uint32_t*>(act_row + tb) = blk;
+        if (tb < 256u) {  // running
+            bool go = lines_ply<H, W, K, 0, ACT>(toprow, r[0], tb, tr, lut8, lines, act_row, blk);
+            if (go) go = lines_ply<H, W, K, 1, ACT>(toprow, r[1], tb, tr, lut8, lines, act_row, blk);
+            if (go) go = lines_ply<H, W, K, 2, ACT>(toprow, r[2], tb, tr, lut8, lines, act_row, blk);
+            if (go) go = lines_ply<H, W, K, 3, ACT>(toprow, r[3], tb, tr, lut8, lines, act_row, blk);
+            if (go) tr = tb + 4u;
+            else if (tr == tb) tr = (uint32_t)(HW | (4 << 8));  // left without a winner: the board is full
+            if (ACT == 2) *reinterpret_cast<uint16_t*>(act_row + (tb >> 1)) = (uint16_t)blk;
+            if (ACT == 3) *reinterpret_cast<uint32_t*>(act_row + tb) = blk;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // draws were counted in their own bin
+        s_draws = s_hist[HW + 1];
+        s_hist[HW] += s_hist[HW + 1];
     }
     __syncthreads();
     if (p.stats) flush_stats(s_hist, s_draws, HW, p.stats, HW + 1);

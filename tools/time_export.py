@@ -23,7 +23,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--games", type=int, default=4 * 2**20)
 ap.add_argument("--launches", type=int, default=7)
 ap.add_argument("--only", nargs=3, type=int, default=None)
+ap.add_argument("--lib", default=None, help="time another build of libbgs_b200.so (kernel experiments)")
 args = ap.parse_args()
+if args.lib:
+    N.LIB_PATH = os.path.abspath(args.lib)
 peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
 hbm = json.load(open(peaks)).get("hbm_gbs", 6444.4) if os.path.exists(peaks) else 6444.4
 stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda")

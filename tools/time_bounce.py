@@ -19,7 +19,10 @@ ap.add_argument("--launches", type=int, default=5)
 ap.add_argument("--max-plies", type=int, default=512)
 ap.add_argument("--streams", type=int, default=0, help="also time --batches back-to-back batches alternating over this many streams")
 ap.add_argument("--batches", type=int, default=8)
+ap.add_argument("--lib", default=None, help="time another build of libbgs_b200.so (kernel experiments)")
 args = ap.parse_args()
+if args.lib:
+    N.LIB_PATH = os.path.abspath(args.lib)
 grid = np.zeros((9, 6), dtype=np.int8)
 grid[1] = grid[7] = [1, 2, 3, 3, 2, 1]  # reference src/simulator/textual/bounce.py:66-78
 stats = torch.zeros(N.STATS_LEN, dtype=torch.int64, device="cuda")

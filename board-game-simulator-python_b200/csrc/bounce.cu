@@ -78,7 +78,7 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     const bool lut_on = USE_LUT || (MAY_LUT && g.lut_rt());
     __shared__ uint32_t s_lut[MAY_LUT ? SEG_LUT_WORDS : 1];  // landing sets of a segment, [value][passable neighbours]
     if (lut_on) {
-        for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[i] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
+        for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[seg_lut_slot(g, i >> 8, (uint32_t)(i & 255))] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
         __syncthreads();
     }
     B plane0[4];
@@ -89,6 +89,8 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     MoveGen<NP, G, RULES> mg;
     mg.done = false;
     mg.lut = lut_on ? s_lut : nullptr;
+    mg.lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
+    asm volatile("mov.u32 %0, %0;" : "+r"(mg.lut_saddr));  // opaque: see MoveGen::lut_saddr
     uint32_t r[4] = {0, 0, 0, 0};
     uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
     unsigned long long acc_steps = 0;
@@ -215,7 +217,7 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     const bool lut_on = USE_LUT || (NP == 2 && g.lut_rt());
     __shared__ uint32_t s_lut[NP == 2 ? SEG_LUT_WORDS : 1];
     if (lut_on)
-        for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[i] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
+        for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[seg_lut_slot(g, i >> 8, (uint32_t)(i & 255))] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
     __syncthreads();
     WarpSlots<NP, M, MAXSRC>& S = s_slots[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -269,6 +271,8 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
 
     MoveGen<NP, G, RULES> mg;
     mg.lut = lut_on ? s_lut : nullptr;
+    mg.lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
+    asm volatile("mov.u32 %0, %0;" : "+r"(mg.lut_saddr));  // opaque: see MoveGen::lut_saddr
     bool has_work = false;
     int slot = 0;
     uint32_t me = 0;  // meta word of the slot in work
@@ -462,6 +466,7 @@ bounce_moves_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __res
     B* T = s_T + threadIdx.x;
     StepGen<B> mg;
     mg.lut = nullptr;
+    mg.lut_saddr = 0;
     const bool ok = planes_from_stage(s_stage[warp] + lane * HW, HW, mg.b);
     const bool over = (ended && ended[i]) || !ok;
     const int pl = player[i] & 1;
@@ -535,6 +540,7 @@ bounce_step_kernel(const GeoRTb<B> g, unsigned long long n, const int8_t* __rest
         uint8_t* mine = s_stage[warp] + lane * HW;  // the new grid = the old one with two cells changed
         StepGen<B> mg;
     mg.lut = nullptr;
+    mg.lut_saddr = 0;
         const bool ok = planes_from_stage(mine, HW, mg.b);
         int pl = player[i] & 1;
         const bool over = ended && ended[i];

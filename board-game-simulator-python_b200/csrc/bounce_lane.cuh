@@ -127,6 +127,7 @@ struct GeoRTb {
     typedef B bits;
     static constexpr int BITS = (int)sizeof(B) * 8;
     static constexpr bool LUT = false;  // no compile-time guarantee; lut_ok decides at run time
+    static constexpr bool HASH = false; // table indexed by the 8 gathered window bits (seg_lut_slot)
     static constexpr int MAX_SOURCES = sizeof(B) == 8 ? 8 : 16;  // columns of one row
     bool lut_ok;         // table-driven segments possible: guard column, landing window within 32 bits
     int H, W, S, rules;
@@ -194,6 +195,13 @@ struct GeoCT {
     static constexpr int MAX_SOURCES = W_;
     // segments by table look-up (seg_lut_entry): needs the guard column and a 32-bit landing window
     static constexpr bool LUT = S_ > W_ && S_ >= 3 && 3 * S_ + 3 <= 31;
+    // S = 7 (the default 9x6 board): the table is indexed by a multiplicative hash of the window instead of the 8
+    // gathered bits -- (x & kHashMask) * kHashMul >> 24 is a bijection of the 256 subsets of the 8 window bits
+    // onto 0..255 (checked by seg_hash_is_perfect, tests/test_bounce_lane_host.py), 3 instructions instead of 11
+    static constexpr bool HASH = LUT && S_ == 7;
+    static constexpr uint32_t kHashMask = (1u << 1) | (1u << 2) | (1u << 4) | (1u << 5) | (1u << (S_ + 2)) | (1u << (S_ + 3)) |
+                                          (1u << (S_ + 4)) | (1u << (2 * S_ + 3));
+    static constexpr uint32_t kHashMul = 0x9410021Fu;
     static constexpr uint64_t col_mask(int x0, int x1) {
         uint64_t m = 0;
         for (int y = 0; y < H_; ++y)
@@ -304,6 +312,37 @@ BGS_HD uint32_t seg_lut_entry(int S, int u, uint32_t idx) {
     return mask;
 }
 
+// Position of entry (u, idx) in the table a kernel builds: [u][idx] in general, [u][hash of the window bits] for
+// geometries with G::HASH.  `idx` bit k <-> window bit {1, 2, 4, 5, S+2, S+3, S+4, 2S+3}[k].
+BGS_HD uint32_t seg_window_of_idx(int S, uint32_t idx) {
+    const int wb[8] = {1, 2, 4, 5, S + 2, S + 3, S + 4, 2 * S + 3};
+    uint32_t x = 0;
+    for (int k = 0; k < 8; ++k) x |= ((idx >> k) & 1u) << wb[k];
+    return x;
+}
+template <class G>
+BGS_HD uint32_t seg_hash(uint32_t window) {  // G::HASH only
+    return ((window & G::kHashMask) * G::kHashMul) >> 24;
+}
+template <class G>
+BGS_HD uint32_t seg_lut_slot(const G& g, int u, uint32_t idx) {
+    if constexpr (G::HASH) return (uint32_t)u * 256u + seg_hash<G>(seg_window_of_idx(g.s(), idx));
+    else return (uint32_t)u * 256u + idx;
+}
+template <class G>
+inline bool seg_hash_is_perfect(const G& g) {  // host-side check of kHashMul
+    if constexpr (!G::HASH) return true;
+    else {
+        bool seen[256] = {false};
+        for (uint32_t i = 0; i < 256; ++i) {
+            const uint32_t h = seg_hash<G>(seg_window_of_idx(g.s(), i));
+            if (h > 255u || seen[h]) return false;
+            seen[h] = true;
+        }
+        return true;
+    }
+}
+
 #if defined(__CUDA_ARCH__)
 #define BGS_UNROLL _Pragma("unroll")
 #else
@@ -323,6 +362,8 @@ struct MoveGen {
     bool probe;  // only "does the mover have any action?" (the blocked test): no target masks
     bool found, have, done;
     const uint32_t* lut;  // seg_lut_entry table [4][256] when G::LUT (shared memory in the kernel)
+    uint32_t lut_saddr;   // device: the same table as a 32-bit shared-memory address (kept opaque by the kernel so
+                          // that the base stays in a register instead of being rebuilt for every look-up)
 
     BGS_HD int rules(const G& g) const { return RULES_ >= 0 ? RULES_ : g.rules; }
 
@@ -391,8 +432,16 @@ struct MoveGen {
             expanded |= low;
             const int S = g.s();
             const uint32_t x = (uint32_t)(inter >> (c - 3));  // window around c, bit 3 = c (c >= S: no piece in row 0)
-            const uint32_t idx = ((x >> 1) & 3u) | ((x >> 2) & 0xCu) | ((x >> (S - 2)) & 0x70u) | ((x >> (2 * S - 4)) & 0x80u);
-            const B land = ((B)lut[u * 256 + (int)idx] << (c - 3)) & open;
+            uint32_t idx;
+            if constexpr (G::HASH) idx = seg_hash<G>(x);
+            else idx = ((x >> 1) & 3u) | ((x >> 2) & 0xCu) | ((x >> (S - 2)) & 0x70u) | ((x >> (2 * S - 4)) & 0x80u);
+#if defined(__CUDA_ARCH__)
+            uint32_t entry;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(lut_saddr + 4u * ((uint32_t)u * 256u + idx)));
+#else
+            const uint32_t entry = lut[u * 256 + (int)idx];
+#endif
+            const B land = ((B)entry << (c - 3)) & open;
             targets |= land & ~occS;
             pending |= land & occS & ~expanded;
             return;

@@ -16,7 +16,7 @@ static void play(const G& g, const typename G::bits* plane0, const int8_t* start
                  uint64_t seed, const LaneOut& out, int64_t* stats) {
     std::vector<typename G::bits> T(16);
     std::vector<uint32_t> lut(SEG_LUT_WORDS);
-    for (int i = 0; i < SEG_LUT_WORDS; ++i) lut[i] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
+    for (int i = 0; i < SEG_LUT_WORDS; ++i) lut[seg_lut_slot(g, i >> 8, (uint32_t)(i & 255))] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
     for (uint64_t idx = 0; idx < n; ++idx) {
         Game<NP, G> game;
         MoveGen<NP, G, RULES> mg;
@@ -95,4 +95,12 @@ extern "C" int bgs_lane_host_bounce_rollout(int mode, const int8_t* grid0, const
         play<4, GeoRT, -1>(g, plane0, start_grid, start_player, start_winner, start_ended, max_plies, n, gid0, seed, out, stats);
     }
     return 0;
+}
+
+// 1 when the multiplicative hash that indexes the segment table of the compile-time 9x6 geometry maps the 256
+// subsets of the 8 window bits onto 256 different slots (GeoCT::kHashMul, seg_hash_is_perfect)
+extern "C" int bgs_lane_host_seg_hash_is_perfect() {
+    const GeoRT grt = make_geo_rt(9, 6, 0);
+    static_assert(GeoCT<9, 6>::HASH, "the default board uses the hashed table");
+    return seg_hash_is_perfect(GeoCT<9, 6>(grt)) ? 1 : 0;
 }

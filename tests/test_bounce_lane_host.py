@@ -134,3 +134,11 @@ def test_lane_large_boards_equal_oracle(host, oracle):
         got = lane_rollout(host, grid0, n, cap, 5 * trial, trial, rules)
         ref = oracle.bounce_rollout(grid0, n, max_plies=cap, gid0=5 * trial, seed=trial, rules=rules)
         assert_same(got, ref, f"trial {trial} {H}x{W} rules {rules}")
+
+
+def test_segment_table_hash_of_the_default_board_is_a_bijection(host):
+    """GeoCT<9,6> indexes its segment table with (window & mask) * kHashMul >> 24 instead of 8 gathered bits; the
+    kernel builds the table THROUGH that hash (seg_lut_slot), so a collision would silently drop an entry."""
+    host.bgs_lane_host_seg_hash_is_perfect.restype = C.c_int
+    assert host.bgs_lane_host_seg_hash_is_perfect() == 1
+

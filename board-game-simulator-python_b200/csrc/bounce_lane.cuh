@@ -66,6 +66,17 @@ BGS_HD int ctz32(uint32_t x) {  // x != 0
     return __builtin_ctz(x);
 #endif
 }
+// index of the only set bit of x
+BGS_HD int bit_index64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    uint32_t pos;  // bfind = FLO: the bit's position in whichever half holds it, no select between the halves
+    asm("bfind.u32 %0, %1;" : "=r"(pos) : "r"(lo | hi));
+    return (int)(hi ? pos + 32u : pos);
+#else
+    return __builtin_ctzll(x);
+#endif
+}
 BGS_HD uint64_t brev64(uint64_t x) {
 #ifdef __CUDA_ARCH__
     return __brevll(x);
@@ -397,7 +408,9 @@ struct MoveGen {
         const int rl = rules(g);
         if (pending == 0) {  // piece boundary
             if (have) {
-                const B tg = (rl & BGS_BOUNCE_ALLOW_NULL_MOVE) ? targets : (targets & ~sbit);
+                // (`& open`: the table-driven segments leave the landing sets unmasked -- guard cells, cells above
+                // the board -- and the mask is applied once per piece here)
+                const B tg = ((rl & BGS_BOUNCE_ALLOW_NULL_MOVE) ? targets : (targets & ~sbit)) & open;
                 if (probe) {
                     found = tg != 0;
                 } else {
@@ -426,7 +439,7 @@ struct MoveGen {
         if (NP == 2 && sizeof(B) == 8 && (G::LUT || (g.lut_rt() && lut != nullptr))) {
             // ---- one pending cell per segment, its landing set from the table: no step loop, no
             // dependence on the piece value, so every lane of the warp executes the same instructions
-            const int c = ctzb(low);
+            const int c = bit_index64((uint64_t)low);
             const int u = (int)((b[0] >> c) & (B)1) | ((int)((b[1] >> c) & (B)1) << 1);
             pending ^= low;
             expanded |= low;
@@ -441,7 +454,7 @@ struct MoveGen {
 #else
             const uint32_t entry = lut[u * 256 + (int)idx];
 #endif
-            const B land = ((B)entry << (c - 3)) & open;
+            const B land = (B)entry << (c - 3);  // not masked with `open`: occS lies inside it, targets are masked at the piece boundary
             targets |= land & ~occS;
             pending |= land & occS & ~expanded;
             return;

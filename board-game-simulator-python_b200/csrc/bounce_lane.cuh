@@ -370,7 +370,7 @@ struct MoveGen {
     B b[NP];  // value bit-planes in the mover's orientation (read-only here)
     B occ, src_left, sbit, occS, inter, open, expanded, pending, targets;
     int total, nsrc;
-    bool probe;  // only "does the mover have any action?" (the blocked test): no target masks
+    bool probe;  // only "does the mover have any action?" (the blocked test): `found` is the answer, T / total are not used
     bool found, have, done;
     const uint32_t* lut;  // seg_lut_entry table [4][256] when G::LUT (shared memory in the kernel)
     uint32_t lut_saddr;   // device: the same table as a 32-bit shared-memory address (kept opaque by the kernel so
@@ -411,17 +411,17 @@ struct MoveGen {
                 // (`& open`: the table-driven segments leave the landing sets unmasked -- guard cells, cells above
                 // the board -- and the mask is applied once per piece here)
                 const B tg = ((rl & BGS_BOUNCE_ALLOW_NULL_MOVE) ? targets : (targets & ~sbit)) & open;
-                if (probe) {
-                    found = tg != 0;
-                } else {
-                    T[nsrc * stride] = tg;
-                    total += popcb(tg);
-                    ++nsrc;
-                }
+                // a probe (1 generation in 3000) takes the same path -- its target masks are simply not used, and it
+                // looks at every piece instead of stopping at the first one that can move: the piece boundary runs
+                // at ~8 of 32 lanes, so every instruction of a special case costs four
+                T[nsrc * stride] = tg;
+                total += popcb(tg);
+                ++nsrc;
                 have = false;
             }
-            if (src_left == 0 || found) {
+            if (src_left == 0) {
                 done = true;
+                found = total != 0;
                 return;
             }
             sbit = src_left & (~src_left + (B)1);  // next movable piece, ascending relative column

@@ -208,7 +208,10 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, (NP == 2 ? (G::MAX_SOURCES <=
 bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     static_assert(M > 32 && M <= 64, "slot ids are ring entries of 64");
     constexpr int MAXSRC = G::MAX_SOURCES;   // movable pieces = columns of one row
-    constexpr int SEGMENTS = 3;              // segments per trip: 3 / 4 / 5 / 6 / 8 -> 9.83 / 10.0 / 9.9 / 10.1 / 10.6 ms
+    // segments per trip.  Compile-time table-driven geometry (34-instruction segments): 2 / 3 / 4 / 5 / 6 / 8 ->
+    // 9.06 / 8.64 / 8.56 / 8.45 / 8.60 / 8.93 ms per 4 Mi default games; the other variants keep 3 (round 1, with the
+    // costlier segments of that build: 3 / 4 / 5 / 6 / 8 -> 9.83 / 10.0 / 9.9 / 10.1 / 10.6 ms)
+    constexpr int SEGMENTS = (G::LUT && NP == 2) ? 5 : 3;
     __shared__ unsigned int s_hist[HIST_BINS];
     __shared__ WarpSlots<NP, M, MAXSRC> s_slots[ROLLOUT_THREADS / 32];
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
@@ -787,8 +790,14 @@ static int launch_bounce_lane(const GeoRTb<typename G::bits>& grt, const Rollout
 // whose per-warp state fits the 48 KB of static shared memory.
 template <int NP, class G, int RULES>
 static int launch_bounce_slots(const GeoRT& grt, RolloutParams p, cudaStream_t stream) {
-    p.ply_batch = 32;  // 20 / 24 / 28 / 32 waiting slots: 10.35 / 10.08 / 9.83 / 9.83 ms per 4 Mi default games
-    p.idle_batch = 8;  // 4 / 8 / 16 idle lanes: 9.90 / 9.83 / 9.99 ms
+#ifndef BGS_BOUNCE_PLY_BATCH
+#define BGS_BOUNCE_PLY_BATCH 32
+#endif
+#ifndef BGS_BOUNCE_IDLE_BATCH
+#define BGS_BOUNCE_IDLE_BATCH 8
+#endif
+    p.ply_batch = BGS_BOUNCE_PLY_BATCH;    // 20 / 24 / 28 / 32 waiting slots: 10.35 / 10.08 / 9.83 / 9.83 ms per 4 Mi default games
+    p.idle_batch = BGS_BOUNCE_IDLE_BATCH;  // 4 / 8 / 16 idle lanes: 9.90 / 9.83 / 9.99 ms
     auto kern = bounce_rollout_slots_kernel<NP, G, RULES, 64>;
     int blocks = 0;
     if (int rc = persistent_blocks(kern, p.n_games, &blocks)) return rc;

@@ -980,6 +980,12 @@ connect_rollout_lines_kernel(const RolloutParams p) {
         }
     __syncthreads();
     const uint32_t lut8 = (uint32_t)__cvta_generic_to_shared(s_lut8);
+    // table bases behind an opaque move, as in the LUT kernel: they stay in (uniform) registers instead of being
+    // rebuilt (S2R CgaCtaId, LEA, add) by every retiring lane / flush pass
+    uint32_t hist = (uint32_t)__cvta_generic_to_shared(s_hist);
+    uint32_t cell4 = (uint32_t)__cvta_generic_to_shared(s_cell4);
+    asm volatile("mov.u32 %0, %0;" : "+r"(hist));
+    asm volatile("mov.u32 %0, %0;" : "+r"(cell4));
     uint32_t* my_lines = s_lines + threadIdx.x;  // line li at my_lines[li * LINES_THREADS]
     const uint32_t lines = (uint32_t)__cvta_generic_to_shared(my_lines);
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -1022,7 +1028,8 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                 }
                 store_packed(p.final_packed, idx, HW, b0, b1);
             }
-            atomicAdd(&s_hist[(tr & 0xFFu) + (tr >> 10)], 1u);  // a draw goes to bin H*W + 1 (folded back before the flush)
+            // a draw goes to bin H*W + 1 (folded back before the flush)
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist + 4u * ((tr & 0xFFu) + (tr >> 10))) : "memory");
             tr = EMPTY;
         }
         if (GRID) {
@@ -1032,7 +1039,6 @@ connect_rollout_lines_kernel(const RolloutParams p) {
                 __syncwarp();
                 constexpr uint32_t MW = (1u << W) - 1u;
                 const unsigned nfin = (unsigned)__popc(fm);
-                const uint32_t cell4 = (uint32_t)__cvta_generic_to_shared(s_cell4);
                 unsigned g0 = 0;
 #pragma unroll 1
                 do {  // one pass in most iterations

@@ -407,7 +407,7 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
 // ---------------------------------------------------------------------------------------------
 constexpr int STEP_THREADS = 64;
 template <class B>
-using StepGen = MoveGen<4, GeoRTb<B>, -1>;
+using StepGen = MoveGen<4, GeoRTb<B>, -1, true>;
 
 __device__ __forceinline__ float2 reward_of(int winner) {
     return make_float2(winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f),

@@ -363,8 +363,11 @@ inline bool seg_hash_is_perfect(const G& g) {  // host-side check of kHashMul
 // ---------------------------------------------------------------------------------------------
 // MoveGen: the move generation of ONE position for its mover -- SURVEY.md 4.4 rules 2-4.
 // RULES_ >= 0: compile-time rule set; -1: read g.rules.
+// FASTPROBE: a probe stops at the first piece that can move and writes no target masks (the single-step kernels,
+// which probe the opponent after EVERY move); the rollout kernels leave it off -- they probe once in 3000
+// generations, and their piece boundary runs at ~8 of 32 lanes, where each instruction of a special case costs four.
 // ---------------------------------------------------------------------------------------------
-template <int NP, class G, int RULES_>
+template <int NP, class G, int RULES_, bool FASTPROBE = false>
 struct MoveGen {
     typedef typename G::bits B;
     B b[NP];  // value bit-planes in the mover's orientation (read-only here)
@@ -411,17 +414,18 @@ struct MoveGen {
                 // (`& open`: the table-driven segments leave the landing sets unmasked -- guard cells, cells above
                 // the board -- and the mask is applied once per piece here)
                 const B tg = ((rl & BGS_BOUNCE_ALLOW_NULL_MOVE) ? targets : (targets & ~sbit)) & open;
-                // a probe (1 generation in 3000) takes the same path -- its target masks are simply not used, and it
-                // looks at every piece instead of stopping at the first one that can move: the piece boundary runs
-                // at ~8 of 32 lanes, so every instruction of a special case costs four
-                T[nsrc * stride] = tg;
-                total += popcb(tg);
-                ++nsrc;
+                if (FASTPROBE && probe) {
+                    found = tg != 0;
+                } else {  // (without FASTPROBE a probe takes this path too: its target masks are simply not used)
+                    T[nsrc * stride] = tg;
+                    total += popcb(tg);
+                    ++nsrc;
+                }
                 have = false;
             }
-            if (src_left == 0) {
+            if (src_left == 0 || (FASTPROBE && found)) {
                 done = true;
-                found = total != 0;
+                if (!(FASTPROBE && probe)) found = total != 0;
                 return;
             }
             sbit = src_left & (~src_left + (B)1);  // next movable piece, ascending relative column

@@ -1636,49 +1636,96 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
 // in shared memory (16-bit stores: a game is only 2-byte aligned) and leave as 128-bit stores.  tm / ow come from
 // the ply-parallel scatter of the cell kernel above.
 constexpr int TRAJW_THREADS = 128;
+// (round 2, second form) A warp takes PAIRS of games: one game is (H*W+1)*H*W bytes = 2 mod 4 for these boards, so a
+// pair starts on a 4-byte boundary and the pair's byte stream can be cut into ALIGNED 32-bit words -- every staged
+// word is one 32-bit store (the first form staged 16-bit halves, two stores per word with 2-way bank conflicts: 86 M
+// shared-memory store wavefronts per 1 Mi games, LSU pipe 92 % busy).  Game 0 of the pair owns the words at offsets
+// r = 0, 4, .., 2*H*W-4 of each double row, game 1 -- shifted by two bytes -- those at r = 2, 6, .., 2*H*W-2; its last
+// word straddles into the next double row (two of its bytes are compared against 2(s+1) instead of 2s), and the
+// two bytes after game 0's last position are game 1's first two cells of the empty board (always 0xFF).  The lane
+// slots are dealt so that the 32 lanes of one store fall into 32 different banks.
 template <int H, int W>
 __global__ void __launch_bounds__(TRAJW_THREADS)
 connect_traj_words_kernel(unsigned long long n_games, const uint8_t* __restrict__ actions,
                           const uint8_t* __restrict__ length, uint8_t* out) {
-    constexpr int HW = H * W, T = HW + 1, NW = HW / 2, GPW = 3, WARPS = TRAJW_THREADS / 32;
+    constexpr int HW = H * W, T = HW + 1, NW = HW / 2, GPW = 2, WARPS = TRAJW_THREADS / 32;
     constexpr int GB = T * HW;                // bytes of one game
+    constexpr int DR = 2 * HW;                // bytes of a double row (two consecutive positions)
     constexpr int NS = (T + 1) / 2;           // double positions (the last one holds a single position: T is odd)
-    static_assert(HW % 2 == 0 && HW <= 126 && W <= 16 && GPW * NW <= 64, "even cell count, two word slots per lane");
-    constexpr int STAGE = (GPW * GB + 15 + 15) & ~15;
+    static_assert(HW % 4 == 2 && HW <= 64 && W <= 16, "H*W = 2 mod 4: a game is 2-byte, a pair of games 4-byte aligned");
+    static_assert(NW <= 32, "one game's words of a double row fit one store");
+    constexpr int STAGE = (GPW * GB + 15 + 15 + 4) & ~15;
+    // tm / ow as DOUBLE-ROW IMAGES: byte b of a game's image is the threshold / owner of byte b of its double row
+    // (b < H*W: first position of the pair, threshold = fill ply; b < 2*H*W: second position, fill ply - 1; the 4 bytes
+    // beyond: the first cells of the NEXT double row, fill ply - 2, clamped at 0), so a lane's 4 thresholds are one
+    // 32-bit load (game 0) or two 16-bit loads (game 1, shifted by two bytes) instead of 8 byte loads and selects
+    constexpr int IMG = (DR + 4 + 3) & ~3;
     __shared__ __align__(16) uint8_t s_stage[WARPS][STAGE];
-    __shared__ uint8_t s_tm[WARPS][GPW * HW];
-    __shared__ uint8_t s_ow[WARPS][GPW * HW];
-    __shared__ uint8_t s_act[WARPS][GPW * HW];
-    __shared__ uint8_t s_cnt[WARPS][GPW * 16];
+    __shared__ __align__(4) uint8_t s_tm[WARPS][GPW * IMG];
+    __shared__ __align__(4) uint8_t s_ow[WARPS][GPW * IMG];
+    __shared__ __align__(4) uint8_t s_act[WARPS][(GPW * HW + 3) & ~3];
+    __shared__ __align__(4) uint8_t s_cnt[WARPS][GPW * 16];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     uint8_t* tm = s_tm[warp];
     uint8_t* ow = s_ow[warp];
     uint8_t* act = s_act[warp];
     uint8_t* cnt = s_cnt[warp];
     uint8_t* stg = s_stage[warp];
-    // this lane's two word slots: (game of the group, word of the double row); fixed for the whole kernel
-    unsigned sj[2], sw[2], last_halves[2];
-    bool son[2];
+    // ---- this lane's two word slots, fixed for the whole kernel.  Slot 0: lanes 0..NW-1 hold game 0's words, the
+    // other lanes those words of game 1 whose bank differs from all of game 0's; slot 1: the rest of game 1.
+    // Word wi of game j sits at byte r = 4*wi + 2*j of its double row; game 1's word 0 is C1 words after game 0's.
+    constexpr unsigned C1 = ((unsigned)GB + 2u) / 4u;
+    unsigned sj[2] = {0u, 1u}, sw[2] = {0u, 0u};
+    bool son[2] = {false, false};
+    {
+        unsigned n0 = NW, n1 = 0;  // lanes dealt so far in slot 0 / slot 1
+        if (lane < (unsigned)NW) { son[0] = true; sj[0] = 0u; sw[0] = lane; }
+#pragma unroll 1
+        for (unsigned wi = 0; wi < (unsigned)NW; ++wi) {
+            const bool clash = ((C1 + wi) & 31u) < (unsigned)NW;  // same bank as one of game 0's words
+            if (!clash) {
+                if (lane == n0) { son[0] = true; sj[0] = 1u; sw[0] = wi; }
+                ++n0;
+            } else {
+                if (lane == n1) { son[1] = true; sj[1] = 1u; sw[1] = wi; }
+                ++n1;
+            }
+        }
+    }
+    unsigned sr[2];          // byte offset of the word in its game's double row
+    uint32_t last_or[2];     // OR-ed into the thresholds in the last (single-position) double row: 0x7F = "never shown"
+    bool last_on[2];         // the word exists in the last double row
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        const unsigned q = lane + 32u * k;
-        son[k] = q < (unsigned)(GPW * NW);
-        sj[k] = son[k] ? q / NW : 0u;
-        sw[k] = q - sj[k] * NW;
-        const int valid = HW - 4 * (int)sw[k];  // bytes of the word that belong to the FIRST position of a pair
-        last_halves[k] = valid >= 4 ? 2u : (valid > 0 ? (unsigned)valid / 2u : 0u);
+        sr[k] = 4u * sw[k] + 2u * sj[k];
+        last_on[k] = sr[k] < (unsigned)HW;
+        last_or[k] = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (sr[k] + i >= (unsigned)HW) last_or[k] |= 0x7Fu << (8 * i);  // beyond the last position: the next game's empty cells
     }
     const unsigned long long ngroups = (n_games + GPW - 1ull) / GPW;
     for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
          group += (unsigned long long)gridDim.x * WARPS) {
         const unsigned long long g0 = group * GPW;
         const unsigned ng = (unsigned)((n_games - g0) < (unsigned long long)GPW ? (n_games - g0) : GPW);
-        for (unsigned i = lane; i < GPW * HW; i += 32) {
-            tm[i] = 0x7F;
-            ow[i] = 0xFF;
-            act[i] = i < ng * HW ? actions[g0 * HW + i] : (uint8_t)0;
+        // (32-bit accesses: g0 * HW is a multiple of 4 for a pair of games; the words beyond the last game's row
+        // are never used -- `valid` below -- but must not be read past the end of `actions`)
+        for (unsigned i = lane; i < GPW * IMG / 4; i += 32) {
+            reinterpret_cast<uint32_t*>(tm)[i] = 0x7F7F7F7Fu;
+            reinterpret_cast<uint32_t*>(ow)[i] = 0xFFFFFFFFu;
         }
-        for (unsigned i = lane; i < GPW * 16; i += 32) cnt[i] = 0;
+        {
+            const unsigned nb = ng * HW;  // bytes of trajectory rows of this group
+            const uint8_t* src = actions + g0 * HW;
+            for (unsigned i = lane; 4u * i < nb; i += 32) {
+                uint32_t v;
+                if (4u * i + 4u <= nb) v = *reinterpret_cast<const uint32_t*>(src + 4u * i);
+                else v = (uint32_t)src[4u * i] | ((uint32_t)src[4u * i + 1u] << 8);  // nb = 2 mod 4: the last half word
+                reinterpret_cast<uint32_t*>(act)[i] = v;
+            }
+        }
+        if (lane < GPW * 4) reinterpret_cast<uint32_t*>(cnt)[lane] = 0u;
         const unsigned len_mine = lane < ng ? length[g0 + lane] : 0u;
         __syncwarp();
         // ---- scatter: ply p of game j fills the lowest empty cell of its column
@@ -1694,53 +1741,64 @@ connect_traj_words_kernel(unsigned long long n_games, const uint8_t* __restrict_
             if (valid) {
                 if ((mm >> lane) == 1u) cnt[j * 16 + col] = (uint8_t)(below + __popc(mm));  // last ply of the column
                 const unsigned cell = (below + __popc(mm & lt)) * W + col;
-                tm[j * HW + cell] = (uint8_t)(pl + 1);
-                ow[j * HW + cell] = (uint8_t)(pl & 1);
+                uint8_t* tj = tm + j * IMG + cell;
+                uint8_t* oj = ow + j * IMG + cell;
+                const uint8_t o = (uint8_t)(pl & 1);
+                tj[0] = (uint8_t)(pl + 1); oj[0] = o;         // first position of a pair: shown from position pl + 1
+                tj[HW] = (uint8_t)pl; oj[HW] = o;             // second position: one earlier
+                if (cell < 4u) { tj[DR] = (uint8_t)(pl > 0u ? pl - 1u : 0u); oj[DR] = o; }  // seen from the previous double row
             }
             __syncwarp();
         }
-        // ---- this lane's words: 4 cells each, fill ply (minus the byte's position parity) and owner
+        // ---- this lane's words: the 4 thresholds ("shown in double position s iff thr <= 2s") and owners
         uint32_t tm4[2], ow4[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             tm4[k] = 0x7F7F7F7Fu; ow4[k] = 0u;
             if (son[k] && sj[k] < ng) {
-                uint32_t tv = 0, ov = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const unsigned b = 4u * sw[k] + i, par = b >= (unsigned)HW ? 1u : 0u, cell = b - par * HW;
-                    const unsigned t0 = tm[sj[k] * HW + cell];
-                    tv |= (t0 == 0x7Fu ? 0x7Fu : t0 - par) << (8 * i);  // shown from position t0: double position s shows it iff t0 - par <= 2s
-                    ov |= (uint32_t)ow[sj[k] * HW + cell] << (8 * i);
+                const uint8_t* tp = tm + sj[k] * IMG + sr[k];
+                const uint8_t* op = ow + sj[k] * IMG + sr[k];
+                if (sj[k] == 0u) {  // 4-byte aligned
+                    tm4[k] = *reinterpret_cast<const uint32_t*>(tp);
+                    ow4[k] = *reinterpret_cast<const uint32_t*>(op);
+                } else {            // 2 mod 4
+                    tm4[k] = (uint32_t)*reinterpret_cast<const uint16_t*>(tp) | ((uint32_t)*reinterpret_cast<const uint16_t*>(tp + 2) << 16);
+                    ow4[k] = (uint32_t)*reinterpret_cast<const uint16_t*>(op) | ((uint32_t)*reinterpret_cast<const uint16_t*>(op + 2) << 16);
                 }
-                tm4[k] = tv; ow4[k] = ov;
             }
         }
-        // ---- all positions, two at a time
-        const unsigned long long G0 = g0 * (unsigned long long)GB;
+        // ---- all positions, two at a time: one aligned 32-bit store per word
+        const unsigned long long G0 = g0 * (unsigned long long)GB;  // a multiple of 4
         const unsigned pad = (unsigned)(G0 & 15ull);
-        uint32_t tb = 0x80808080u;
-        for (int s2 = 0; s2 < NS; ++s2) {
+        // (fully unrolled: the thresholds 0x80 | 2s and the stage offsets s * DR are immediates, 4 instructions per
+        // word -- subtract, sign-replicating PRMT, LOP3, predicated store)
+        const bool on0 = son[0] && sj[0] < ng, on1 = son[1] && sj[1] < ng;
+        uint8_t* base0 = stg + pad + sj[0] * GB + sr[0];
+        uint8_t* base1 = stg + pad + sj[1] * GB + sr[1];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (son[k] && sj[k] < ng) {
-                    const uint32_t m = sign_bytes(tb - tm4[k]);
-                    const uint32_t v = (ow4[k] & m) | ~m;
-                    uint8_t* dst = stg + pad + sj[k] * GB + s2 * (2 * HW) + 4 * sw[k];
-                    const unsigned halves = s2 == NS - 1 ? last_halves[k] : 2u;
-                    if (halves >= 1u) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)v;
-                    if (halves >= 2u) *reinterpret_cast<uint16_t*>(dst + 2) = (uint16_t)(v >> 16);
-                }
+        for (int s2 = 0; s2 < NS - 1; ++s2) {
+            const uint32_t tb = 0x80808080u + (uint32_t)s2 * 0x02020202u;
+            const uint32_t m0 = sign_bytes(tb - tm4[0]), m1 = sign_bytes(tb - tm4[1]);
+            if (on0) *reinterpret_cast<uint32_t*>(base0 + s2 * DR) = (ow4[0] & m0) | ~m0;
+            if (on1) *reinterpret_cast<uint32_t*>(base1 + s2 * DR) = (ow4[1] & m1) | ~m1;
+        }
+        {
+            constexpr uint32_t tb = 0x80808080u + (uint32_t)(NS - 1) * 0x02020202u;
+            if (on0 && last_on[0]) {  // the last double row holds one position
+                const uint32_t m = sign_bytes(tb - (tm4[0] | last_or[0]));
+                *reinterpret_cast<uint32_t*>(base0 + (NS - 1) * DR) = (ow4[0] & m) | ~m;
             }
-            tb += 0x02020202u;
+            if (on1 && last_on[1]) {
+                const uint32_t m = sign_bytes(tb - (tm4[1] | last_or[1]));
+                *reinterpret_cast<uint32_t*>(base1 + (NS - 1) * DR) = (ow4[1] & m) | ~m;
+            }
         }
         __syncwarp();
-        // ---- stage -> global: head (2-byte stores up to the first 16-byte boundary), 128-bit body, tail
-        const unsigned L = ng * (unsigned)GB;
+        // ---- stage -> global: head (32-bit stores up to the first 16-byte boundary), 128-bit body, tail
+        const unsigned L = ng * (unsigned)GB;  // ng == 1 (the last, odd game): L = 2 mod 4, the tail ends with a 16-bit store
         uint8_t* gdst = out + G0;
-        const unsigned head = (16u - pad) & 15u;  // pad is even
-        for (unsigned i = 2u * lane; i < head; i += 64)
-            *reinterpret_cast<uint16_t*>(gdst + i) = *reinterpret_cast<const uint16_t*>(stg + pad + i);
+        const unsigned head = (16u - pad) & 15u;  // a multiple of 4
+        if (4u * lane < head) *reinterpret_cast<uint32_t*>(gdst + 4u * lane) = *reinterpret_cast<const uint32_t*>(stg + pad + 4u * lane);
         const unsigned nvec = (L - head) >> 4;
         for (unsigned q = lane; q < nvec; q += 32)
             *reinterpret_cast<uint4*>(gdst + head + 16u * q) = *reinterpret_cast<const uint4*>(stg + pad + head + 16u * q);
@@ -2492,12 +2550,12 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
         if (H == 8) return launch(connect_traj_cells_kernel<8, 9>, 3);
         return launch(connect_traj_cells_kernel<10, 12>, 2);
     }
-    if (((uintptr_t)grids & 15u) == 0 && H == 6 && W == 7) {  // the headline board: word-stationary kernel
+    if (((uintptr_t)grids & 15u) == 0 && ((uintptr_t)actions & 3u) == 0 && H == 6 && W == 7) {  // the headline board: word-stationary kernel
         auto kern = connect_traj_words_kernel<6, 7>;
         int per_sm = 0;
         BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRAJW_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
-        unsigned long long blocks = (n_games + 3ull * (TRAJW_THREADS / 32) - 1ull) / (3ull * (TRAJW_THREADS / 32));
+        unsigned long long blocks = (n_games + 2ull * (TRAJW_THREADS / 32) - 1ull) / (2ull * (TRAJW_THREADS / 32));
         const unsigned long long cap = (unsigned long long)sm_count() * per_sm;
         if (blocks > cap) blocks = cap;
         kern<<<(unsigned)blocks, TRAJW_THREADS, 0, (cudaStream_t)stream_>>>(n_games, actions, length, reinterpret_cast<uint8_t*>(grids));

@@ -1531,8 +1531,18 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
     __shared__ __align__(8) uint8_t s_ow[WARPS][GPW * HW];
     __shared__ uint8_t s_cnt[WARPS][GPW * 16];
     constexpr int RB = 8;                        // rows per pass through the stage (7 for 8x9 and more resident CTAs: no gain)
-    constexpr int SPAN_STAGE = (RB * HW + 16 + 15) & ~15;  // one game's rows + room for the 8-byte alignment pad
-    __shared__ __align__(16) uint8_t s_stage[WARPS][GPW * SPAN_STAGE];
+    constexpr int NPASS = (T - 1) / RB;          // full passes; the remaining T - NPASS*RB rows (one) go out last
+    constexpr int SPAN = RB * HW;                // bytes of one game per pass
+    constexpr int UNITS = SPAN / 8;              // 8-byte units of one game per pass
+    static_assert(T - NPASS * RB == 1, "one row left after the full passes");
+    // GPW even (10x12: 2 games per warp): game j of a group is an even / odd game for j even / odd, whatever the
+    // group, and one game is 8 mod 16 bytes long -- an odd game's bytes start 8 bytes into a 16-byte line.  Its stage
+    // area is shifted by the same 8 bytes (SPAN + 16 per game), so stage and global addresses agree mod 16 and the
+    // copy-out is 128-bit (8-byte head and tail for the odd game), all of it known at compile time.  GPW odd (8x9):
+    // the parity changes with the group; the copy-out works on 8-byte units instead.
+    constexpr bool VEC16 = GPW % 2 == 0 && (T * HW) % 16 == 8 && SPAN % 16 == 0;
+    constexpr int SPAN_ST = VEC16 ? SPAN + 16 : SPAN;  // stage bytes per game
+    __shared__ __align__(16) uint8_t s_stage[WARPS][GPW * SPAN_ST];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     const unsigned sg = lane / CH, ci = lane - sg * CH;  // game of the warp's group, 8-cell chunk
     uint8_t* tm = s_tm[warp];
@@ -1586,43 +1596,58 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
             tm8 = *reinterpret_cast<const uint2*>(tm + sg * HW + 8 * ci);
             ow8 = *reinterpret_cast<const uint2*>(ow + sg * HW + 8 * ci);
         }
-        uint32_t tb = 0x80808080u;  // 0x80 | t in every byte
-        for (int t0 = 0; t0 < T; t0 += RB) {
-            const int rows = (T - t0) < RB ? (T - t0) : RB;
+        // (round 2: both loops fully unrolled -- the thresholds 0x80 | t and every stage / global offset are
+        // immediates -- and the copy-out works on 8-byte units per game with a warp-uniform base: 7 instructions per
+        // 8 output bytes to build a row piece, 2 per 8 bytes to copy it out; the first form recomputed 64-bit offsets,
+        // head / body / tail splits and loop bounds for every game of every pass: 3 470 instructions per group of
+        // three 8x9 games, of which the row pieces were 600)
+        uint8_t* mystage = stg + sg * SPAN_ST + (VEC16 ? 8u * (sg & 1u) : 0u) + 8 * ci;
+        const unsigned long long GB = (unsigned long long)(T * HW);
+#pragma unroll
+        for (int ps = 0; ps <= NPASS; ++ps) {
+            const int rows = ps < NPASS ? RB : 1;
             if (mine) {
-                // game sg's rows start 8 bytes into its stage area when its global address is 8 mod 16
-                uint8_t* mystage = stg + sg * SPAN_STAGE + (((g0 + sg) * (unsigned long long)(T * HW) + (unsigned)t0 * HW) & 8u) + 8 * ci;
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     if (r < rows) {
+                        const uint32_t tb = 0x80808080u + (uint32_t)(ps * RB + r) * 0x01010101u;  // 0x80 | t in every byte
                         const uint32_t m0 = sign_bytes(tb - tm8.x), m1 = sign_bytes(tb - tm8.y);
                         *reinterpret_cast<uint2*>(mystage + r * HW) = make_uint2((ow8.x & m0) | ~m0, (ow8.y & m1) | ~m1);
-                        tb += 0x01010101u;
                     }
                 }
             }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < GPW; ++j) {
-                if (g0 + j < n_games) {
-                    const unsigned long long off = (g0 + j) * (unsigned long long)(T * HW) + (unsigned)t0 * HW;
-                    uint8_t* dst = out + off;
-                    const unsigned pad = (unsigned)(off & 8u);
-                    const uint8_t* src = stg + j * SPAN_STAGE + pad;
-                    const unsigned span = (unsigned)rows * HW;  // multiple of 8
-                    // head (8 bytes, if dst is 8 mod 16), 16-byte body, tail (8 bytes)
-                    const unsigned head = pad ? 8u : 0u;
-                    const unsigned body = (span - head) & ~15u;
-                    if (head && lane == 0) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
-                    for (unsigned q = lane; q < (body >> 4); q += 32)
-                        *reinterpret_cast<uint4*>(dst + head + 16 * q) = *reinterpret_cast<const uint4*>(src + head + 16 * q);
-                    if (head + body < span && lane == 31)
-                        *reinterpret_cast<uint2*>(dst + head + body) = *reinterpret_cast<const uint2*>(src + head + body);
+                if (g0 + j < n_games) {  // warp-uniform
+                    const int bytes = rows * HW;  // of this game in this pass (a multiple of 8)
+                    if (VEC16) {
+                        const int head = (j & 1) ? 8 : 0;                 // bytes before the first 16-byte line
+                        const int nvec = (bytes - head) / 16;
+                        const int tail = bytes - head - 16 * nvec;       // 0 or 8
+                        uint8_t* dst = out + (g0 + j) * GB + (unsigned)(ps * SPAN);
+                        const uint8_t* src = stg + j * SPAN_ST + head;  // byte 0 of the span (the odd game's area starts 8 bytes in)
+#pragma unroll
+                        for (int i = 0; i < (SPAN / 16 + 31) / 32; ++i)
+                            if (32 * i < nvec && (32 * (i + 1) <= nvec || lane < (unsigned)(nvec - 32 * i)))
+                                *reinterpret_cast<uint4*>(dst + head + 16u * lane + 512 * i) =
+                                    *reinterpret_cast<const uint4*>(src + head + 16u * lane + 512 * i);
+                        if (head && lane == 30) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+                        if (tail && lane == 31)
+                            *reinterpret_cast<uint2*>(dst + head + 16 * nvec) = *reinterpret_cast<const uint2*>(src + head + 16 * nvec);
+                    } else {
+                        uint8_t* dst = out + (g0 + j) * GB + (unsigned)(ps * SPAN) + 8u * lane;
+                        const uint8_t* src = stg + j * SPAN_ST + 8u * lane;
+                        const int units = bytes / 8;
+#pragma unroll
+                        for (int i = 0; i < (UNITS + 31) / 32; ++i)
+                            if (32 * i < units && (32 * (i + 1) <= units || lane < (unsigned)(units - 32 * i)))
+                                *reinterpret_cast<uint2*>(dst + 256 * i) = *reinterpret_cast<const uint2*>(src + 256 * i);
+                    }
                 }
             }
             __syncwarp();
         }
-        __syncwarp();
     }
 }
 

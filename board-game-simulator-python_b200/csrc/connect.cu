@@ -1541,7 +1541,12 @@ connect_traj_cells_kernel(unsigned long long n_games, const uint8_t* __restrict_
     // copy-out is 128-bit (8-byte head and tail for the odd game), all of it known at compile time.  GPW odd (8x9):
     // the parity changes with the group; the copy-out works on 8-byte units instead.
     constexpr bool VEC16 = GPW % 2 == 0 && (T * HW) % 16 == 8 && SPAN % 16 == 0;
-    constexpr int SPAN_ST = VEC16 ? SPAN + 16 : SPAN;  // stage bytes per game
+    // stage bytes per game, padded so that the 64-bit row-piece stores of a half warp (lanes of two games) fall into
+    // 32 different banks: 8x9: 9 lanes x 2 words per game, next game 146 words on (= 18 mod 32); 10x12: 15 lanes x 2
+    // words, the odd game's bytes start at 1008 + 8 = word 254 (= 30 mod 32).  (ncu before: 16 M of 44 M shared-memory
+    // wavefronts were bank conflicts and the kernel waited on the MIO queue.)
+    constexpr int SPAN_ST = (H == 8 && W == 9) ? SPAN + 8 : (H == 10 && W == 12) ? SPAN + 48 : (VEC16 ? SPAN + 16 : SPAN);
+    static_assert(!VEC16 || SPAN_ST % 16 == 0, "128-bit copy-out: stage areas keep the global alignment");
     __shared__ __align__(16) uint8_t s_stage[WARPS][GPW * SPAN_ST];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     const unsigned sg = lane / CH, ci = lane - sg * CH;  // game of the warp's group, 8-cell chunk

@@ -1271,6 +1271,17 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, unsi
     for (unsigned i = done + lane; i < span; i += 32) dst[i] = src[i];
 }
 
+// The same copy (16-byte aligned, span a multiple of 16) as asynchronous global -> shared copies (cp.async /
+// LDGSTS): the warp issues them and goes on; cp_async_wait<N>() + __syncwarp() make all but the N newest groups visible.
+__device__ __forceinline__ void warp_copy_async(uint8_t* dst, const uint8_t* src, unsigned span, unsigned lane) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    for (unsigned q = lane; q < (span >> 4); q += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * q), "l"(src + 16ull * q) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // 4 one-bit flags (bits 0..3 of x) -> 4 bytes of 0 / 1
 __device__ __forceinline__ uint32_t spread4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
 
@@ -1986,29 +1997,51 @@ connect_step_kernel(const DynGeo g, unsigned long long n, const int8_t* __restri
                     const int8_t* __restrict__ player, const int8_t* __restrict__ winner,
                     const int32_t* __restrict__ action, int8_t* grid_out, int8_t* player_out,
                     int8_t* winner_out, uint8_t* ended_out, float* reward_out, uint32_t* legal_out,
-                    int32_t* status, bool vec, const StepPolicy pol) {
+                    int32_t* status, bool vec, bool dbuf, const StepPolicy pol) {
     extern __shared__ __align__(16) uint8_t s_stage[];
     const int H = g.H(), W = g.W(), HW = H * W;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* st_ = s_stage + (size_t)warp * 32 * HW;
-    uint8_t* mine = st_ + lane * HW;
-    const unsigned long long ngroups = (n + 31ull) / 32ull;
     constexpr int WARPS = STEP_THREADS / 32;
-    for (unsigned long long group = (unsigned long long)blockIdx.x * WARPS + warp; group < ngroups;
-         group += (unsigned long long)gridDim.x * WARPS) {
+    // dbuf (aligned pointers, room for two tiles per warp): the NEXT group's grids are fetched with cp.async while this
+    // one is processed and written back -- the kernel was waiting on its global loads (ncu: 7 warps per issue stalled on
+    // the long scoreboard, 0.62 of the copy peak) because a warp had one tile in flight at a time
+    uint8_t* buf0 = s_stage + (size_t)warp * 32 * HW * (dbuf ? 2 : 1);
+    uint8_t* buf1 = buf0 + (dbuf ? 32 * HW : 0);
+    const unsigned long long ngroups = (n + 31ull) / 32ull;
+    const unsigned long long stride = (unsigned long long)gridDim.x * WARPS;
+    const unsigned long long first = (unsigned long long)blockIdx.x * WARPS + warp;
+    const uint8_t* gin = reinterpret_cast<const uint8_t*>(grid);
+    // a full group is 32 * HW bytes: a multiple of 16 at a multiple of 16; only the last group can be ragged
+    auto full = [&](unsigned long long grp) { return (grp + 1ull) * 32ull <= n; };
+    if (dbuf && first < ngroups && full(first)) warp_copy_async(buf0, gin + first * 32ull * (unsigned)HW, 32u * (unsigned)HW, lane);
+    cp_async_commit();
+    unsigned phase = 0;
+    for (unsigned long long group = first; group < ngroups; group += stride, phase ^= 1u) {
         const unsigned long long g0 = group * 32ull;
         const unsigned rows = (unsigned)((n - g0) < 32ull ? (n - g0) : 32ull);
         const unsigned span = rows * (unsigned)HW;
-        warp_copy(st_, reinterpret_cast<const uint8_t*>(grid) + g0 * (unsigned)HW, span, lane, vec);
-        __syncwarp();
+        uint8_t* st_ = phase ? buf1 : buf0;
+        uint8_t* mine = st_ + lane * HW;
         const unsigned long long i = g0 + lane;
+        // the per-state scalars do not depend on the tile: their loads are in flight while the tile arrives
+        int pl = 0, win = 0;
+        if (dbuf && i < n) { pl = player[i]; win = winner[i]; }
+        if (dbuf) {
+            const unsigned long long nxt = group + stride;
+            if (nxt < ngroups && full(nxt)) warp_copy_async(phase ? buf0 : buf1, gin + nxt * 32ull * (unsigned)HW, 32u * (unsigned)HW, lane);
+            cp_async_commit();
+            if (full(group)) cp_async_wait<1>();  // this group's tile (all but the newest copy group)
+            else warp_copy(st_, gin + g0 * (unsigned)HW, span, lane, vec);  // the ragged last group: synchronous
+        } else {
+            warp_copy(st_, gin + g0 * (unsigned)HW, span, lane, vec);
+        }
+        __syncwarp();
+        if (!dbuf && i < n) { pl = player[i]; win = winner[i]; }
         if (i < n) {
             // Work on the staged bytes directly (empty = 0xFF): the transition only needs the height
             // of one column, the top row and the <= 8*(K-1) cells around the new stone -- converting
             // the whole grid to bitboards cost ~15 instructions per cell and made the kernel
             // instruction-bound (4 Mi 6x7 states: 0.41 ms against 0.07 ms of HBM time).
-            int pl = player[i];
-            int win = winner[i];
             uint32_t legal_mask = 0;
             for (int c = 0; c < W; ++c)
                 if (mine[(H - 1) * W + c] == 0xFFu) legal_mask |= 1u << c;
@@ -2669,15 +2702,17 @@ static int step_impl(int H, int W, int K, uint64_t n, const int8_t* grid, const 
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
     const DynGeo g = make_dyn_geo(H, W, K);
-    const size_t smem = (size_t)(STEP_THREADS / 32) * 32 * H * W;
-    if (smem > 48 * 1024)  // boards of more than 192 cells: opt in to the large carve-out
+    const bool vec = (((uintptr_t)grid | (uintptr_t)grid_out) & 15u) == 0;
+    const bool dbuf = vec && H * W <= 128;  // two tiles per warp (cp.async prefetch of the next group)
+    const size_t smem = (size_t)(STEP_THREADS / 32) * 32 * H * W * (dbuf ? 2 : 1);
+    if (smem > 48 * 1024)  // large tiles: opt in to the large carve-out
         BGS_CUDA_TRY(cudaFuncSetAttribute(connect_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
     const unsigned long long cap = (unsigned long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     connect_step_kernel<<<(unsigned)blocks, STEP_THREADS, smem, (cudaStream_t)stream_>>>(
         g, n, grid, player, winner, action, grid_out, player_out, winner_out, ended_out, reward_out,
-        legal_out, status, (((uintptr_t)grid | (uintptr_t)grid_out) & 15u) == 0, pol);
+        legal_out, status, vec, dbuf, pol);
     BGS_CUDA_TRY(cudaGetLastError());
     return BGS_OK;
 }

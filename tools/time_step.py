@@ -10,6 +10,10 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from simulator import batch  # noqa: E402
+from simulator import _native as _N  # noqa: E402
+
+if len(sys.argv) > 2 and sys.argv[1] == "--lib":  # time another build of libbgs_b200.so (kernel experiments)
+    _N.LIB_PATH = os.path.abspath(sys.argv[2])
 
 
 def timed(fn, reps=10):

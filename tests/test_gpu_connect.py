@@ -406,9 +406,9 @@ def test_per_ply_grids_equal_oracle_replay(oracle, cfg):
 @pytest.mark.parametrize("cfg", [(6, 7, 4), (8, 9, 5), (10, 12, 6)])
 @pytest.mark.parametrize("n", [1, 7, 1031])
 def test_per_ply_grids_ragged_batches(cfg, n):
-    """The cell-stationary per-ply kernel packs 3 (8x9) / 2 (10x12) games into a warp, the row kernel (6x7)
-    32 positions: batch sizes that are not a multiple of that, checked against a host replay of the
-    recorded trajectories."""
+    """The cell-stationary per-ply kernel packs 3 (8x9) / 2 (10x12) games into a warp, the word-stationary kernel
+    (6x7) PAIRS of games (the last, odd game is a 2-byte aligned stream of its own): batch sizes that are not a
+    multiple of that, checked against a host replay of the recorded trajectories."""
     from simulator import batch
 
     H, W, K = cfg

@@ -208,10 +208,20 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, (NP == 2 ? (G::MAX_SOURCES <=
 bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     static_assert(M > 32 && M <= 64, "slot ids are ring entries of 64");
     constexpr int MAXSRC = G::MAX_SOURCES;   // movable pieces = columns of one row
-    // segments per trip.  Compile-time table-driven geometry (34-instruction segments): 2 / 3 / 4 / 5 / 6 / 8 ->
-    // 9.06 / 8.64 / 8.56 / 8.45 / 8.60 / 8.93 ms per 4 Mi default games; the other variants keep 3 (round 1, with the
-    // costlier segments of that build: 3 / 4 / 5 / 6 / 8 -> 9.83 / 10.0 / 9.9 / 10.1 / 10.6 ms)
-    constexpr int SEGMENTS = (G::LUT && NP == 2) ? 5 : 3;
+    // iterations (piece boundary + segment) per trip.  Compile-time table-driven geometry (34-instruction segments):
+    // 2 / 3 / 4 / 5 / 6 / 8 -> 9.06 / 8.64 / 8.56 / 8.45 / 8.60 / 8.93 ms per 4 Mi default games; with ONE extra,
+    // boundary-free segment after each (for the lanes that still have a pending cell: 63 % of the pieces need more than
+    // one segment, and the boundary block costs more than a segment): 2 / 3 / 4 iterations -> 8.33 / 8.25 / 8.40 ms; two
+    // or three extra segments lose (8.57 - 9.11 ms).  The other variants keep 3 iterations (round 1, with the costlier
+    // segments of that build: 3 / 4 / 5 / 6 / 8 -> 9.83 / 10.0 / 9.9 / 10.1 / 10.6 ms)
+#ifndef BGS_BOUNCE_ITERS
+#define BGS_BOUNCE_ITERS 3
+#endif
+#ifndef BGS_BOUNCE_EXTRA
+#define BGS_BOUNCE_EXTRA 1
+#endif
+    constexpr int SEGMENTS = (G::LUT && NP == 2) ? BGS_BOUNCE_ITERS : 3;
+    constexpr int EXTRA_SEG = (G::LUT && NP == 2) ? BGS_BOUNCE_EXTRA : 0;  // boundary-free segments after the first one of an iteration
     __shared__ unsigned int s_hist[HIST_BINS];
     __shared__ WarpSlots<NP, M, MAXSRC> s_slots[ROLLOUT_THREADS / 32];
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
@@ -365,8 +375,16 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
         if (has_work) {
             mg.iter(g, &S.T[0][slot], M);
 #pragma unroll
+            for (int e = 0; e < EXTRA_SEG; ++e)
+                if (!mg.done && mg.pending != 0) mg.lut_segment(g);
+#pragma unroll
             for (int q = 1; q < SEGMENTS; ++q)
-                if (!mg.done) mg.iter(g, &S.T[0][slot], M);
+                if (!mg.done) {
+                    mg.iter(g, &S.T[0][slot], M);
+#pragma unroll
+                    for (int e = 0; e < EXTRA_SEG; ++e)
+                        if (!mg.done && mg.pending != 0) mg.lut_segment(g);
+                }
             if (mg.done) {
                 S.meta[slot] = me | ((uint32_t)mg.total << META_TOTAL_SHIFT) | (mg.found ? META_FOUND : 0u);
                 has_work = false;

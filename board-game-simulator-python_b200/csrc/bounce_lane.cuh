@@ -405,6 +405,32 @@ struct MoveGen {
 
     BGS_HD void begin(const G& g, bool prb, bool no_moves) { begin_with(g, sources(g, b, no_moves), prb); }
 
+    // One table-driven segment (pending != 0): one pending cell, its landing set from the table -- no step loop, no
+    // dependence on the piece value, so every lane of the warp executes the same instructions.  The rollout kernel
+    // also calls it on its own: a second segment for the lanes that still have a pending cell, without paying for
+    // another piece-boundary block (37 % of the pieces need one segment, 23 % two, the rest up to twelve).
+    BGS_HD void lut_segment(const G& g) {
+        const B low = pending & (~pending + (B)1);
+        const int c = bit_index64((uint64_t)low);
+        const int u = (int)((b[0] >> c) & (B)1) | ((int)((b[1] >> c) & (B)1) << 1);
+        pending ^= low;
+        expanded |= low;
+        const int S = g.s();
+        const uint32_t x = (uint32_t)(inter >> (c - 3));  // window around c, bit 3 = c (c >= S: no piece in row 0)
+        uint32_t idx;
+        if constexpr (G::HASH) idx = seg_hash<G>(x);
+        else idx = ((x >> 1) & 3u) | ((x >> 2) & 0xCu) | ((x >> (S - 2)) & 0x70u) | ((x >> (2 * S - 4)) & 0x80u);
+#if defined(__CUDA_ARCH__)
+        uint32_t entry;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(lut_saddr + 4u * ((uint32_t)u * 256u + idx)));
+#else
+        const uint32_t entry = lut[u * 256 + (int)idx];
+#endif
+        const B land = (B)entry << (c - 3);  // not masked with `open`: occS lies inside it, targets are masked at the piece boundary
+        targets |= land & ~occS;
+        pending |= land & occS & ~expanded;
+    }
+
     // One iteration: at most one piece boundary, then one whole segment.  T[j * stride] receives the
     // target mask (mover-relative) of the j-th movable piece.  Sets done when nothing is left.
     BGS_HD void iter(const G& g, B* T, int stride) {
@@ -439,30 +465,11 @@ struct MoveGen {
             targets = 0;
             pending = sbit;  // the first segment = a "bounce" off the piece itself
         }
-        const B low = pending & (~pending + (B)1);
         if (NP == 2 && sizeof(B) == 8 && (G::LUT || (g.lut_rt() && lut != nullptr))) {
-            // ---- one pending cell per segment, its landing set from the table: no step loop, no
-            // dependence on the piece value, so every lane of the warp executes the same instructions
-            const int c = bit_index64((uint64_t)low);
-            const int u = (int)((b[0] >> c) & (B)1) | ((int)((b[1] >> c) & (B)1) << 1);
-            pending ^= low;
-            expanded |= low;
-            const int S = g.s();
-            const uint32_t x = (uint32_t)(inter >> (c - 3));  // window around c, bit 3 = c (c >= S: no piece in row 0)
-            uint32_t idx;
-            if constexpr (G::HASH) idx = seg_hash<G>(x);
-            else idx = ((x >> 1) & 3u) | ((x >> 2) & 0xCu) | ((x >> (S - 2)) & 0x70u) | ((x >> (2 * S - 4)) & 0x80u);
-#if defined(__CUDA_ARCH__)
-            uint32_t entry;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(lut_saddr + 4u * ((uint32_t)u * 256u + idx)));
-#else
-            const uint32_t entry = lut[u * 256 + (int)idx];
-#endif
-            const B land = (B)entry << (c - 3);  // not masked with `open`: occS lies inside it, targets are masked at the piece boundary
-            targets |= land & ~occS;
-            pending |= land & occS & ~expanded;
+            lut_segment(g);
             return;
         }
+        const B low = pending & (~pending + (B)1);
         // ---- segment setup: all unexpanded landing cells holding a piece of the same value as the
         // lowest one travel together
         B S = pending;

@@ -129,6 +129,20 @@ BGS_HD void philox_hd(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// ---- segment-table hash ---------------------------------------------------------------------------
+// The table-driven segment (MoveGen::lut_segment) indexes its table with 8 bits of the 32-bit window around the
+// pending cell: window bits {1, 2, 4, 5, S+2, S+3, S+4, 2S+3}.  Gathering them costs 11 instructions; for the row
+// strides S = 4..9 a multiplier M exists (random search, checked by seg_hash_is_perfect) such that
+// (window & mask) * M >> 24 maps the 256 subsets of those bits onto 256 different values -- 3 instructions -- and
+// the kernels build their tables THROUGH that map (seg_lut_slot).  S = 3 (two columns) has no 8 distinct bits.
+BGS_HD constexpr uint32_t seg_hash_mask(int S) {
+    return (1u << 1) | (1u << 2) | (1u << 4) | (1u << 5) | (1u << (S + 2)) | (1u << (S + 3)) | (1u << (S + 4)) | (1u << (2 * S + 3));
+}
+BGS_HD constexpr uint32_t seg_hash_mul(int S) {
+    return S == 4 ? 0x0C808055u : S == 5 ? 0x68401173u : S == 6 ? 0x4420061Du : S == 7 ? 0x9410021Fu
+         : S == 8 ? 0x1C00C409u : S == 9 ? 0xB4012103u : 0u;  // 0: no hash, gather the bits
+}
+
 // ---- geometry: run-time (any board) or compile-time (the BASELINE default 9x6) -------------------
 // Cell (x, y) is bit y*S + x.  S = W + 1 whenever H*(W+1) <= 64: the spare GUARD column (never part
 // of `board`) absorbs horizontal steps off the left / right edge, so that the frontier steps need no
@@ -138,9 +152,12 @@ struct GeoRTb {
     typedef B bits;
     static constexpr int BITS = (int)sizeof(B) * 8;
     static constexpr bool LUT = false;  // no compile-time guarantee; lut_ok decides at run time
-    static constexpr bool HASH = false; // table indexed by the 8 gathered window bits (seg_lut_slot)
+    static constexpr bool HASH = false; // no compile-time hash; hash_mul decides at run time (0 = gather the 8 bits)
     static constexpr int MAX_SOURCES = sizeof(B) == 8 ? 8 : 16;  // columns of one row
     bool lut_ok;         // table-driven segments possible: guard column, landing window within 32 bits
+    uint32_t hash_mask, hash_mul;  // segment-table hash of this row stride (seg_hash_mul), 0 = none
+    BGS_HD uint32_t hmask() const { return hash_mask; }
+    BGS_HD uint32_t hmul() const { return hash_mul; }
     int H, W, S, rules;
     int rot_shift;       // BITS-1 - (index of the last cell): rot180(x) = bit-reverse(x) >> rot_shift
     B board;             // the H*W valid cells
@@ -185,6 +202,8 @@ inline GeoRTb<B> make_geo_rt_b(int H, int W, int rules, bool guard = true) {
     // segment within 32 bits.  The caller clears the flag when the goal rows hold pieces or values exceed 3.
     // (S >= 3: the lowest piece cell is S, and the window starts 3 cells below the piece.)
     g.lut_ok = GeoRTb<B>::BITS == 64 && g.S > W && g.S >= 3 && 3 * g.S + 3 <= 31;
+    g.hash_mul = g.lut_ok ? seg_hash_mul(g.S) : 0u;
+    g.hash_mask = g.hash_mul ? seg_hash_mask(g.S) : 0u;
     return g;
 }
 inline GeoRT make_geo_rt(int H, int W, int rules, bool guard = true) { return make_geo_rt_b<uint64_t>(H, W, rules, guard); }
@@ -206,13 +225,12 @@ struct GeoCT {
     static constexpr int MAX_SOURCES = W_;
     // segments by table look-up (seg_lut_entry): needs the guard column and a 32-bit landing window
     static constexpr bool LUT = S_ > W_ && S_ >= 3 && 3 * S_ + 3 <= 31;
-    // S = 7 (the default 9x6 board): the table is indexed by a multiplicative hash of the window instead of the 8
-    // gathered bits -- (x & kHashMask) * kHashMul >> 24 is a bijection of the 256 subsets of the 8 window bits
-    // onto 0..255 (checked by seg_hash_is_perfect, tests/test_bounce_lane_host.py), 3 instructions instead of 11
-    static constexpr bool HASH = LUT && S_ == 7;
-    static constexpr uint32_t kHashMask = (1u << 1) | (1u << 2) | (1u << 4) | (1u << 5) | (1u << (S_ + 2)) | (1u << (S_ + 3)) |
-                                          (1u << (S_ + 4)) | (1u << (2 * S_ + 3));
-    static constexpr uint32_t kHashMul = 0x9410021Fu;
+    // the table is indexed by a multiplicative hash of the window instead of the 8 gathered bits (seg_hash_mul)
+    static constexpr bool HASH = LUT && seg_hash_mul(S_) != 0u;
+    static constexpr uint32_t kHashMask = seg_hash_mask(S_);
+    static constexpr uint32_t kHashMul = seg_hash_mul(S_);
+    BGS_HD uint32_t hmask() const { return kHashMask; }
+    BGS_HD uint32_t hmul() const { return kHashMul; }
     static constexpr uint64_t col_mask(int x0, int x1) {
         uint64_t m = 0;
         for (int y = 0; y < H_; ++y)
@@ -335,23 +353,32 @@ template <class G>
 BGS_HD uint32_t seg_hash(uint32_t window) {  // G::HASH only
     return ((window & G::kHashMask) * G::kHashMul) >> 24;
 }
+// table index of a window for geometry g: compile-time hash, run-time hash, or -- no multiplier for this stride --
+// the 8 gathered bits
 template <class G>
-BGS_HD uint32_t seg_lut_slot(const G& g, int u, uint32_t idx) {
-    if constexpr (G::HASH) return (uint32_t)u * 256u + seg_hash<G>(seg_window_of_idx(g.s(), idx));
-    else return (uint32_t)u * 256u + idx;
+BGS_HD uint32_t seg_index(const G& g, uint32_t x) {
+    if constexpr (G::HASH) return seg_hash<G>(x);
+    else {
+        const uint32_t mul = g.hmul();
+        if (mul) return ((x & g.hmask()) * mul) >> 24;
+        const int S = g.s();
+        return ((x >> 1) & 3u) | ((x >> 2) & 0xCu) | ((x >> (S - 2)) & 0x70u) | ((x >> (2 * S - 4)) & 0x80u);
+    }
 }
 template <class G>
-inline bool seg_hash_is_perfect(const G& g) {  // host-side check of kHashMul
-    if constexpr (!G::HASH) return true;
-    else {
-        bool seen[256] = {false};
-        for (uint32_t i = 0; i < 256; ++i) {
-            const uint32_t h = seg_hash<G>(seg_window_of_idx(g.s(), i));
-            if (h > 255u || seen[h]) return false;
-            seen[h] = true;
-        }
-        return true;
+BGS_HD uint32_t seg_lut_slot(const G& g, int u, uint32_t idx) {
+    return (uint32_t)u * 256u + seg_index(g, seg_window_of_idx(g.s(), idx));
+}
+inline bool seg_hash_is_perfect(int S) {  // host-side check of seg_hash_mul(S)
+    const uint32_t mul = seg_hash_mul(S), mask = seg_hash_mask(S);
+    if (!mul) return true;
+    bool seen[256] = {false};
+    for (uint32_t i = 0; i < 256; ++i) {
+        const uint32_t h = ((seg_window_of_idx(S, i) & mask) * mul) >> 24;
+        if (h > 255u || seen[h]) return false;
+        seen[h] = true;
     }
+    return true;
 }
 
 #if defined(__CUDA_ARCH__)
@@ -415,11 +442,8 @@ struct MoveGen {
         const int u = (int)((b[0] >> c) & (B)1) | ((int)((b[1] >> c) & (B)1) << 1);
         pending ^= low;
         expanded |= low;
-        const int S = g.s();
         const uint32_t x = (uint32_t)(inter >> (c - 3));  // window around c, bit 3 = c (c >= S: no piece in row 0)
-        uint32_t idx;
-        if constexpr (G::HASH) idx = seg_hash<G>(x);
-        else idx = ((x >> 1) & 3u) | ((x >> 2) & 0xCu) | ((x >> (S - 2)) & 0x70u) | ((x >> (2 * S - 4)) & 0x80u);
+        const uint32_t idx = seg_index(g, x);
 #if defined(__CUDA_ARCH__)
         uint32_t entry;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(lut_saddr + 4u * ((uint32_t)u * 256u + idx)));

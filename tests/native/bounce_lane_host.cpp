@@ -97,10 +97,14 @@ extern "C" int bgs_lane_host_bounce_rollout(int mode, const int8_t* grid0, const
     return 0;
 }
 
-// 1 when the multiplicative hash that indexes the segment table of the compile-time 9x6 geometry maps the 256
-// subsets of the 8 window bits onto 256 different slots (GeoCT::kHashMul, seg_hash_is_perfect)
+// 1 when the multiplicative hashes that index the segment tables (seg_hash_mul: row strides 4..9, the default 9x6
+// board is 7) map the 256 subsets of the 8 window bits onto 256 different slots
 extern "C" int bgs_lane_host_seg_hash_is_perfect() {
-    const GeoRT grt = make_geo_rt(9, 6, 0);
     static_assert(GeoCT<9, 6>::HASH, "the default board uses the hashed table");
-    return seg_hash_is_perfect(GeoCT<9, 6>(grt)) ? 1 : 0;
+    int hashed = 0;
+    for (int S = 3; S <= 9; ++S) {
+        if (!seg_hash_is_perfect(S)) return 0;
+        hashed += seg_hash_mul(S) != 0u;
+    }
+    return hashed == 6 ? 1 : 0;
 }

@@ -221,7 +221,7 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
 #define BGS_BOUNCE_EXTRA 1
 #endif
     constexpr int SEGMENTS = (G::LUT && NP == 2) ? BGS_BOUNCE_ITERS : 3;
-    constexpr int EXTRA_SEG = (G::LUT && NP == 2) ? BGS_BOUNCE_EXTRA : 0;  // boundary-free segments after the first one of an iteration
+    constexpr int EXTRA_SEG = NP == 2 ? BGS_BOUNCE_EXTRA : 0;  // boundary-free table-driven segments after the first one of an iteration (lut_on)
     __shared__ unsigned int s_hist[HIST_BINS];
     __shared__ WarpSlots<NP, M, MAXSRC> s_slots[ROLLOUT_THREADS / 32];
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
@@ -286,6 +286,9 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     mg.lut = lut_on ? s_lut : nullptr;
     mg.lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
     asm volatile("mov.u32 %0, %0;" : "+r"(mg.lut_saddr));  // opaque: see MoveGen::lut_saddr
+    // the extra segment pays where pieces bounce often: boards of 5+ columns (8x7: 4.72 -> 4.14 ms per 2 Mi games,
+    // 7x5: 2.60 -> 2.31; 6x3: 3.10 -> 3.33, so not there)
+    const bool extra_on = lut_on && g.w() >= 5;
     bool has_work = false;
     int slot = 0;
     uint32_t me = 0;  // meta word of the slot in work
@@ -376,14 +379,14 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
             mg.iter(g, &S.T[0][slot], M);
 #pragma unroll
             for (int e = 0; e < EXTRA_SEG; ++e)
-                if (!mg.done && mg.pending != 0) mg.lut_segment(g);
+                if (extra_on && !mg.done && mg.pending != 0) mg.lut_segment(g);
 #pragma unroll
             for (int q = 1; q < SEGMENTS; ++q)
                 if (!mg.done) {
                     mg.iter(g, &S.T[0][slot], M);
 #pragma unroll
                     for (int e = 0; e < EXTRA_SEG; ++e)
-                        if (!mg.done && mg.pending != 0) mg.lut_segment(g);
+                        if (extra_on && !mg.done && mg.pending != 0) mg.lut_segment(g);
                 }
             if (mg.done) {
                 S.meta[slot] = me | ((uint32_t)mg.total << META_TOTAL_SHIFT) | (mg.found ? META_FOUND : 0u);

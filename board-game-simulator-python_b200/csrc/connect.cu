@@ -467,7 +467,7 @@ connect_rollout_kernel(const G g, const RolloutParams p) {
 // The ALU pipe (LOP3/SHF, 64 lanes/clk/SM) is what bounds the rollout, so everything that is not
 // the k-in-a-row test is moved off it: the playable-column mask is ONE LOP3 (the top row is bits
 // 0..W-1), its population count runs on the XU pipe, "k-th playable column" is a shared-memory
-// table lookup (LSU pipe), column heights live in per-thread shared-memory bytes (LSU pipe) and
+// table lookup (LSU pipe), each column's landing cell lives in per-thread shared-memory bytes (LSU pipe) and
 // the arithmetic in between is IMAD (FMA pipe).
 __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
     uint32_t v;

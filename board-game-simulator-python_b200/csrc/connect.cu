@@ -2597,7 +2597,9 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
     if (!actions || !length || !grids) return set_error(BGS_EINVAL, "connect_trajectory_grids: null pointer");
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
-    if (((uintptr_t)grids & 15u) == 0 && ((H == 8 && W == 9) || (H == 10 && W == 12))) {
+    // (the cell kernels read the trajectories as 8-byte pieces, the word kernel as 4-byte words: other pointers take
+    // the row kernel below)
+    if (((uintptr_t)grids & 15u) == 0 && ((uintptr_t)actions & 7u) == 0 && ((H == 8 && W == 9) || (H == 10 && W == 12))) {
         cudaStream_t stream = (cudaStream_t)stream_;
         auto launch = [&](auto kern, int gpw) {
             int per_sm = 0;

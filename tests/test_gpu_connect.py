@@ -433,6 +433,54 @@ def test_per_ply_grids_ragged_batches(cfg, n):
     np.testing.assert_array_equal(got[np.arange(n), lens.astype(np.int64)], res.final_grid.cpu().numpy())
 
 
+@pytest.mark.parametrize("cfg", [(6, 7, 4), (8, 9, 5), (10, 12, 6)])
+def test_per_ply_grids_with_unaligned_pointers_take_the_fallback_kernel(cfg):
+    """The word- / cell-stationary per-ply kernels need a 16-byte aligned output and (6x7) 4-byte aligned
+    trajectories; a C-ABI caller may pass anything, and the row kernel behind it must give the same bytes."""
+    from simulator import batch
+
+    H, W, K = cfg
+    n = 333
+    res = batch.connect_rollout(cfg, n, 9, 5, per_game=True, actions=True)
+    want = batch.connect_trajectory_grids(cfg, res.actions, res.length)
+    for a_off, o_off in ((1, 0), (0, 8), (2, 4), (3, 1)):
+        abuf = torch.zeros(n * H * W + 16, dtype=torch.uint8, device="cuda")
+        acts = abuf[a_off:a_off + n * H * W].view(n, H * W)
+        acts.copy_(res.actions)
+        obuf = torch.full((n * (H * W + 1) * H * W + 32,), 7, dtype=torch.int8, device="cuda")
+        out = obuf[o_off:o_off + n * (H * W + 1) * H * W].view(n, H * W + 1, H, W)
+        assert acts.data_ptr() % 16 == a_off % 16 and out.data_ptr() % 16 == o_off % 16
+        got = batch.connect_trajectory_grids(cfg, acts, res.length, out=out)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (a_off, o_off)
+        assert int((obuf[:o_off] != 7).sum()) == 0 and int((obuf[o_off + out.numel():] != 7).sum()) == 0
+
+
+@pytest.mark.parametrize("cfg", [(6, 7, 4), (10, 12, 6), (12, 12, 5)])
+def test_batched_step_with_unaligned_grids_equals_the_aligned_call(cfg):
+    """connect_step_kernel prefetches the next tile with cp.async when both grid pointers are 16-byte aligned (boards
+    up to 128 cells); other pointers / boards take the synchronous copy -- same outputs, ragged last group included."""
+    from simulator import batch
+
+    H, W, K = cfg
+    n = 32 * 37 + 5
+    b = batch.ConnectBatch.initial(cfg, n)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for _ in range(6):
+        b, _ = b.step(torch.randint(0, W, (n,), device="cuda", generator=gen))
+    acts = torch.randint(0, W, (n,), device="cuda", generator=gen).to(torch.int32)
+    want, wstatus = b.step(acts)
+    gbuf = torch.zeros(n * H * W + 16, dtype=torch.int8, device="cuda")
+    g2 = gbuf[1:1 + n * H * W].view(n, H, W)
+    g2.copy_(b.grid)
+    assert g2.data_ptr() % 16 == 1
+    b2 = batch.ConnectBatch(cfg, g2, b.player, b.winner)
+    got, gstatus = b2.step(acts)
+    torch.cuda.synchronize()
+    assert torch.equal(got.grid, want.grid) and torch.equal(got.player, want.player)
+    assert torch.equal(got.winner, want.winner) and torch.equal(gstatus, wstatus)
+
+
 def test_packed_host_results_equal_oracle(oracle):
     """HostRollout(packed=True): one byte per game over PCIe, unpacked on the host = the oracle's results."""
     from simulator import batch

@@ -37,6 +37,13 @@ struct DeviceGuard {
     DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 
+// float[n,2] reward arrays are written as float2: BGS_EINVAL for a pointer that is not 8-byte aligned (null is fine)
+inline int check_reward_alignment(const float* reward, const char* who) {
+    if (reward && (reinterpret_cast<uintptr_t>(reward) & 7u) != 0)
+        return set_error(BGS_EINVAL, "%s: the reward array must be 8-byte aligned", who);
+    return BGS_OK;
+}
+
 // Number of SMs of the current device (cached per device).
 int sm_count();
 

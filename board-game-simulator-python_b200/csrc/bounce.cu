@@ -742,6 +742,7 @@ static int bounce_step_impl(int H, int W, int rules, uint64_t n, const int8_t* g
                             const int8_t* winner, const uint8_t* ended, const int32_t* move, int8_t* grid_out, int8_t* player_out,
                             int8_t* winner_out, uint8_t* ended_out, float* reward_out, int32_t* status,
                             void* stream_, const SamplePolicy& pol) {
+    if (int rc = check_reward_alignment(reward_out, "bounce_step")) return rc;
     if (!supported(H, W, 0)) return set_error(BGS_EUNSUPPORTED, "bounce: unsupported board %dx%d", H, W);
     if (!grid || !player || !grid_out || !player_out || !winner_out)
         return set_error(BGS_EINVAL, "bounce_step: null required pointer");

@@ -2429,6 +2429,8 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
     const bool bytes_board = !bitboard_supported(H, W, K);
     if (bytes_board && start) return set_error(BGS_EUNSUPPORTED, "connect: rollouts from positions need a board of at most 128 cells, 16 columns, 15 rows (%dx%d)", H, W);
     const int act_mode = actions ? (fused ? 3 : (bytes_board ? 1 : actions_mode(H, W))) : 0;
+    if (act_mode == 2 && ((uintptr_t)actions & 1u) != 0)  // 4-ply blocks are stored as 16-bit words
+        return set_error(BGS_EINVAL, "connect_rollout: `actions` must be 2-byte aligned");
     if (rc == BGS_OK && act_mode == 1) {
         e = cudaMemsetAsync(actions, 0xFF, n_games * HW, stream);
         if (e != cudaSuccess) rc = cuda_error(e, "cudaMemsetAsync");
@@ -2483,6 +2485,7 @@ extern "C" int bgs_connect_rollout_export(int H, int W, int K, uint64_t n_games,
                                           float* reward, int64_t* stats, void* stream_) {
     if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
     if (actions && !length) return set_error(BGS_EINVAL, "connect_rollout_export: `actions` requires `length`");
+    if (int rc = check_reward_alignment(reward, "connect_rollout_export")) return rc;
     if (int rc = require_device()) return rc;
     if (n_games == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -2568,6 +2571,7 @@ extern "C" int bgs_connect_rollout_from_packed(int H, int W, int K, uint64_t n_g
 extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* packed, const int8_t* winner,
                                   int8_t* grid, float* reward, void* stream_) {
     if (!supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
+    if (int rc = check_reward_alignment(reward, "connect_export")) return rc;
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -2701,6 +2705,7 @@ static int step_impl(int H, int W, int K, uint64_t n, const int8_t* grid, const 
     if (!supported(H, W, K)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d k=%d", H, W, K);
     if (!grid || !player || !winner || !grid_out || !player_out || !winner_out)
         return set_error(BGS_EINVAL, "connect_step: null required pointer");
+    if (int rc = check_reward_alignment(reward_out, "connect_step")) return rc;
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
     const DynGeo g = make_dyn_geo(H, W, K);
@@ -2746,6 +2751,7 @@ extern "C" int bgs_connect_query(int H, int W, uint64_t n, const int8_t* grid, c
                                  uint8_t* ended_out, uint32_t* legal_out, float* reward_out, void* stream_) {
     if (!supported(H, W, 1)) return set_error(BGS_EUNSUPPORTED, "connect: unsupported board %dx%d", H, W);
     if (!grid || !winner) return set_error(BGS_EINVAL, "connect_query: null required pointer");
+    if (int rc = check_reward_alignment(reward_out, "connect_query")) return rc;
     if (int rc = require_device()) return rc;
     if (n == 0) return BGS_OK;
     const unsigned long long blocks = (n + 127) / 128;

@@ -372,6 +372,14 @@ def test_c_abi_argument_validation():
     assert L.bgs_connect_rollout_from(6, 7, 4, 4, 0, 0, None, None, None, None, None, None, None, None, None, st) == -1
     assert L.bgs_bounce_rollout(None, 9, 6, 0, 64, 4, 0, 0, None, None, None, None, None, None, st) == -1
     assert L.bgs_bounce_moves(12, 11, 0, 1, N.ptr(buf), N.ptr(buf), None, None, N.ptr(buf), None, st) == -2
+    # alignment the kernels rely on (include/bgs_b200.h, "Alignment"): rewards are written as float pairs, the
+    # trajectories of even boards as 16-bit blocks
+    assert buf.data_ptr() % 16 == 0
+    assert L.bgs_connect_query(6, 7, 1, N.ptr(buf), N.ptr(buf), None, None, buf.data_ptr() + 4, st) == -1
+    assert "8-byte aligned" in N.last_error()
+    assert L.bgs_connect_export(6, 7, 1, N.ptr(buf), N.ptr(buf), None, buf.data_ptr() + 4, st) == -1
+    assert L.bgs_connect_rollout(6, 7, 4, 8, 0, 0, buf.data_ptr() + 1, N.ptr(buf), None, None, None, st) == -1
+    assert "2-byte aligned" in N.last_error()
     # zero games is a no-op
     assert L.bgs_connect_rollout(6, 7, 4, 0, 0, 0, None, None, None, None, None, st) == 0
     torch.cuda.synchronize()

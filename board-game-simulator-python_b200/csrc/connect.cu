@@ -2431,6 +2431,8 @@ static int rollout_impl(int H, int W, int K, uint64_t n_games, uint64_t game_id0
     const int act_mode = actions ? (fused ? 3 : (bytes_board ? 1 : actions_mode(H, W))) : 0;
     if (act_mode == 2 && ((uintptr_t)actions & 1u) != 0)  // 4-ply blocks are stored as 16-bit words
         return set_error(BGS_EINVAL, "connect_rollout: `actions` must be 2-byte aligned");
+    if (!bytes_board && ((((uintptr_t)final_packed) | (uintptr_t)start) & 15u) != 0)  // records move as 16-byte pairs
+        return set_error(BGS_EINVAL, "connect_rollout: `final_packed` / the start-record workspace must be 16-byte aligned");
     if (rc == BGS_OK && act_mode == 1) {
         e = cudaMemsetAsync(actions, 0xFF, n_games * HW, stream);
         if (e != cudaSuccess) rc = cuda_error(e, "cudaMemsetAsync");
@@ -2578,6 +2580,8 @@ extern "C" int bgs_connect_export(int H, int W, uint64_t n, const uint64_t* pack
     const int sms = sm_count();
     if (grid) {
         if (!packed) return set_error(BGS_EINVAL, "connect_export: grid requested without packed boards");
+        if (((uintptr_t)packed & 15u) != 0 && bitboard_supported(H, W, 1))
+            return set_error(BGS_EINVAL, "connect_export: `packed` must be 16-byte aligned");
         if (!bitboard_supported(H, W, 1)) {  // byte boards: the record is the grid, padded to 8 bytes
             BGS_CUDA_TRY(cudaMemcpy2DAsync(grid, (size_t)H * W, packed, (size_t)bgs_connect_packed_words(H, W) * 8,
                                            (size_t)H * W, n, cudaMemcpyDeviceToDevice, stream));

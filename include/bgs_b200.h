@@ -22,8 +22,8 @@
  *     BGS_ENODEVICE.
  *   - Alignment: every pointer needs the natural alignment of its element type; on top of that float[n,2]
  *     reward arrays must be 8-byte aligned (they are written as pairs), `actions` of bgs_connect_rollout 2-byte
- *     aligned on boards with an even number of cells, and the arrays documented as "16-byte aligned" exactly that
- *     (BGS_EINVAL otherwise).  Byte grids / trajectories may sit anywhere: 16-byte aligned ones take the vectorised
+ *     aligned on boards with an even number of cells, and packed boards (`final_packed`, `packed`), start-record
+ *     workspaces, state keys and the inputs of the pack_results calls 16-byte aligned (BGS_EINVAL otherwise).  Byte grids / trajectories may sit anywhere: 16-byte aligned ones take the vectorised
  *     kernels, others a slower path with the same results.
  */
 #ifndef BGS_B200_H

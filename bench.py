@@ -319,6 +319,35 @@ def other_configs(torch, batch, N, dev):
             **bounce_counters(),
         },
     }
+    try:  # the same kernel over 8 back-to-back batches alternating over two streams: the straggler tail of a batch
+        # (a few ~400-ply games among 4 Mi leave the GPU nearly idle for ~1 ms) overlaps the next batch
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        bstats = torch.zeros((8, N.STATS_LEN), dtype=torch.int64, device=dev)
+        for _rep in range(2):
+            bstats.zero_()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            done = []
+            for st in streams:
+                st.wait_event(t0)
+            for b in range(8):
+                with torch.cuda.stream(streams[b % 2]):
+                    batch.bounce_rollout(grid, n, SEED, (200 + b) * n, max_plies=512, stats=bstats[b])
+                    e = torch.cuda.Event()
+                    e.record()
+                    done.append(e)
+            for e in done:
+                torch.cuda.current_stream().wait_event(e)
+            t1.record()
+            torch.cuda.synchronize()
+        tot_ms, tot_steps = t0.elapsed_time(t1), int(bstats[:, N.STAT_STEPS].sum())
+        out["bounce_default_9x6"]["two_streams"] = {
+            "batches": 8, "ms_per_batch": tot_ms / 8, "env_steps_per_s": tot_steps / tot_ms * 1e3,
+            "frac_of_budget": tot_steps / tot_ms * 1e3 * BOUNCE_OPS_PER_STEP / 1e9 / peak_g,
+        }
+    except Exception as e:
+        out["bounce_default_9x6"]["two_streams"] = {"error": repr(e)}
     try:  # configs[2] end to end: per-game results (2 bytes, packed) + statistics to pinned host memory, pipelined
         bh = batch.HostRollout(grid, n, depth=2, packed=True, game="bounce", max_plies=512)
         for _ in bh.stream(SEED, 0, 2):

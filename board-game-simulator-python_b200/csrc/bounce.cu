@@ -48,9 +48,20 @@ struct RolloutParams {
     const int8_t* start_winner;   // [n] or null
     const uint8_t* start_ended;   // [n] or null
     int ply_batch, idle_batch;    // slot kernel: waiting slots / idle lanes that trigger the transition pass
+    uint32_t one;                 // always 1 (MoveGen::one)
 };
 
 constexpr int ROLLOUT_THREADS = 128;
+
+// The tables of the table-driven segment (MoveGen::lut_segment) in shared memory: landing sets [value][window hash],
+// then the power table at byte 4096.
+template <class G>
+__device__ __forceinline__ void build_seg_tables(const G& g, uint32_t* s_lut) {
+    static_assert(SEG_LUT_WORDS * 4 == 4096, "lut_segment addresses the power table at byte 4096");
+    for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x)
+        s_lut[seg_lut_slot(g, i >> 8, (uint32_t)(i & 255))] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
+    for (int i = threadIdx.x; i < SEG_POW_WORDS; i += blockDim.x) s_lut[SEG_LUT_WORDS + i] = seg_pow_entry(i >> 2, i & 3);
+}
 // Lanes that must be ready before the ply transition runs, and move-generation segments per readiness
 // check (straight-line copies; a run-time loop is slower).  Frontier-propagation kernels: batch 8 / 12 /
 // 16 / 24 -> 13.0 / 12.45 / 12.6 / 13.3 ms, segments 1 / 2 -> 12.8 / 11.9 ms.  Table-driven kernel
@@ -76,9 +87,9 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     constexpr bool USE_LUT = G::LUT && NP == 2;                  // compile-time: the default board
     constexpr bool MAY_LUT = NP == 2 && sizeof(B) == 8;          // run-time: any small board with a guard column
     const bool lut_on = USE_LUT || (MAY_LUT && g.lut_rt());
-    __shared__ uint32_t s_lut[MAY_LUT ? SEG_LUT_WORDS : 1];  // landing sets of a segment, [value][passable neighbours]
+    __shared__ __align__(16) uint32_t s_lut[MAY_LUT ? SEG_LUT_WORDS + SEG_POW_WORDS : 1];  // landing sets of a segment, [value][passable neighbours]; the power table
     if (lut_on) {
-        for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[seg_lut_slot(g, i >> 8, (uint32_t)(i & 255))] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
+        build_seg_tables(g, s_lut);
         __syncthreads();
     }
     B plane0[4];
@@ -91,6 +102,7 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     mg.lut = lut_on ? s_lut : nullptr;
     mg.lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
     asm volatile("mov.u32 %0, %0;" : "+r"(mg.lut_saddr));  // opaque: see MoveGen::lut_saddr
+    mg.one = p.one;
     uint32_t r[4] = {0, 0, 0, 0};
     uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
     unsigned long long acc_steps = 0;
@@ -228,9 +240,8 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     const G g(grt);
     constexpr bool USE_LUT = G::LUT && NP == 2;
     const bool lut_on = USE_LUT || (NP == 2 && g.lut_rt());
-    __shared__ uint32_t s_lut[NP == 2 ? SEG_LUT_WORDS : 1];
-    if (lut_on)
-        for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x) s_lut[seg_lut_slot(g, i >> 8, (uint32_t)(i & 255))] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
+    __shared__ __align__(16) uint32_t s_lut[NP == 2 ? SEG_LUT_WORDS + SEG_POW_WORDS : 1];
+    if (lut_on) build_seg_tables(g, s_lut);
     __syncthreads();
     WarpSlots<NP, M, MAXSRC>& S = s_slots[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -286,6 +297,7 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     mg.lut = lut_on ? s_lut : nullptr;
     mg.lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
     asm volatile("mov.u32 %0, %0;" : "+r"(mg.lut_saddr));  // opaque: see MoveGen::lut_saddr
+    mg.one = p.one;
     // the extra segment pays where pieces bounce often: boards of 5+ columns (8x7: 4.72 -> 4.14 ms per 2 Mi games,
     // 7x5: 2.60 -> 2.31; 6x3: 3.10 -> 3.33, so not there)
     const bool extra_on = lut_on && g.w() >= 5;
@@ -847,6 +859,7 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     if (n_games == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     RolloutParams p;
+    p.one = 1u;
     p.n_games = (uint32_t)n_games; p.game_id0 = game_id0;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.max_plies = max_plies;

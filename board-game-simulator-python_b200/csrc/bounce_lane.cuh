@@ -77,6 +77,14 @@ BGS_HD int bit_index64(uint64_t x) {
     return __builtin_ctzll(x);
 #endif
 }
+// index of the highest set bit of x (x != 0), minus 3: FLO finds the highest bit directly (no isolation of the lowest one)
+BGS_HD int top_bit_minus3(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return 60 - __clzll((long long)x);
+#else
+    return 60 - __builtin_clzll(x);
+#endif
+}
 BGS_HD uint64_t brev64(uint64_t x) {
 #ifdef __CUDA_ARCH__
     return __brevll(x);
@@ -381,6 +389,23 @@ inline bool seg_hash_is_perfect(int S) {  // host-side check of seg_hash_mul(S)
     return true;
 }
 
+// Power table of the table-driven segment: entry i (16 bytes) = {1 << i, 8 << i} as two 64-bit words, i = the
+// pending cell's index minus 3; word k of the entry (0..3) is what this returns.
+constexpr int SEG_POW_WORDS = 64 * 4;
+BGS_HD uint32_t seg_pow_entry(int i, int k) {
+    const uint64_t v = (k < 2 ? 1ull : 8ull) << i;  // (8 << i loses bits for i > 60: no such cell)
+    return (uint32_t)(v >> (32 * (k & 1)));
+}
+
+#if defined(__CUDA_ARCH__)
+// a * b + c on the FMA pipe (IMAD); with an opaque b ptxas cannot turn it into an ALU-pipe add / LEA
+__device__ __forceinline__ uint32_t fma_mad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define BGS_UNROLL _Pragma("unroll")
 #else
@@ -398,13 +423,16 @@ template <int NP, class G, int RULES_, bool FASTPROBE = false>
 struct MoveGen {
     typedef typename G::bits B;
     B b[NP];  // value bit-planes in the mover's orientation (read-only here)
-    B occ, src_left, sbit, occS, inter, open, expanded, pending, targets;
+    B occ, src_left, sbit, occS, inter, open, unexp, pending, targets;  // unexp: pieces (of occS) not expanded yet; pending is a subset of it, except for the source cell itself
     int total, nsrc;
     bool probe;  // only "does the mover have any action?" (the blocked test): `found` is the answer, T / total are not used
     bool found, have, done;
     const uint32_t* lut;  // seg_lut_entry table [4][256] when G::LUT (shared memory in the kernel)
     uint32_t lut_saddr;   // device: the same table as a 32-bit shared-memory address (kept opaque by the kernel so
-                          // that the base stays in a register instead of being rebuilt for every look-up)
+                          // that the base stays in a register instead of being rebuilt for every look-up); the
+                          // power table (seg_pow_entry) follows it at byte 4096
+    uint32_t one;         // device: always 1, from a kernel parameter -- a multiplier ptxas cannot fold, which keeps
+                          // adds and shifts by constants on the FMA pipe (IMAD)
 
     BGS_HD int rules(const G& g) const { return RULES_ >= 0 ? RULES_ : g.rules; }
 
@@ -437,22 +465,56 @@ struct MoveGen {
     // also calls it on its own: a second segment for the lanes that still have a pending cell, without paying for
     // another piece-boundary block (37 % of the pieces need one segment, 23 % two, the rest up to twelve).
     BGS_HD void lut_segment(const G& g) {
-        const B low = pending & (~pending + (B)1);
-        const int c = bit_index64((uint64_t)low);
-        const int u = (int)((b[0] >> c) & (B)1) | ((int)((b[1] >> c) & (B)1) << 1);
-        pending ^= low;
-        expanded |= low;
-        const uint32_t x = (uint32_t)(inter >> (c - 3));  // window around c, bit 3 = c (c >= S: no piece in row 0)
-        const uint32_t idx = seg_index(g, x);
+        // The kernel is bound by the ALU pipe (logic, shifts, compares, adds: 80 % busy where 81 % is its ceiling)
+        // while the FMA pipe (integer multiply-add) idles at 15 %, so the segment is written for few instructions
+        // on the former: 14 instead of 28.
+        //  * The HIGHEST pending cell is expanded (the closure does not depend on the order): FLO finds that bit
+        //    directly -- no isolation of the lowest bit, no select between the halves (the second FLO is predicated).
+        //  * Everything is taken from words shifted by c - 3: the window of passable cells (bit 3 = c) and the value
+        //    bits of c (bit 3 of the shifted planes; they select the table's quarter through two multiply-adds).
+        //  * 1 << (c - 3) and the bit of c itself come from a 64-entry table (one 128-bit load), and the landing set
+        //    is entry * 2^(c-3) as a wide multiply instead of a 64-bit shift.
+        //  * unexp (pieces not expanded yet) replaces the set of expanded cells: c leaves pending because it is no
+        //    longer in unexp, one three-input logic operation per half.
 #if defined(__CUDA_ARCH__)
+        const uint32_t plo = (uint32_t)pending, phi = (uint32_t)(pending >> 32);
+        uint32_t c3;  // c - 3, c >= S >= 3: no piece in row 0
+        asm("{\n\t.reg .pred p;\n\t.reg .u32 f;\n\t"
+            "setp.ne.u32 p, %2, 0;\n\t"
+            "bfind.u32 f, %1;\n\t"
+            "@p bfind.u32 f, %2;\n\t"
+            "mad.lo.u32 %0, %3, 0xfffffffd, f;\n\t"
+            "@p mad.lo.u32 %0, %3, 29, f;\n\t}"
+            : "=r"(c3) : "r"(plo), "r"(phi), "r"(one));
+        uint32_t p1lo, p1hi, lowlo, lowhi;  // 1 << c3 and 8 << c3
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4 + 4096];"
+                     : "=r"(p1lo), "=r"(p1hi), "=r"(lowlo), "=r"(lowhi) : "r"(fma_mad(c3, 16u * one, lut_saddr)));
+        const uint32_t x = (uint32_t)(inter >> c3);
+        const uint32_t v0 = (uint32_t)(b[0] >> c3) & 8u, v1 = (uint32_t)(b[1] >> c3) & 8u;
+        const uint32_t idx = seg_index(g, x);
         uint32_t entry;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(lut_saddr + 4u * ((uint32_t)u * 256u + idx)));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry)
+                     : "r"(fma_mad(idx, 4u * one, fma_mad(v0, 128u * one, fma_mad(v1, 256u * one, lut_saddr)))));
+        uint32_t ldlo, ldhi;  // the landing set = entry << c3 (not masked with `open`: occS lies inside it, targets are
+                              // masked at the piece boundary)
+        asm("{\n\t.reg .u64 w;\n\t"
+            "mul.wide.u32 w, %2, %3;\n\t"
+            "mov.b64 {%0, %1}, w;\n\t"
+            "mad.lo.u32 %1, %2, %4, %1;\n\t}"
+            : "=r"(ldlo), "=&r"(ldhi) : "r"(entry), "r"(p1lo), "r"(p1hi));
+        const B land = (B)(((uint64_t)ldhi << 32) | ldlo);
+        const B low = (B)(((uint64_t)lowhi << 32) | lowlo);
 #else
-        const uint32_t entry = lut[u * 256 + (int)idx];
+        const int c3 = top_bit_minus3((uint64_t)pending);
+        const uint32_t x = (uint32_t)(inter >> c3);
+        const uint32_t v0 = (uint32_t)(b[0] >> c3) & 8u, v1 = (uint32_t)(b[1] >> c3) & 8u;
+        const uint32_t idx = seg_index(g, x);
+        const B low = (B)8 << c3;
+        const B land = (B)lut[(v0 >> 3) * 256 + (v1 >> 3) * 512 + (int)idx] << c3;
 #endif
-        const B land = (B)entry << (c - 3);  // not masked with `open`: occS lies inside it, targets are masked at the piece boundary
+        unexp &= ~low;
         targets |= land & ~occS;
-        pending |= land & occS & ~expanded;
+        pending = (pending | land) & unexp;  // c leaves (it is no longer in unexp), unexpanded pieces landed on enter
     }
 
     // One iteration: at most one piece boundary, then one whole segment.  T[j * stride] receives the
@@ -485,7 +547,7 @@ struct MoveGen {
             occS = variant == BGS_BOUNCE_SOURCE_PIECE ? occ : (occ & ~sbit);
             open = variant == BGS_BOUNCE_SOURCE_BLOCKED ? (g.m_board() & ~sbit) : g.m_board();
             inter = open & ~occS & ~g.m_far();  // cells a path may pass through
-            expanded = 0;
+            unexp = occS;
             targets = 0;
             pending = sbit;  // the first segment = a "bounce" off the piece itself
         }
@@ -504,8 +566,7 @@ struct MoveGen {
             S &= in ? b[i] : ~b[i];
             u |= in ? (1 << i) : 0;
         }
-        pending ^= S;
-        expanded |= S;
+        unexp &= ~S;
         // ---- u steps, every frontier cell at once; x* = cells entered by a forward / left / right
         // step (a left step may not follow a right step and vice versa; never backwards)
         const int W = g.s();  // one row up
@@ -535,7 +596,7 @@ struct MoveGen {
         // last step: rest on an empty cell, or bounce off a piece
         const B land = (xf | xl | xr) & open;
         targets |= land & ~occS;
-        pending |= land & occS & ~expanded;
+        pending = (pending | land) & unexp;  // S leaves, unexpanded pieces landed on enter
     }
 };
 

@@ -48,7 +48,7 @@ struct RolloutParams {
     const int8_t* start_winner;   // [n] or null
     const uint8_t* start_ended;   // [n] or null
     int ply_batch, idle_batch;    // slot kernel: waiting slots / idle lanes that trigger the transition pass
-    uint32_t one;                 // always 1 (MoveGen::one)
+    uint32_t one, k16;            // always 1 and 16 (MoveGen::one, k16)
 };
 
 constexpr int ROLLOUT_THREADS = 128;
@@ -61,6 +61,20 @@ __device__ __forceinline__ void build_seg_tables(const G& g, uint32_t* s_lut) {
     for (int i = threadIdx.x; i < SEG_LUT_WORDS; i += blockDim.x)
         s_lut[seg_lut_slot(g, i >> 8, (uint32_t)(i & 255))] = seg_lut_entry(g.s(), i >> 8, (uint32_t)(i & 255));
     for (int i = threadIdx.x; i < SEG_POW_WORDS; i += blockDim.x) s_lut[SEG_LUT_WORDS + i] = seg_pow_entry(i >> 2, i & 3);
+}
+
+// MoveGen::one / k16: read back from shared memory (values stored from kernel parameters), so that ptxas keeps them
+// in registers -- it re-loads a kernel parameter from the constant bank wherever it is used, and that load then sits
+// on the critical path of every segment.
+template <class MG>
+__device__ __forceinline__ void load_seg_consts(MG& mg, uint32_t* s_two, uint32_t one, uint32_t k16) {  // s_two: 8-byte aligned
+    if (threadIdx.x == 0) {
+        s_two[0] = one;
+        s_two[1] = k16;
+    }
+    __syncthreads();
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mg.one), "=r"(mg.k16)
+                 : "r"((uint32_t)__cvta_generic_to_shared(s_two)));
 }
 // Lanes that must be ready before the ply transition runs, and move-generation segments per readiness
 // check (straight-line copies; a run-time loop is slower).  Frontier-propagation kernels: batch 8 / 12 /
@@ -87,7 +101,7 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     constexpr bool USE_LUT = G::LUT && NP == 2;                  // compile-time: the default board
     constexpr bool MAY_LUT = NP == 2 && sizeof(B) == 8;          // run-time: any small board with a guard column
     const bool lut_on = USE_LUT || (MAY_LUT && g.lut_rt());
-    __shared__ __align__(16) uint32_t s_lut[MAY_LUT ? SEG_LUT_WORDS + SEG_POW_WORDS : 1];  // landing sets of a segment, [value][passable neighbours]; the power table
+    __shared__ __align__(16) uint32_t s_lut[MAY_LUT ? SEG_LUT_WORDS + SEG_POW_WORDS + 4 : 4];  // landing sets of a segment, [value][passable neighbours]; the power table
     if (lut_on) {
         build_seg_tables(g, s_lut);
         __syncthreads();
@@ -102,7 +116,7 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     mg.lut = lut_on ? s_lut : nullptr;
     mg.lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
     asm volatile("mov.u32 %0, %0;" : "+r"(mg.lut_saddr));  // opaque: see MoveGen::lut_saddr
-    mg.one = p.one;
+    load_seg_consts(mg, s_lut + (MAY_LUT ? SEG_LUT_WORDS + SEG_POW_WORDS : 0), p.one, p.k16);
     uint32_t r[4] = {0, 0, 0, 0};
     uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
     unsigned long long acc_steps = 0;
@@ -235,12 +249,18 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     constexpr int SEGMENTS = (G::LUT && NP == 2) ? BGS_BOUNCE_ITERS : 3;
     constexpr int EXTRA_SEG = NP == 2 ? BGS_BOUNCE_EXTRA : 0;  // boundary-free table-driven segments after the first one of an iteration (lut_on)
     __shared__ unsigned int s_hist[HIST_BINS];
+    // outcome counters of the CTA, indexed by winner + 2 (truncated, draw, player 0, player 1), and its env-steps: one
+    // shared-memory atomic each per finished game instead of six accumulator registers per lane
+    __shared__ unsigned int s_outcome[4];
+    __shared__ unsigned long long s_steps;
     __shared__ WarpSlots<NP, M, MAXSRC> s_slots[ROLLOUT_THREADS / 32];
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x < 4) s_outcome[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_steps = 0;
     const G g(grt);
     constexpr bool USE_LUT = G::LUT && NP == 2;
     const bool lut_on = USE_LUT || (NP == 2 && g.lut_rt());
-    __shared__ __align__(16) uint32_t s_lut[NP == 2 ? SEG_LUT_WORDS + SEG_POW_WORDS : 1];
+    __shared__ __align__(16) uint32_t s_lut[NP == 2 ? SEG_LUT_WORDS + SEG_POW_WORDS + 4 : 4];
     if (lut_on) build_seg_tables(g, s_lut);
     __syncthreads();
     WarpSlots<NP, M, MAXSRC>& S = s_slots[threadIdx.x >> 5];
@@ -249,8 +269,6 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     uint64_t plane0[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) plane0[k] = p.plane0[k];
-    uint32_t acc_w0 = 0, acc_w1 = 0, acc_dr = 0, acc_tr = 0;
-    unsigned long long acc_steps = 0;
     uint32_t pool_next = 0, pool_cnt = 0;
     int rq_head = 0, rq_cnt = 0, wq_head = 0, wq_cnt = 0;  // warp-uniform
     bool more = true;                                        // the game counter may still have games
@@ -297,7 +315,7 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     mg.lut = lut_on ? s_lut : nullptr;
     mg.lut_saddr = (uint32_t)__cvta_generic_to_shared(s_lut);
     asm volatile("mov.u32 %0, %0;" : "+r"(mg.lut_saddr));  // opaque: see MoveGen::lut_saddr
-    mg.one = p.one;
+    load_seg_consts(mg, s_lut + (NP == 2 ? SEG_LUT_WORDS + SEG_POW_WORDS : 0), p.one, p.k16);
     // the extra segment pays where pieces bounce often: boards of 5+ columns (8x7: 4.72 -> 4.14 ms per 2 Mi games,
     // 7x5: 2.60 -> 2.31; 6x3: 3.10 -> 3.33, so not there)
     const bool extra_on = lut_on && g.w() >= 5;
@@ -354,11 +372,8 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
                     });
                 if (nx == NEXT_OVER) {
                     gm.write_result(g, out, gidx);
-                    acc_w0 += (gm.win == 0);
-                    acc_w1 += (gm.win == 1);
-                    acc_dr += (gm.win == BGS_WINNER_DRAW);
-                    acc_tr += (gm.win == BGS_WINNER_TRUNCATED);
-                    acc_steps += (unsigned)gm.t;
+                    atomicAdd(&s_outcome[gm.win + 2], 1u);
+                    atomicAdd(&s_steps, (unsigned long long)(unsigned)gm.t);
                     atomicAdd(&s_hist[hist_bin(gm.t)], 1u);
                     over = true;
                 } else {
@@ -416,17 +431,16 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     __syncwarp();
 
     if (p.stats) {
-        const unsigned long long w0 = warp_sum(acc_w0), w1 = warp_sum(acc_w1), dr = warp_sum(acc_dr);
-        const unsigned long long tr = warp_sum(acc_tr), st = warp_sum(acc_steps);
-        if (lane == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long tr = s_outcome[0], dr = s_outcome[1], w0 = s_outcome[2], w1 = s_outcome[3];
             atomicAdd(&p.stats[BGS_STAT_GAMES], w0 + w1 + dr + tr);
             atomicAdd(&p.stats[BGS_STAT_WIN0], w0);
             atomicAdd(&p.stats[BGS_STAT_WIN1], w1);
             atomicAdd(&p.stats[BGS_STAT_DRAWS], dr);
             atomicAdd(&p.stats[BGS_STAT_TRUNCATED], tr);
-            atomicAdd(&p.stats[BGS_STAT_STEPS], st);
+            atomicAdd(&p.stats[BGS_STAT_STEPS], s_steps);
         }
-        __syncthreads();
         for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
             if (s_hist[i]) atomicAdd(&p.stats[BGS_STAT_HIST0 + i], (unsigned long long)s_hist[i]);
     }
@@ -859,7 +873,7 @@ static int bounce_rollout_impl(const int8_t* grid0, const int8_t* start_grid, co
     if (n_games == 0) return BGS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     RolloutParams p;
-    p.one = 1u;
+    p.one = 1u; p.k16 = 16u;
     p.n_games = (uint32_t)n_games; p.game_id0 = game_id0;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     p.max_plies = max_plies;

@@ -321,7 +321,7 @@ struct LaneOut {
 // forward / left / right, no left<->right reversal inside a segment, never backwards; cells off the
 // left / right edge are guard cells (never passable, never a landing cell once masked with the board).
 // ---------------------------------------------------------------------------------------------
-constexpr int SEG_LUT_WORDS = 4 * 256;  // [u][idx], u = 0 unused
+constexpr int SEG_LUT_WORDS = 4 * 256;  // [idx][u], u = 0 unused (seg_lut_slot)
 BGS_HD uint32_t seg_lut_entry(int S, int u, uint32_t idx) {
     if (u < 1 || u > 3) return 0u;
     const int off[8] = {-2, -1, 1, 2, S - 1, S, S + 1, 2 * S};
@@ -349,8 +349,8 @@ BGS_HD uint32_t seg_lut_entry(int S, int u, uint32_t idx) {
     return mask;
 }
 
-// Position of entry (u, idx) in the table a kernel builds: [u][idx] in general, [u][hash of the window bits] for
-// geometries with G::HASH.  `idx` bit k <-> window bit {1, 2, 4, 5, S+2, S+3, S+4, 2S+3}[k].
+// Position of entry (u, idx) in the table a kernel builds: [idx][u] in general, [hash of the window bits][u] for
+// geometries with G::HASH (16 bytes per window: the value bits of the piece are address bits 2 and 3).  `idx` bit k <-> window bit {1, 2, 4, 5, S+2, S+3, S+4, 2S+3}[k].
 BGS_HD uint32_t seg_window_of_idx(int S, uint32_t idx) {
     const int wb[8] = {1, 2, 4, 5, S + 2, S + 3, S + 4, 2 * S + 3};
     uint32_t x = 0;
@@ -375,7 +375,7 @@ BGS_HD uint32_t seg_index(const G& g, uint32_t x) {
 }
 template <class G>
 BGS_HD uint32_t seg_lut_slot(const G& g, int u, uint32_t idx) {
-    return (uint32_t)u * 256u + seg_index(g, seg_window_of_idx(g.s(), idx));
+    return seg_index(g, seg_window_of_idx(g.s(), idx)) * 4u + (uint32_t)u;
 }
 inline bool seg_hash_is_perfect(int S) {  // host-side check of seg_hash_mul(S)
     const uint32_t mul = seg_hash_mul(S), mask = seg_hash_mask(S);
@@ -431,8 +431,9 @@ struct MoveGen {
     uint32_t lut_saddr;   // device: the same table as a 32-bit shared-memory address (kept opaque by the kernel so
                           // that the base stays in a register instead of being rebuilt for every look-up); the
                           // power table (seg_pow_entry) follows it at byte 4096
-    uint32_t one;         // device: always 1, from a kernel parameter -- a multiplier ptxas cannot fold, which keeps
-                          // adds and shifts by constants on the FMA pipe (IMAD)
+    uint32_t one, k16;    // device: always 1 and 16, from kernel parameters -- multipliers ptxas cannot fold, which
+                          // keeps adds and shifts by constants on the FMA pipe (IMAD)
+    B b0r;                // b[0] >> 1 (table-driven segments: the value's bit 0 where the table address wants it)
 
     BGS_HD int rules(const G& g) const { return RULES_ >= 0 ? RULES_ : g.rules; }
 
@@ -456,6 +457,7 @@ struct MoveGen {
         src_left = src;
         probe = prb; found = false; have = false; done = false;
         pending = 0; total = 0; nsrc = 0;
+        if (NP == 2 && sizeof(B) == 8) b0r = b[0] >> 1;
     }
 
     BGS_HD void begin(const G& g, bool prb, bool no_moves) { begin_with(g, sources(g, b, no_moves), prb); }
@@ -488,13 +490,12 @@ struct MoveGen {
             : "=r"(c3) : "r"(plo), "r"(phi), "r"(one));
         uint32_t p1lo, p1hi, lowlo, lowhi;  // 1 << c3 and 8 << c3
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4 + 4096];"
-                     : "=r"(p1lo), "=r"(p1hi), "=r"(lowlo), "=r"(lowhi) : "r"(fma_mad(c3, 16u * one, lut_saddr)));
+                     : "=r"(p1lo), "=r"(p1hi), "=r"(lowlo), "=r"(lowhi) : "r"(fma_mad(c3, k16, lut_saddr)));
         const uint32_t x = (uint32_t)(inter >> c3);
-        const uint32_t v0 = (uint32_t)(b[0] >> c3) & 8u, v1 = (uint32_t)(b[1] >> c3) & 8u;
-        const uint32_t idx = seg_index(g, x);
+        // bit 0 of the value -> address bit 2 (b0r = b[0] >> 1), bit 1 -> address bit 3
+        const uint32_t vv = ((uint32_t)(b0r >> c3) & 4u) | ((uint32_t)(b[1] >> c3) & 8u);
         uint32_t entry;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry)
-                     : "r"(fma_mad(idx, 4u * one, fma_mad(v0, 128u * one, fma_mad(v1, 256u * one, lut_saddr)))));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(fma_mad(seg_index(g, x), k16, vv) + lut_saddr));
         uint32_t ldlo, ldhi;  // the landing set = entry << c3 (not masked with `open`: occS lies inside it, targets are
                               // masked at the piece boundary)
         asm("{\n\t.reg .u64 w;\n\t"
@@ -507,10 +508,9 @@ struct MoveGen {
 #else
         const int c3 = top_bit_minus3((uint64_t)pending);
         const uint32_t x = (uint32_t)(inter >> c3);
-        const uint32_t v0 = (uint32_t)(b[0] >> c3) & 8u, v1 = (uint32_t)(b[1] >> c3) & 8u;
-        const uint32_t idx = seg_index(g, x);
+        const uint32_t u = ((uint32_t)(b[0] >> c3) >> 3 & 1u) | ((uint32_t)(b[1] >> c3) >> 2 & 2u);
         const B low = (B)8 << c3;
-        const B land = (B)lut[(v0 >> 3) * 256 + (v1 >> 3) * 512 + (int)idx] << c3;
+        const B land = (B)lut[seg_index(g, x) * 4u + u] << c3;
 #endif
         unexp &= ~low;
         targets |= land & ~occS;

@@ -325,6 +325,61 @@ bounce_rollout_slots_kernel(const GeoRT grt, const RolloutParams p) {
     for (;;) {
         // ---- (1) lanes without work take ready slots
         const unsigned need = __ballot_sync(0xffffffffu, !has_work);
+#ifndef BGS_BOUNCE_COOP
+#define BGS_BOUNCE_COOP 1
+#endif
+        // ---- (0) cooperative tail.  Once the game counter is exhausted a warp ends up with a handful of long games,
+        // each a chain of plies whose move generation (6 pieces x ~2.5 segments) runs on ONE lane: ~3.5 us per ply,
+        // and the launch waits for the longest chain.  With at most 32 / MAXSRC games left (and nothing in flight) the
+        // movable pieces of a position are dealt to MAXSRC consecutive lanes instead -- lane j generates the moves of
+        // the j-th piece (MoveGen on a one-piece source set, its targets into T[j]) -- all lanes run to completion,
+        // the totals are summed over the lane group, and the ordinary transition pass follows.  Run-time geometries
+        // only: 2 Mi games on 6x3 / 8x7 / 7x5 boards 3.28 / 3.95 / 2.17 -> 2.89 / 3.83 / 2.14 ms, values up to 7 on 9x6
+        // 6.37 -> 6.11 ms; on the default board (compile-time geometry) the drain of a warp's last 64 games is spread
+        // over 6..64 live slots most of the time and the extra code costs what the last five games gain (7.50 -> 7.60 ms).
+        constexpr int COOP_SLOTS = 32 / MAXSRC;
+        constexpr bool COOP = BGS_BOUNCE_COOP && !(G::LUT && NP == 2);
+        if (COOP && !more && need == 0xffffffffu && wq_cnt == 0 && rq_cnt > 0 && rq_cnt <= COOP_SLOTS) {
+            const int grp = (int)lane / MAXSRC, j = (int)lane - grp * MAXSRC;
+            const int nsl = rq_cnt;
+            bool running = false;
+            int cslot = 0;
+            uint32_t cme = 0;
+            if (grp < nsl) {
+                cslot = S.rq[(rq_head + grp) & 63];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) mg.b[i] = S.b[i][cslot];
+                cme = S.meta[cslot];
+                uint64_t sj = S.src[cslot];
+                for (int q = 0; q < j; ++q) sj &= sj - 1ull;
+                sj &= ~sj + 1ull;  // the j-th movable piece, or nothing
+                mg.begin_with(g, sj, (cme & META_PROBE) != 0u);
+                mg.nsrc = j;
+                running = true;
+            }
+            rq_head = (rq_head + nsl) & 63;
+            rq_cnt = 0;
+            while (__any_sync(0xffffffffu, running)) {
+                if (running) {
+                    mg.iter(g, &S.T[0][cslot], M);
+                    running = !mg.done;
+                }
+            }
+            int tot = grp < nsl ? mg.total : 0;
+            int sum = tot;
+#pragma unroll
+            for (int k = 1; k < MAXSRC; ++k) {
+                const int o = __shfl_down_sync(0xffffffffu, tot, k);
+                if (j + k < MAXSRC) sum += o;
+            }
+            if (grp < nsl && j == 0) {
+                S.meta[cslot] = cme | ((uint32_t)sum << META_TOTAL_SHIFT) | (sum ? META_FOUND : 0u);
+                S.wq[(wq_head + wq_cnt + grp) & 63] = (uint8_t)cslot;
+            }
+            wq_cnt += nsl;
+            __syncwarp();
+            continue;
+        }
         if (need != 0u && rq_cnt > 0) {
             const int rank = __popc(need & lt);
             if (!has_work && rank < rq_cnt) {

@@ -8,7 +8,11 @@ sys.path.insert(0, os.path.join(ROOT, "board-game-simulator-python_b200"))
 
 import torch  # noqa: E402
 
+from simulator import _native as N  # noqa: E402
 from simulator import batch  # noqa: E402
+
+if len(sys.argv) > 2 and sys.argv[1] == "--lib":  # time another build of libbgs_b200.so (kernel experiments)
+    N.LIB_PATH = os.path.abspath(sys.argv[2])
 
 for cfg, n in (((6, 7, 4), 2**20), ((8, 9, 5), 2**18), ((10, 12, 6), 2**17)):
     H, W, K = cfg

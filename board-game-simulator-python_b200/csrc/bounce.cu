@@ -53,7 +53,7 @@ struct RolloutParams {
 
 constexpr int ROLLOUT_THREADS = 128;
 
-// The tables of the table-driven segment (MoveGen::lut_segment) in shared memory: landing sets [value][window hash],
+// The tables of the table-driven segment (MoveGen::lut_segment) in shared memory: landing sets [window hash][value],
 // then the power table at byte 4096.
 template <class G>
 __device__ __forceinline__ void build_seg_tables(const G& g, uint32_t* s_lut) {
@@ -101,7 +101,7 @@ bounce_rollout_lane_kernel(const GeoRTb<typename G::bits> grt, const RolloutPara
     constexpr bool USE_LUT = G::LUT && NP == 2;                  // compile-time: the default board
     constexpr bool MAY_LUT = NP == 2 && sizeof(B) == 8;          // run-time: any small board with a guard column
     const bool lut_on = USE_LUT || (MAY_LUT && g.lut_rt());
-    __shared__ __align__(16) uint32_t s_lut[MAY_LUT ? SEG_LUT_WORDS + SEG_POW_WORDS + 4 : 4];  // landing sets of a segment, [value][passable neighbours]; the power table
+    __shared__ __align__(16) uint32_t s_lut[MAY_LUT ? SEG_LUT_WORDS + SEG_POW_WORDS + 4 : 4];  // landing sets of a segment, [passable neighbours][value]; the power table; MoveGen::one / k16
     if (lut_on) {
         build_seg_tables(g, s_lut);
         __syncthreads();

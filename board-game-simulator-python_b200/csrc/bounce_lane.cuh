@@ -350,7 +350,8 @@ BGS_HD uint32_t seg_lut_entry(int S, int u, uint32_t idx) {
 }
 
 // Position of entry (u, idx) in the table a kernel builds: [idx][u] in general, [hash of the window bits][u] for
-// geometries with G::HASH (16 bytes per window: the value bits of the piece are address bits 2 and 3).  `idx` bit k <-> window bit {1, 2, 4, 5, S+2, S+3, S+4, 2S+3}[k].
+// geometries with G::HASH (16 bytes per window: the value bits of the piece are address bits 2 and 3).
+// `idx` bit k <-> window bit {1, 2, 4, 5, S+2, S+3, S+4, 2S+3}[k].
 BGS_HD uint32_t seg_window_of_idx(int S, uint32_t idx) {
     const int wb[8] = {1, 2, 4, 5, S + 2, S + 3, S + 4, 2 * S + 3};
     uint32_t x = 0;
@@ -427,7 +428,7 @@ struct MoveGen {
     int total, nsrc;
     bool probe;  // only "does the mover have any action?" (the blocked test): `found` is the answer, T / total are not used
     bool found, have, done;
-    const uint32_t* lut;  // seg_lut_entry table [4][256] when G::LUT (shared memory in the kernel)
+    const uint32_t* lut;  // seg_lut_entry table [256][4] (seg_lut_slot) when G::LUT (shared memory in the kernel)
     uint32_t lut_saddr;   // device: the same table as a 32-bit shared-memory address (kept opaque by the kernel so
                           // that the base stays in a register instead of being rebuilt for every look-up); the
                           // power table (seg_pow_entry) follows it at byte 4096
@@ -467,17 +468,19 @@ struct MoveGen {
     // also calls it on its own: a second segment for the lanes that still have a pending cell, without paying for
     // another piece-boundary block (37 % of the pieces need one segment, 23 % two, the rest up to twelve).
     BGS_HD void lut_segment(const G& g) {
-        // The kernel is bound by the ALU pipe (logic, shifts, compares, adds: 80 % busy where 81 % is its ceiling)
-        // while the FMA pipe (integer multiply-add) idles at 15 %, so the segment is written for few instructions
-        // on the former: 14 instead of 28.
+        // The rollout kernel was bound by the ALU pipe (logic, shifts, compares, adds: 80 % busy where 81 % is its
+        // ceiling) while the FMA pipe (integer multiply-add) idled at 15 %, so the segment is written for few
+        // instructions on the former: 15 of its 28, where the first form had 28 of 34.
         //  * The HIGHEST pending cell is expanded (the closure does not depend on the order): FLO finds that bit
-        //    directly -- no isolation of the lowest bit, no select between the halves (the second FLO is predicated).
+        //    directly -- no isolation of the lowest bit (a 64-bit negate and two ANDs).
         //  * Everything is taken from words shifted by c - 3: the window of passable cells (bit 3 = c) and the value
-        //    bits of c (bit 3 of the shifted planes; they select the table's quarter through two multiply-adds).
+        //    bits of c, which land on bits 2 and 3 -- the table is laid out [window][value], so they ARE address bits
+        //    and the value itself is never extracted.
         //  * 1 << (c - 3) and the bit of c itself come from a 64-entry table (one 128-bit load), and the landing set
         //    is entry * 2^(c-3) as a wide multiply instead of a 64-bit shift.
         //  * unexp (pieces not expanded yet) replaces the set of expanded cells: c leaves pending because it is no
         //    longer in unexp, one three-input logic operation per half.
+        //  * The adds and the table strides are multiply-adds with opaque multipliers (one, k16).
 #if defined(__CUDA_ARCH__)
         const uint32_t plo = (uint32_t)pending, phi = (uint32_t)(pending >> 32);
         uint32_t c3;  // c - 3, c >= S >= 3: no piece in row 0

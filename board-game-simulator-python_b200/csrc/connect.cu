@@ -2627,6 +2627,15 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
             int per_sm = 0;
             BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EXPORT_THREADS, 0));
             if (per_sm < 1) per_sm = 1;
+            // TWO resident CTAs per SM, not the five that fit: the kernel is bound by how well its writes stream into
+            // HBM, and the fewer warps write at the same time, the closer together their addresses are -- resident
+            // CTAs per SM 1 / 2 / 3 / 5: 8x9 0.376 / 0.280 / 0.294 / 0.313 ms per 256 Ki games, 10x12 0.414 / 0.376 /
+            // 0.390 / 0.403 ms per 128 Ki games (more registers per thread, prefetching the next group's
+            // trajectories or a bulk-copy copy-out changed nothing beyond that)
+#ifndef BGS_TRAJ_MAX_PER_SM
+#define BGS_TRAJ_MAX_PER_SM 2
+#endif
+            if (per_sm > BGS_TRAJ_MAX_PER_SM) per_sm = BGS_TRAJ_MAX_PER_SM;
             unsigned long long blocks = (n_games + 8ull * gpw - 1ull) / (8ull * gpw);
             const unsigned long long cap = (unsigned long long)sm_count() * per_sm;
             if (blocks > cap) blocks = cap;
@@ -2642,6 +2651,8 @@ extern "C" int bgs_connect_trajectory_grids(int H, int W, uint64_t n_games, cons
         int per_sm = 0;
         BGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TRAJW_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
+        // (no cap as in the cell kernels: this one is instruction-bound -- 2 / 3 / 4 / 6 resident CTAs per SM:
+        // 1.06 / 0.76 / 0.64 / 0.50 ms against 0.44 ms with all nine)
         unsigned long long blocks = (n_games + 2ull * (TRAJW_THREADS / 32) - 1ull) / (2ull * (TRAJW_THREADS / 32));
         const unsigned long long cap = (unsigned long long)sm_count() * per_sm;
         if (blocks > cap) blocks = cap;
@@ -2733,6 +2744,8 @@ static int step_impl(int H, int W, int K, uint64_t n, const int8_t* grid, const 
     if (smem > 48 * 1024)  // large tiles: opt in to the large carve-out
         BGS_CUDA_TRY(cudaFuncSetAttribute(connect_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned long long blocks = (n + STEP_THREADS - 1) / STEP_THREADS;
+    // (unlike the per-ply grid kernels this one does not gain from fewer resident CTAs: 2 / 3 / 4 per SM 0.236 / 0.181 /
+    // 0.157 ms per 4 Mi 6x7 states against 0.155 ms with 8; neither do the export / expansion kernels)
     const unsigned long long cap = (unsigned long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     connect_step_kernel<<<(unsigned)blocks, STEP_THREADS, smem, (cudaStream_t)stream_>>>(

@@ -718,6 +718,48 @@ def test_full_size_launch_equals_oracle(oracle):
         np.testing.assert_array_equal(winner[k * chunk:(k + 1) * chunk], parts[k]["winner"])
 
 
+@pytest.mark.parametrize("cfg", [(8, 9, 5), (10, 12, 6)])
+def test_line_kernels_many_games_per_lane_equal_oracle(oracle, cfg):
+    """BASELINE.json configs[3] boards with MANY games per lane: the line kernels clear only part of a lane's line
+    words when a game starts (diagonals shorter than K keep the bits of earlier games -- LineGeo::per_game_reset),
+    and a launch of a few thousand games gives every lane two games at most.  Here every lane of the resident grid
+    plays ~8 games in a row, plain and with the fused export: statistics and every game's length / winner equal the
+    oracle's over the same global ids, trajectories and final grids on a slice."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    from simulator import batch
+
+    n, seed, gid0 = 5 * 2**18 + 77, 977, 7 * 2**34
+    chunk = 2**16
+    oracle.lib()
+    bounds = [(a, min(chunk, n - a)) for a in range(0, n, chunk)]
+
+    def part(b):
+        a, cnt = b
+        return oracle.connect_rollout(*cfg, cnt, gid0=gid0 + a, seed=seed, want_actions=a == 0, want_grid=a == 0)
+
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        parts = list(ex.map(part, bounds))
+    want_stats = np.sum([p["stats"] for p in parts], axis=0)
+    want_len = np.concatenate([p["length"] for p in parts])
+    want_win = np.concatenate([p["winner"] for p in parts])
+    for kw in (dict(), dict(actions=True, final_grid=True, reward=True)):
+        res = batch.connect_rollout(cfg, n, seed, gid0, per_game=True, **kw)
+        np.testing.assert_array_equal(res.stats.cpu().numpy(), want_stats)
+        np.testing.assert_array_equal(res.length.cpu().numpy(), want_len)
+        np.testing.assert_array_equal(res.winner.cpu().numpy(), want_win)
+        if kw:
+            np.testing.assert_array_equal(res.actions[:chunk].cpu().numpy(), parts[0]["actions"])
+            np.testing.assert_array_equal(res.final_grid[:chunk].cpu().numpy(), parts[0]["final_grid"])
+            # a later slice, replayed: lanes are several games into the launch by then
+            lo = n - chunk
+            bad, first = oracle.connect_replay(
+                *cfg, res.actions[lo:].cpu().numpy(), res.length[lo:].cpu().numpy(), res.winner[lo:].cpu().numpy(),
+                res.final_grid[lo:].cpu().numpy(), res.reward[lo:].cpu().numpy())
+            assert (bad, first) == (0, -1)
+
+
 @pytest.mark.parametrize("cfg", [(6, 7, 4), (4, 5, 3), (8, 9, 5)])
 def test_dense_host_results_equal_oracle(oracle, cfg):
     """HostRollout(packed="dense"): several games per 16-bit word in base S (6x7x4: 3 games, 5.33 bits each)."""
